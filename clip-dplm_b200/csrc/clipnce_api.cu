@@ -1,0 +1,371 @@
+// C-ABI entry points (include/clipnce.h): argument validation, workspace carving, TMA descriptor
+// construction and kernel launches.  No torch types, no host synchronisation, no allocation.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/clipnce.h"
+#include "kernels_aux.cuh"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(CLIPNCE_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));     \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t elem_size(int dtype) { return dtype == CLIPNCE_BF16 ? 2 : 4; }
+
+bool tc_eligible(int dtype, int64_t d, float scale, int flags) {
+  return dtype == CLIPNCE_BF16 && !(flags & CLIPNCE_FLAG_FORCE_EXACT) && d >= 8 && d % 8 == 0 && d <= 768 &&
+         scale > 0.f && 2.f * scale <= 86.f;
+}
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+std::mutex g_mu;
+EncodeTiledFn g_encode = nullptr;
+bool g_attr_done[3] = {false, false, false};
+
+int get_encode(EncodeTiledFn* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+      return fail(CLIPNCE_ECUDA, "cuTensorMapEncodeTiled not available from this driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = g_encode;
+  return 0;
+}
+
+// bf16 row-major [outer, inner] (row stride ld elements), box {64, box_rows}, 128-byte swizzle.
+int make_tmap(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
+  EncodeTiledFn enc;
+  int rc = get_encode(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CLIPNCE_ECUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld", (int)r, (long long)outer,
+                (long long)inner, (long long)ld);
+  return 0;
+}
+
+int check_device_sm100() {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  int major = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(CLIPNCE_EUNSUPPORTED, "clipnce needs an sm_100 (B200) device, found sm_%d", major * 10);
+  return 0;
+}
+
+template <int MODE, int BLOCK_I>
+int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tyt, tc::Params p,
+              int grid, cudaStream_t st) {
+  auto kern = tc::clip_tc_kernel<MODE, BLOCK_I>;
+  const int fixed = tc::smem_bytes(MODE, BLOCK_I, p.nkc, 0);
+  int stages = (tc::SMEM_LIMIT - fixed) / tc::STAGE_BYTES;
+  if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+  if (stages < 2) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for a TMA ring", p.d);
+  p.num_stages = stages;
+  const int smem = tc::smem_bytes(MODE, BLOCK_I, p.nkc, stages);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_attr_done[attr_slot]) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+      g_attr_done[attr_slot] = true;
+    }
+  }
+  kern<<<grid, tc::NUM_THREADS, smem, st>>>(tx, ty, tyt, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int fwd_block_i(int64_t n_rows, int64_t d) { return (d <= 512 && n_rows >= 128 * 148) ? 128 : 64; }
+
+struct SimtFwdWs {
+  float *row_pm, *row_pl, *col_pm, *col_pl;
+  int64_t n_it, n_jt;
+  size_t bytes;
+};
+SimtFwdWs simt_fwd_ws(void* ws, int64_t n_rows, int64_t n_cols) {
+  SimtFwdWs w;
+  w.n_it = ceil_div(n_rows, simt::TILE);
+  w.n_jt = ceil_div(n_cols, simt::TILE);
+  float* f = reinterpret_cast<float*>(ws);
+  w.row_pm = f;
+  w.row_pl = w.row_pm + w.n_jt * n_rows;
+  w.col_pm = w.row_pl + w.n_jt * n_rows;
+  w.col_pl = w.col_pm + w.n_it * n_cols;
+  w.bytes = sizeof(float) * 2 * (size_t)(w.n_jt * n_rows + w.n_it * n_cols);
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int clipnce_version(void) { return CLIPNCE_VERSION; }
+const char* clipnce_last_error(void) { return g_err.c_str(); }
+
+int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags) {
+  return tc_eligible(dtype, d, scale, flags) ? 1 : 0;
+}
+
+int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, int flags, size_t* out) {
+  if (!out || n_rows < 1 || n_cols < 1 || d < 1) return fail(CLIPNCE_EINVAL, "workspace_bytes: bad shape");
+  if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "workspace_bytes: bad dtype %d", dtype);
+  (void)flags;
+  // tensor-core path (worst case over BLOCK_I choices) and exact path, forward and backward
+  size_t tc_fwd = sizeof(float) * 2 * (size_t)ceil_div(n_rows, 64) * (size_t)round_up(n_cols, 32);
+  size_t tc_bwd = sizeof(float) * (size_t)ceil_div(n_rows, 64);
+  SimtFwdWs w = simt_fwd_ws(nullptr, n_rows, n_cols);
+  size_t simt_bwd = sizeof(float) * (size_t)ceil_div(n_rows, simt::TILE);
+  size_t m = tc_fwd;
+  if (tc_bwd > m) m = tc_bwd;
+  if (w.bytes > m) m = w.bytes;
+  if (simt_bwd > m) m = simt_bwd;
+  *out = m + 256;
+  return 0;
+}
+
+int clipnce_normalize(const void* x, int in_dtype, int64_t n, int64_t d, void* x_hat, void* x_hat_t, int64_t ld_t,
+                      int out_dtype, float* rinv, void* stream) {
+  if (!x || !x_hat || !rinv || n < 1 || d < 1) return fail(CLIPNCE_EINVAL, "normalize: null pointer or empty shape");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "normalize: bad dtype");
+  if (d > (1 << 20)) return fail(CLIPNCE_EINVAL, "normalize: d too large");
+  cudaStream_t st = as_stream(stream);
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
+  const int di = (int)d;
+  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16)
+    aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, (__nv_bfloat16*)x_hat, rinv);
+  else if (in_dtype == CLIPNCE_F32 && out_dtype == CLIPNCE_BF16)
+    aux::normalize_rows<<<grid, block, 0, st>>>((const float*)x, n, di, (__nv_bfloat16*)x_hat, rinv);
+  else if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_F32)
+    aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, (float*)x_hat, rinv);
+  else
+    aux::normalize_rows<<<grid, block, 0, st>>>((const float*)x, n, di, (float*)x_hat, rinv);
+  CUDA_TRY(cudaGetLastError());
+  if (x_hat_t) return clipnce_transpose(x_hat, n, d, x_hat_t, ld_t, out_dtype, stream);
+  return 0;
+}
+
+int clipnce_transpose(const void* x_hat, int64_t n, int64_t d, void* x_hat_t, int64_t ld_t, int dtype, void* stream) {
+  if (!x_hat || !x_hat_t || n < 1 || d < 1 || ld_t < n) return fail(CLIPNCE_EINVAL, "transpose: bad argument");
+  if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "transpose: bad dtype");
+  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(d, 32)), block(32, 8);
+  if (dtype == CLIPNCE_BF16)
+    aux::transpose_tiled<<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)x_hat, n, (int)d,
+                                                                (__nv_bfloat16*)x_hat_t, ld_t);
+  else
+    aux::transpose_tiled<<<grid, block, 0, as_stream(stream)>>>((const float*)x_hat, n, (int)d, (float*)x_hat_t, ld_t);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset,
+                    float scale, int dtype, int flags, float* row_lse, float* col_m, float* col_l, float* diag,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x_hat || !y_hat || !row_lse || !col_m || !col_l || !diag || !workspace)
+    return fail(CLIPNCE_EINVAL, "forward: null pointer");
+  if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
+    return fail(CLIPNCE_EINVAL, "forward: bad shape");
+  if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "forward: bad dtype %d", dtype);
+  if (!std::isfinite(scale)) return fail(CLIPNCE_EINVAL, "forward: scale is not finite");
+  cudaStream_t st = as_stream(stream);
+  int rc = check_device_sm100();
+  if (rc) return rc;
+
+  if (tc_eligible(dtype, d, scale, flags)) {
+    if (!aligned16(x_hat) || !aligned16(y_hat)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
+    const int bi = fwd_block_i(n_rows, d);
+    const int64_t n_ib = ceil_div(n_rows, bi);
+    const int64_t col_ld = round_up(n_cols, 32);
+    const size_t need = sizeof(float) * 2 * (size_t)n_ib * (size_t)col_ld;
+    if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
+    CUtensorMap tx, ty;
+    if ((rc = make_tmap(&tx, x_hat, d, n_rows, d, bi))) return rc;
+    if ((rc = make_tmap(&ty, y_hat, d, n_cols, d, tc::BLOCK_J))) return rc;
+    tc::Params p;
+    memset(&p, 0, sizeof p);
+    p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
+    p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
+    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
+    p.row_lse = row_lse; p.col_part = reinterpret_cast<float*>(workspace); p.col_ld = col_ld; p.diag = diag;
+    if (bi == 128) rc = launch_tc<0, 128>(0, tx, ty, ty, p, (int)n_ib, st);
+    else           rc = launch_tc<0, 64>(1, tx, ty, ty, p, (int)n_ib, st);
+    if (rc) return rc;
+    aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, (int)(2 * n_ib), col_ld,
+                                                                                n_cols, scale, col_m, col_l);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  // exact CUDA-core path
+  SimtFwdWs w = simt_fwd_ws(workspace, n_rows, n_cols);
+  if (workspace_bytes < w.bytes) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, w.bytes);
+  if (w.n_it > 65535) return fail(CLIPNCE_EUNSUPPORTED, "forward (exact path): n_rows too large");
+  dim3 grid((unsigned)w.n_jt, (unsigned)w.n_it);
+  if (dtype == CLIPNCE_BF16)
+    simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x_hat, (const __nv_bfloat16*)y_hat, n_rows,
+                                                     n_cols, (int)d, diag_offset, scale, w.row_pm, w.row_pl, w.col_pm,
+                                                     w.col_pl, diag);
+  else
+    simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const float*)x_hat, (const float*)y_hat, n_rows, n_cols, (int)d,
+                                                     diag_offset, scale, w.row_pm, w.row_pl, w.col_pm, w.col_pl, diag);
+  CUDA_TRY(cudaGetLastError());
+  aux::reduce_ml_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(w.row_pm, w.row_pl, (int)w.n_jt, n_rows,
+                                                                             n_rows, 0, row_lse, nullptr);
+  aux::reduce_ml_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(w.col_pm, w.col_pl, (int)w.n_it, n_cols,
+                                                                             n_cols, 1, col_m, col_l);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_backward(const void* x_hat, const void* y_hat, const void* y_hat_t, int64_t ld_t, int64_t n_rows,
+                     int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* log_u,
+                     const float* log_v, float diag_w, float grad_out, int dtype, int flags, float* dx_hat,
+                     float* d_scale_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x_hat || !y_hat || !log_u || !dx_hat || !workspace) return fail(CLIPNCE_EINVAL, "backward: null pointer");
+  if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
+    return fail(CLIPNCE_EINVAL, "backward: bad shape");
+  if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "backward: bad dtype %d", dtype);
+  if (!std::isfinite(scale)) return fail(CLIPNCE_EINVAL, "backward: scale is not finite");
+  cudaStream_t st = as_stream(stream);
+  int rc = check_device_sm100();
+  if (rc) return rc;
+
+  if (tc_eligible(dtype, d, scale, flags)) {
+    if (!y_hat_t) return fail(CLIPNCE_EINVAL, "backward: the tensor-core path needs y_hat_t");
+    if (ld_t < n_cols || ld_t % 8 != 0) return fail(CLIPNCE_EINVAL, "backward: ld_t must be >= n_cols and a multiple of 8");
+    if (!aligned16(x_hat) || !aligned16(y_hat) || !aligned16(y_hat_t))
+      return fail(CLIPNCE_EINVAL, "backward: operands must be 16-byte aligned");
+    const int64_t n_ib = ceil_div(n_rows, 64);
+    const size_t need = sizeof(float) * (size_t)n_ib;
+    if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
+    CUtensorMap tx, ty, tyt;
+    if ((rc = make_tmap(&tx, x_hat, d, n_rows, d, 64))) return rc;
+    if ((rc = make_tmap(&ty, y_hat, d, n_cols, d, tc::BLOCK_J))) return rc;
+    if ((rc = make_tmap(&tyt, y_hat_t, n_cols, d, ld_t, 128))) return rc;
+    tc::Params p;
+    memset(&p, 0, sizeof p);
+    p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
+    p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
+    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
+    p.log_u = log_u; p.log_v = log_v; p.diag_w = diag_w; p.out_scale = grad_out * scale;
+    p.dx = dx_hat; p.ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
+    if ((rc = launch_tc<1, 64>(2, tx, ty, tyt, p, (int)n_ib, st))) return rc;
+    if (d_scale_sum) {
+      aux::reduce_scalar_partials<<<1, 32, 0, st>>>(p.ds_part, (int)n_ib, grad_out, d_scale_sum);
+      CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+  }
+
+  const int64_t n_it = ceil_div(n_rows, simt::TILE);
+  const size_t need = sizeof(float) * (size_t)n_it;
+  if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
+  if (n_it > 65535) return fail(CLIPNCE_EUNSUPPORTED, "backward (exact path): n_rows too large");
+  float* ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
+  dim3 grid((unsigned)ceil_div(d, simt::TILE), (unsigned)n_it);
+  if (dtype == CLIPNCE_BF16)
+    simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x_hat, (const __nv_bfloat16*)y_hat, n_rows,
+                                                    n_cols, (int)d, diag_offset, scale, log_u, log_v, diag_w,
+                                                    grad_out * scale, dx_hat, ds_part);
+  else
+    simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const float*)x_hat, (const float*)y_hat, n_rows, n_cols, (int)d,
+                                                    diag_offset, scale, log_u, log_v, diag_w, grad_out * scale, dx_hat,
+                                                    ds_part);
+  CUDA_TRY(cudaGetLastError());
+  if (d_scale_sum) {
+    aux::reduce_scalar_partials<<<1, 32, 0, st>>>(ds_part, (int)n_it, grad_out, d_scale_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int clipnce_log_weights(const float* lse, int64_t n, float log_coef, float* out, void* stream) {
+  if (!lse || !out || n < 1) return fail(CLIPNCE_EINVAL, "log_weights: bad argument");
+  aux::log_weights<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(lse, n, log_coef, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_combine_lse(const float* m, const float* l, int64_t n, float* lse, void* stream) {
+  if (!m || !l || !lse || n < 1) return fail(CLIPNCE_EINVAL, "combine_lse: bad argument");
+  aux::combine_lse<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(m, l, n, lse);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_normalize_backward(const void* x, int in_dtype, const float* rinv, const float* dx_hat,
+                               const float* grad_scale, int64_t n, int64_t d, void* dx, int out_dtype, void* stream) {
+  if (!x || !rinv || !dx_hat || !dx || n < 1 || d < 1) return fail(CLIPNCE_EINVAL, "normalize_backward: bad argument");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "normalize_backward: bad dtype");
+  cudaStream_t st = as_stream(stream);
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
+  const int di = (int)d;
+  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16)
+    aux::normalize_rows_bwd<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, rinv, dx_hat, grad_scale, n, di, (__nv_bfloat16*)dx);
+  else if (in_dtype == CLIPNCE_F32 && out_dtype == CLIPNCE_BF16)
+    aux::normalize_rows_bwd<<<grid, block, 0, st>>>((const float*)x, rinv, dx_hat, grad_scale, n, di, (__nv_bfloat16*)dx);
+  else if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_F32)
+    aux::normalize_rows_bwd<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, rinv, dx_hat, grad_scale, n, di, (float*)dx);
+  else
+    aux::normalize_rows_bwd<<<grid, block, 0, st>>>((const float*)x, rinv, dx_hat, grad_scale, n, di, (float*)dx);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_loss(const float* row_lse, const float* col_lse, const float* diag, int64_t n_rows, int64_t diag_offset,
+                 int64_t n_global, int symmetric, float* loss, void* stream) {
+  if (!row_lse || !diag || !loss || n_rows < 1 || n_global < 1) return fail(CLIPNCE_EINVAL, "loss: bad argument");
+  if (symmetric && !col_lse) return fail(CLIPNCE_EINVAL, "loss: symmetric loss needs col_lse");
+  const double inv = 1.0 / ((symmetric ? 2.0 : 1.0) * (double)n_global);
+  aux::loss_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_lse, col_lse, diag, n_rows, diag_offset, inv, symmetric, loss);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

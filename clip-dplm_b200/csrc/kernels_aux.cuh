@@ -1,0 +1,161 @@
+// HBM-bound helper kernels around the two contraction kernels: normalise (+ its backward),
+// transpose, LSE plumbing on [N] vectors, deterministic reductions of per-CTA partials.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace aux {
+
+template <typename T> __device__ __forceinline__ float ld_f(const T* p);
+template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
+template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr float kNormEps = 1e-12f;  // F.normalize default eps
+
+// One warp per row: x_hat = x / max(|x|, eps)   (old/clip.py:63-64).
+template <typename TI, typename TO>
+__global__ void normalize_rows(const TI* __restrict__ x, int64_t n, int d, TO* __restrict__ xh, float* __restrict__ rinv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const TI* xr = x + row * d;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    float v = ld_f(xr + k);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), kNormEps);
+  TO* o = xh + row * d;
+  for (int k = lane; k < d; k += 32) st_f(o + k, ld_f(xr + k) / denom);
+  if (lane == 0) rinv[row] = 1.f / denom;
+}
+
+// Tiled transpose [n,d] -> [d,ld_t]; padding columns n..ld_t are left untouched (TMA never reads
+// them: the tensor map's extent is n).
+template <typename T>
+__global__ void transpose_tiled(const T* __restrict__ in, int64_t n, int d, T* __restrict__ out, int64_t ld_t) {
+  __shared__ T tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int64_t rr = r0 + r;
+    int cc = c0 + threadIdx.x;
+    if (rr < n && cc < d) tile[r][threadIdx.x] = in[rr * d + cc];
+  }
+  __syncthreads();
+  for (int c = threadIdx.y; c < 32; c += blockDim.y) {
+    int cc = c0 + c;
+    int64_t rr = r0 + threadIdx.x;
+    if (rr < n && cc < d) out[(int64_t)cc * ld_t + rr] = tile[threadIdx.x][c];
+  }
+}
+
+// dx_i = rinv_i (g_i - xhat_i (xhat_i . g_i));  clamped rows (|x| < eps): dx_i = g_i * rinv_i.
+template <typename TI, typename TO>
+__global__ void normalize_rows_bwd(const TI* __restrict__ x, const float* __restrict__ rinv,
+                                   const float* __restrict__ g, const float* __restrict__ grad_scale, int64_t n, int d,
+                                   TO* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float ri = rinv[row];
+  const float gs = grad_scale ? grad_scale[0] : 1.f;
+  const TI* xr = x + row * d;
+  const float* gr = g + row * d;
+  TO* o = dx + row * d;
+  const bool clamped = ri >= 0.5f / kNormEps;
+  float dot = 0.f;
+  if (!clamped) {
+    for (int k = lane; k < d; k += 32) dot = fmaf(ld_f(xr + k) * ri, gr[k], dot);
+    dot = warp_sum(dot);
+  }
+  for (int k = lane; k < d; k += 32) {
+    float xh = ld_f(xr + k) * ri;
+    st_f(o + k, (gr[k] - xh * dot) * (ri * gs));
+  }
+}
+
+__global__ void log_weights(const float* __restrict__ lse, int64_t n, float log_coef, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = log_coef - lse[i];
+}
+
+__global__ void combine_lse(const float* __restrict__ m, const float* __restrict__ l, int64_t n, float* __restrict__ lse) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lse[i] = m[i] + logf(l[i]);
+}
+
+// Deterministic single-block loss reduction (double accumulators, fixed order).
+__global__ void loss_reduce(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                            const float* __restrict__ diag, int64_t n_rows, int64_t diag_offset, double inv_denom,
+                            int symmetric, float* __restrict__ loss) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n_rows; i += blockDim.x) {
+    double dg = diag[i];
+    acc += (double)row_lse[i] - dg;
+    if (symmetric) acc += (double)col_lse[i + diag_offset] - dg;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = (float)(sh[0] * inv_denom);
+}
+
+// col_l[j] = sum_p part[p][j] (fixed order), col_m[j] = shift.   Used by the tensor-core forward
+// whose partials all share the fixed shift s.
+__global__ void reduce_col_partials(const float* __restrict__ part, int n_part, int64_t ld, int64_t n_cols, float shift,
+                                    float* __restrict__ col_m, float* __restrict__ col_l) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cols) return;
+  float acc = 0.f;
+  for (int p = 0; p < n_part; ++p) acc += part[(int64_t)p * ld + j];
+  col_m[j] = shift;
+  col_l[j] = acc;
+}
+
+// Combine (m,l) partial pairs: out over `n` entries, `n_part` partials with leading dimension ld.
+// mode 0: write lse = M + log L;  mode 1: write (M, L).
+__global__ void reduce_ml_partials(const float* __restrict__ pm, const float* __restrict__ pl, int n_part, int64_t ld,
+                                   int64_t n, int mode, float* __restrict__ out0, float* __restrict__ out1) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float M = -INFINITY;
+  for (int p = 0; p < n_part; ++p) M = fmaxf(M, pm[(int64_t)p * ld + i]);
+  float L = 0.f;
+  for (int p = 0; p < n_part; ++p) {
+    float m = pm[(int64_t)p * ld + i];
+    if (m > -INFINITY) L += pl[(int64_t)p * ld + i] * expf(m - M);
+  }
+  if (mode == 0) {
+    out0[i] = M + logf(L);
+  } else {
+    out0[i] = M;
+    out1[i] = L;
+  }
+}
+
+// *dst += coef * sum_p part[p]   (single thread, fixed order -> deterministic).
+__global__ void reduce_scalar_partials(const float* __restrict__ part, int n_part, float coef, float* __restrict__ dst) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double acc = 0.0;
+    for (int p = 0; p < n_part; ++p) acc += (double)part[p];
+    dst[0] += (float)(acc * (double)coef);
+  }
+}
+
+}  // namespace aux

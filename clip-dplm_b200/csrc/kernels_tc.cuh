@@ -1,0 +1,407 @@
+// tcgen05 / TMEM / TMA kernels for the contrastive hot path (sm_100a only).
+//
+// One kernel template, two modes, both sweeping the logits S = s * Xhat Yhat^T tile by tile without
+// ever writing S (or G) to HBM:
+//
+//   MODE 0  forward statistics   row sums  sum_j exp(S_ij - s),  column partial sums, diagonal
+//   MODE 1  backward, one side   dXhat = s * G Yhat,  G_ij = exp(S_ij - s)(u_i + v_j) - w [j == i+off]
+//
+// Orientation.  A CTA owns BLOCK_I rows of Xhat (resident in shared memory for the whole sweep) and
+// streams 128-row tiles of Yhat.  The logits tile is computed TRANSPOSED,
+//       St[j (128 TMEM lanes), i (BLOCK_I TMEM columns)] = Yhat_J . Xhat_I^T        (UMMA 128 x BLOCK_I x 16)
+// so that epilogue thread <-> lane <-> column j of S:  per-column quantities (v_j, the column
+// partial sum) are thread-local scalars, per-row quantities (u_i, the row sums) are register arrays
+// indexed by the TMEM column, accumulated thread-locally over the whole sweep and reduced across
+// lanes once per CTA.  No shuffle, no shared-memory traffic in the per-element path.
+//
+// In MODE 1 the gradient tile is rounded to bf16, written to shared memory as the K-major B operand
+// of a second MMA and contracted against the TRANSPOSED streamed operand:
+//       dXhat^T[d (128 lanes, nq chunks), i (64 columns)] += Yhat^T[d, j] . G^T[j, i]   (UMMA 128 x 64 x 16)
+// The accumulators (nq * 64 <= 384 TMEM columns) stay resident for the whole sweep; the two S
+// buffers use the remaining 128 columns.  Every MMA operand is the same canonical layout: K-major,
+// 128-byte rows, SWIZZLE_128B (what a TMA box {64 elems, R rows} writes), so one descriptor builder
+// serves all of them.
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM
+// allocator, warp 3 idle, warps 4-11 epilogue (two warps per TMEM lane quarter, each taking half of
+// the tile's columns).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ptx.cuh"
+
+namespace tc {
+
+constexpr int BLOCK_J = 128;                         // streamed rows per tile == UMMA M == TMEM lanes
+constexpr int BLOCK_K = 64;                          // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGE_BYTES = BLOCK_J * BLOCK_K * 2;   // 16 KiB per ring stage
+constexpr int G_BYTES = 64 * BLOCK_J * 2;            // one bf16 gradient tile [64 i][128 j]
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
+constexpr int TMEM_COLS = 512;
+constexpr int BWD_S_COL0 = 384;                      // S buffers of MODE 1 live at TMEM columns 384..511
+constexpr int SMALL_BYTES = 3072;                    // barriers, tmem pointer, u_i, reduction scratch
+constexpr int SMEM_LIMIT = 232448;                   // 227 KiB opt-in maximum per CTA
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct Params {
+  int n_rows, n_cols, d;
+  int nkc;         // ceil(d / 64)   contraction chunks of the logits MMA
+  int nq;          // ceil(d / 128)  accumulator chunks of the gradient MMA
+  int n_jt;        // ceil(n_cols / 128)
+  int num_stages;
+  long long diag_offset;
+  float scale;     // s
+  float k2;        // s * log2(e)
+  // MODE 0 outputs
+  float* row_lse;      // [n_rows]           s + log sum_j exp(S_ij - s)
+  float* col_part;     // [2 * gridDim.x][col_ld]  partial sum_i exp(S_ij - s)
+  long long col_ld;
+  float* diag;         // [n_rows]
+  // MODE 1 inputs / outputs
+  const float* log_u;  // [n_rows]
+  const float* log_v;  // [n_cols] or nullptr
+  float diag_w;
+  float out_scale;     // grad_out * s
+  float* dx;           // [n_rows, d] f32
+  float* ds_part;      // [gridDim.x]  sum G.S of this CTA
+};
+
+__host__ __device__ constexpr int smem_bytes(int mode, int block_i, int nkc, int stages) {
+  return 1024 + nkc * block_i * 128 + stages * STAGE_BYTES + (mode == 1 ? 2 * G_BYTES : 0) + SMALL_BYTES;
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
+
+// Transposing butterfly: every lane holds N partial sums v[0..N); afterwards lane L holds, in
+// v[0..N/32), the totals over the warp of entries (N/32)*L + {0..N/32-1}.
+template <int N>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int mask = 16 >> s;
+    const int half = (N / 2) >> s;
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+  }
+}
+
+template <int MODE, int BLOCK_I>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+               const __grid_constant__ CUtensorMap tmap_yt, const Params p) {
+  static_assert(BLOCK_I == 64 || BLOCK_I == 128, "BLOCK_I");
+  static_assert(MODE == 0 || BLOCK_I == 64, "backward keeps 64 rows per CTA");
+  constexpr int X_CHUNK = BLOCK_I * 128;        // bytes of one [BLOCK_I rows x 64 k] chunk of the resident panel
+  constexpr int HALF = BLOCK_I / 2;             // TMEM columns per epilogue warp
+  constexpr int NCH = HALF / 32;                // 32-column TMEM loads per tile per warp
+  constexpr int S_COL0 = (MODE == 0) ? 0 : BWD_S_COL0;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const smem = smem_raw + (base - raw_u32);
+
+  const uint32_t x_smem = base;
+  const uint32_t ring_smem = x_smem + p.nkc * X_CHUNK;
+  const uint32_t g_smem = ring_smem + p.num_stages * STAGE_BYTES;
+  const uint32_t small_off = (g_smem - base) + (MODE == 1 ? 2 * G_BYTES : 0);
+  const uint32_t bars = base + small_off;
+  auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
+  constexpr int B_FULL = 0, B_EMPTY = MAX_STAGES, B_XFULL = 2 * MAX_STAGES, B_SFULL = B_XFULL + 1,
+                B_SEMPTY = B_SFULL + 2, B_GFULL = B_SEMPTY + 2, B_GEMPTY = B_GFULL + 2, B_ACCFULL = B_GEMPTY + 2;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + small_off + 256);
+  float* const u_s = reinterpret_cast<float*>(smem + small_off + 512);     // [BLOCK_I]
+  float* const red = reinterpret_cast<float*>(smem + small_off + 1024);    // [8][64]
+
+  const int warp = threadIdx.x >> 5;   // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * BLOCK_I;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_y);
+    if (MODE == 1) ptx::prefetch_tmap(&tmap_yt);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      ptx::mbar_init(bar(B_FULL + s), 1);
+      ptx::mbar_init(bar(B_EMPTY + s), 1);
+    }
+    ptx::mbar_init(bar(B_XFULL), 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar(B_SFULL + b), 1);
+      ptx::mbar_init(bar(B_SEMPTY + b), NUM_EPI_WARPS);
+      ptx::mbar_init(bar(B_GFULL + b), NUM_EPI_WARPS);
+      ptx::mbar_init(bar(B_GEMPTY + b), 1);
+    }
+    ptx::mbar_init(bar(B_ACCFULL), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ======================================================================= TMA producer
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(B_XFULL), p.nkc * X_CHUNK);
+      for (int kc = 0; kc < p.nkc; ++kc)
+        ptx::tma_load_2d(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * BLOCK_K, i0);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto push = [&](const CUtensorMap* m, int c0, int c1) {
+        ptx::mbar_wait(bar(B_EMPTY + stage), phase ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar(B_FULL + stage), STAGE_BYTES);
+        ptx::tma_load_2d(ring_smem + stage * STAGE_BYTES, m, bar(B_FULL + stage), c0, c1);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      };
+      auto load_y = [&](int t) {   // Yhat[t*128 .. +128, :] as nkc K-major chunks
+        for (int kc = 0; kc < p.nkc; ++kc) push(&tmap_y, kc * BLOCK_K, t * BLOCK_J);
+      };
+      auto load_yt = [&](int t) {  // Yhat^T[:, t*128 .. +128] as nq x 2 chunks [128 d][64 j]
+        for (int q = 0; q < p.nq; ++q)
+          for (int kk = 0; kk < 2; ++kk) push(&tmap_yt, t * BLOCK_J + kk * BLOCK_K, q * 128);
+      };
+      if (MODE == 0) {
+        for (int t = 0; t < p.n_jt; ++t) load_y(t);
+      } else {
+        load_y(0);
+        for (int t = 0; t < p.n_jt; ++t) {
+          if (t + 1 < p.n_jt) load_y(t + 1);
+          load_yt(t);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
+      constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      ptx::mbar_wait(bar(B_XFULL), 0);
+      auto mma_s = [&](int t) {
+        const int b = t & 1;
+        ptx::mbar_wait(bar(B_SEMPTY + b), ((t >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + S_COL0 + b * BLOCK_I;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          ptx::mbar_wait(bar(B_FULL + stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ring_smem + stage * STAGE_BYTES;
+          const uint32_t b0 = x_smem + kc * X_CHUNK;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            ptx::mma_f16(d_tmem, ptx::smem_desc_k_sw128(a0 + k * 32), ptx::smem_desc_k_sw128(b0 + k * 32), idesc_s,
+                         (kc | k) != 0);
+          ptx::mma_commit(bar(B_EMPTY + stage));
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(bar(B_SFULL + b));
+      };
+      auto mma_g = [&](int t) {
+        const int b = t & 1;
+        ptx::mbar_wait(bar(B_GFULL + b), (t >> 1) & 1);
+        ptx::tc_fence_after();
+        for (int q = 0; q < p.nq; ++q) {
+          for (int kk = 0; kk < 2; ++kk) {
+            ptx::mbar_wait(bar(B_FULL + stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t a0 = ring_smem + stage * STAGE_BYTES;          // Yhat^T chunk [128 d][64 j]
+            const uint32_t b0 = g_smem + b * G_BYTES + kk * (G_BYTES / 2);  // G chunk     [ 64 i][64 j]
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              ptx::mma_f16(tmem_base + q * 64, ptx::smem_desc_k_sw128(a0 + k * 32),
+                           ptx::smem_desc_k_sw128(b0 + k * 32), idesc_g, (t | kk | k) != 0);
+            ptx::mma_commit(bar(B_EMPTY + stage));
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        ptx::mma_commit(bar(B_GEMPTY + b));
+      };
+      if (MODE == 0) {
+        for (int t = 0; t < p.n_jt; ++t) mma_s(t);
+      } else {
+        mma_s(0);
+        for (int t = 0; t < p.n_jt; ++t) {
+          if (t + 1 < p.n_jt) mma_s(t + 1);   // keeps the tensor core busy while tile t is in the epilogue
+          mma_g(t);
+        }
+        ptx::mma_commit(bar(B_ACCFULL));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ======================================================================= epilogue
+    const int e = warp - 4;        // 0..7
+    const int q = warp & 3;        // TMEM lane quarter this warp may read
+    const int h = e >> 2;          // which half of the tile's columns
+    const int j_local = q * 32 + lane;
+    const int te = threadIdx.x - 128;
+    const int i_valid = min(BLOCK_I, p.n_rows - i0);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const long long dcol0 = (long long)i0 + p.diag_offset;   // column of the positive of block row 0
+
+    if (MODE == 0) {
+      float racc[HALF];
+#pragma unroll
+      for (int i = 0; i < HALF; ++i) racc[i] = 0.f;
+      for (int t = 0; t < p.n_jt; ++t) {
+        const int b = t & 1;
+        ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
+        ptx::tc_fence_after();
+        const long long jg = (long long)t * BLOCK_J + j_local;
+        const bool jvalid = jg < p.n_cols;
+        const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
+        float csum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + b * BLOCK_I + h * HALF + c * 32, r);
+          ptx::tmem_ld_wait();
+          if (c == NCH - 1) {   // S buffer drained by this warp -> let the MMA warp overwrite it
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(B_SEMPTY + b));
+          }
+          if (jvalid) {
+            const int ibase = h * HALF + c * 32;
+            if (i_valid == BLOCK_I) {
+#pragma unroll
+              for (int x = 0; x < 32; ++x) {
+                const float ev = ex2(fmaf(__uint_as_float(r[x]), p.k2, -p.k2));
+                racc[c * 32 + x] += ev;
+                csum += ev;
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < 32; ++x) {
+                const float ev = (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]), p.k2, -p.k2)) : 0.f;
+                racc[c * 32 + x] += ev;
+                csum += ev;
+              }
+            }
+            if (diag_tile) {
+              const long long id = jg - dcol0 - ibase;   // TMEM column (within this load) holding S_{i,i+off}
+#pragma unroll
+              for (int x = 0; x < 32; ++x)
+                if (id == x && ibase + x < i_valid) p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * p.scale;
+            }
+          }
+        }
+        if (jvalid) p.col_part[(long long)(blockIdx.x * 2 + h) * p.col_ld + jg] = csum;
+      }
+      // row sums: reduce the per-lane partials over the 128 lanes (4 warps) that share half h
+      warp_transpose_reduce<HALF>(racc, lane);
+#pragma unroll
+      for (int x = 0; x < HALF / 32; ++x) red[e * 64 + (HALF / 32) * lane + x] = racc[x];
+      epi_bar_sync();
+      if (te < BLOCK_I) {
+        const int hh = te / HALF, ii = te % HALF;
+        const float tot = red[(hh * 4 + 0) * 64 + ii] + red[(hh * 4 + 1) * 64 + ii] + red[(hh * 4 + 2) * 64 + ii] +
+                          red[(hh * 4 + 3) * 64 + ii];
+        if (te < i_valid) p.row_lse[i0 + te] = p.scale + logf(tot);
+      }
+    } else {
+      // u_i = exp(log_u_i + s): with exp(S - s) <= 1 it gives exp(S + log_u_i) from ONE ex2 per logit
+      if (te < BLOCK_I) u_s[te] = (te < i_valid) ? ex2((p.log_u[i0 + te] + p.scale) * LOG2E) : 0.f;
+      epi_bar_sync();
+      float ds = 0.f;
+      for (int t = 0; t < p.n_jt; ++t) {
+        const int b = t & 1;
+        ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + b * 64 + h * 32, r);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(B_SEMPTY + b));
+
+        const long long jg = (long long)t * BLOCK_J + j_local;
+        const bool jvalid = jg < p.n_cols;
+        const float vj = (jvalid && p.log_v != nullptr) ? ex2((p.log_v[jg] + p.scale) * LOG2E) : 0.f;
+        const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
+        const bool plain = jvalid && (i_valid == BLOCK_I) && !diag_tile;
+        const long long id = jg - dcol0 - h * 32;
+
+        ptx::mbar_wait(bar(B_GEMPTY + b), ((t >> 1) & 1) ^ 1u);   // gradient MMA of tile t-2 has read this buffer
+        const int jj = j_local & 63;
+        const uint32_t g_row0 = g_smem + b * G_BYTES + (j_local >> 6) * (G_BYTES / 2) + (jj & 7) * 2;
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          const int i = h * 32 + x;
+          const float y = __uint_as_float(r[x]) * p.k2;      // S_ij * log2(e)
+          float g = ex2(y - p.k2) * (u_s[i] + vj);
+          if (!plain) {
+            if (id == x) g -= p.diag_w;
+            if (!(jvalid && i < i_valid)) g = 0.f;
+          }
+          ds = fmaf(g, y, ds);
+          const uint32_t addr = g_row0 + (i >> 3) * 1024 + (i & 7) * 128 + ((((jj >> 3) ^ (i & 7))) << 4);
+          const __nv_bfloat16 gb = __float2bfloat16_rn(g);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&gb)) : "memory");
+        }
+        ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(B_GFULL + b));
+      }
+      // accumulators complete: dXhat^T[d = qc*128 + lane_global, i]  ->  dx[i][d]
+      ptx::mbar_wait(bar(B_ACCFULL), 0);
+      ptx::tc_fence_after();
+      for (int qc = 0; qc < p.nq; ++qc) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_lane + qc * 64 + h * 32, r);
+        ptx::tmem_ld_wait();
+        const int dd = qc * 128 + j_local;
+        if (dd < p.d) {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const int i = h * 32 + x;
+            if (i < i_valid) p.dx[(long long)(i0 + i) * p.d + dd] = __uint_as_float(r[x]) * p.out_scale;
+          }
+        }
+      }
+      if (p.ds_part != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        if (lane == 0) red[e] = ds;
+        epi_bar_sync();
+        if (te == 0) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < NUM_EPI_WARPS; ++w) tot += red[w];
+          p.ds_part[blockIdx.x] = tot * LN2;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace tc

@@ -1,0 +1,147 @@
+"""CudaEngine: the C-ABI calls of include/clipnce.h on torch CUDA tensors.
+
+torch is plumbing only (device memory, current stream).  Every method enqueues on the current CUDA
+stream and returns freshly allocated (or cached-workspace) tensors; nothing synchronises the host.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DT = {torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CudaEngine:
+    """One instance per device; caches the scratch workspace per shape."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self._ws = {}
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _chk(t, dtypes, what):
+        if not t.is_cuda:
+            raise RuntimeError(f"clip_dplm_b200: {what} must be a CUDA tensor (there is no CPU path)")
+        if t.dtype not in dtypes:
+            raise RuntimeError(f"clip_dplm_b200: {what} has unsupported dtype {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError(f"clip_dplm_b200: {what} must be contiguous")
+
+    def uses_tensor_cores(self, dtype, d, scale, flags=0):
+        return bool(self.lib.clipnce_uses_tensor_cores(_DT[dtype], d, float(scale), flags))
+
+    def workspace(self, n_rows, n_cols, d, dtype, flags, device):
+        key = (n_rows, n_cols, d, dtype, flags, device, torch.cuda.current_stream(device).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(self.lib.clipnce_workspace_bytes(n_rows, n_cols, d, _DT[dtype], flags, ctypes.byref(nbytes)),
+                       "workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+            if len(self._ws) > 16:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ stages
+    def normalize(self, x, out_dtype, want_t=False):
+        """-> (x_hat [n,d], x_hat_t [d,ld] or None, rinv [n])   (F.normalize, old/clip.py:63-64)"""
+        self._chk(x, (torch.bfloat16, torch.float32), "embedding")
+        n, d = x.shape
+        xh = torch.empty((n, d), dtype=out_dtype, device=x.device)
+        rinv = torch.empty((n,), dtype=torch.float32, device=x.device)
+        xt, ld = None, 0
+        if want_t:
+            ld = (n + 63) // 64 * 64
+            xt = torch.empty((d, ld), dtype=out_dtype, device=x.device)
+        _lib.check(self.lib.clipnce_normalize(_p(x), _DT[x.dtype], n, d, _p(xh), _p(xt), ld, _DT[out_dtype], _p(rinv),
+                                              _stream()), "normalize")
+        return xh, xt, rinv
+
+    def transpose(self, xh):
+        self._chk(xh, (torch.bfloat16, torch.float32), "normalised embedding")
+        n, d = xh.shape
+        ld = (n + 63) // 64 * 64
+        xt = torch.empty((d, ld), dtype=xh.dtype, device=xh.device)
+        _lib.check(self.lib.clipnce_transpose(_p(xh), n, d, _p(xt), ld, _DT[xh.dtype], _stream()), "transpose")
+        return xt
+
+    def forward(self, x_hat, y_hat, diag_offset, scale, flags=0):
+        """-> row_lse [n_rows], col_m [n_cols], col_l [n_cols], diag [n_rows]"""
+        self._chk(x_hat, (torch.bfloat16, torch.float32), "x_hat")
+        self._chk(y_hat, (x_hat.dtype,), "y_hat")
+        n_rows, d = x_hat.shape
+        n_cols = y_hat.shape[0]
+        dev = x_hat.device
+        ws = self.workspace(n_rows, n_cols, d, x_hat.dtype, flags, dev)
+        row_lse = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        col_m = torch.empty(n_cols, dtype=torch.float32, device=dev)
+        col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
+        diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+        _lib.check(self.lib.clipnce_forward(_p(x_hat), _p(y_hat), n_rows, n_cols, d, int(diag_offset), float(scale),
+                                            _DT[x_hat.dtype], flags, _p(row_lse), _p(col_m), _p(col_l), _p(diag),
+                                            _p(ws), ws.numel(), _stream()), "forward")
+        return row_lse, col_m, col_l, diag
+
+    def backward(self, x_hat, y_hat, y_hat_t, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
+                 want_dscale=True):
+        """-> dx_hat [n_rows,d] f32, d_scale_sum [1] f32 (or None)"""
+        n_rows, d = x_hat.shape
+        n_cols = y_hat.shape[0]
+        dev = x_hat.device
+        ws = self.workspace(n_rows, n_cols, d, x_hat.dtype, flags, dev)
+        dx = torch.empty((n_rows, d), dtype=torch.float32, device=dev)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+        ld_t = y_hat_t.shape[1] if y_hat_t is not None else 0
+        _lib.check(self.lib.clipnce_backward(_p(x_hat), _p(y_hat), _p(y_hat_t), ld_t, n_rows, n_cols, d,
+                                             int(diag_offset), float(scale), _p(log_u), _p(log_v), float(diag_w),
+                                             float(grad_out), _DT[x_hat.dtype], flags, _p(dx), _p(ds), _p(ws),
+                                             ws.numel(), _stream()), "backward")
+        return dx, ds
+
+    def log_weights(self, lse, log_coef):
+        out = torch.empty_like(lse)
+        _lib.check(self.lib.clipnce_log_weights(_p(lse), lse.numel(), float(log_coef), _p(out), _stream()), "log_weights")
+        return out
+
+    def combine_lse(self, m, l):
+        out = torch.empty_like(m)
+        _lib.check(self.lib.clipnce_combine_lse(_p(m), _p(l), m.numel(), _p(out), _stream()), "combine_lse")
+        return out
+
+    def normalize_backward(self, x, rinv, dx_hat, out_dtype, grad_scale=None):
+        n, d = x.shape
+        dx = torch.empty((n, d), dtype=out_dtype, device=x.device)
+        _lib.check(self.lib.clipnce_normalize_backward(_p(x), _DT[x.dtype], _p(rinv), _p(dx_hat), _p(grad_scale), n, d, _p(dx),
+                                                       _DT[out_dtype], _stream()), "normalize_backward")
+        return dx
+
+    def loss(self, row_lse, col_lse, diag, diag_offset, n_global, symmetric):
+        out = torch.empty(1, dtype=torch.float32, device=row_lse.device)
+        _lib.check(self.lib.clipnce_loss(_p(row_lse), _p(col_lse), _p(diag), row_lse.numel(), int(diag_offset),
+                                         int(n_global), int(bool(symmetric)), _p(out), _stream()), "loss")
+        return out
+
+
+_engine = None
+
+
+def default_engine() -> CudaEngine:
+    global _engine
+    if _engine is None:
+        _engine = CudaEngine()
+    return _engine

@@ -1,0 +1,146 @@
+"""Host-side orchestration of one contrastive step (engine-agnostic).
+
+Single GPU:   normalise -> forward statistics -> loss      |  backward (two sides) -> normalise-bwd
+Row-sharded global batch over a process group (replaces the autograd-blind
+``dist.all_gather`` + ``torch.cat`` of old/clip_opt.py:102-112 / run1/full.py:77-84):
+
+    rank p owns rows [p*n, (p+1)*n) of both modalities
+    fwd:  all-gather normalised B  ->  local rows x all columns  ->  all-reduce column (max, sumexp)
+          -> all-reduce the scalar loss
+    bwd:  dA complete locally;  dB partial [N,d] -> reduce-scatter -> local normalise-bwd
+
+The engine (``engine.CudaEngine`` in production) provides the kernels; tests drive the same code
+with a CPU stand-in over gloo to cover the sharding/offset/collective logic without a GPU.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+FLAG_FORCE_EXACT = 1
+
+
+# ------------------------------------------------------------------------------------------------
+# collectives (NCCL on GPUs; gloo in the CPU tests, which lacks some tensor collectives)
+# ------------------------------------------------------------------------------------------------
+def _all_gather_rows(x, group):
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if dist.get_backend(group) == "gloo" and x.dtype == torch.bfloat16:
+        tmp = torch.empty(out.shape, dtype=torch.float32, device=x.device)
+        dist.all_gather_into_tensor(tmp, x.float().contiguous(), group=group)
+        return tmp.to(x.dtype)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_rows(x, group):
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = x.shape[0] // world
+    if dist.get_backend(group) == "gloo":
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y[rank * n:(rank + 1) * n].contiguous()
+    out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+@dataclass
+class StepState:
+    a: torch.Tensor
+    b: torch.Tensor
+    a_hat: torch.Tensor
+    a_hat_t: Optional[torch.Tensor]
+    y_hat: torch.Tensor            # all columns: gathered B (+ extra negatives)
+    y_hat_t: Optional[torch.Tensor]
+    rinv_a: torch.Tensor
+    rinv_b: torch.Tensor
+    row_lse: torch.Tensor
+    col_lse: torch.Tensor
+    diag: torch.Tensor
+    scale: float
+    symmetric: bool
+    n_local: int
+    n_global: int
+    diag_offset: int
+    flags: int
+    group: object
+
+
+def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra_hat=None, group=None,
+                        compute_dtype=torch.bfloat16, flags=0, need_grad=True):
+    """Returns (loss [1] f32 -- the GLOBAL mean loss, identical on every rank --, StepState)."""
+    if a.dim() != 2 or b.dim() != 2 or a.shape != b.shape:
+        raise ValueError(f"expected two [N,d] embedding matrices of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+    n_local = a.shape[0]
+    world = dist.get_world_size(group) if group is not None else 1
+    rank = dist.get_rank(group) if group is not None else 0
+    n_global = n_local * world
+    diag_offset = rank * n_local
+
+    tc = engine.uses_tensor_cores(compute_dtype, a.shape[1], scale, flags)
+    want_t = need_grad and tc
+    a_hat, a_hat_t, rinv_a = engine.normalize(a, compute_dtype, want_t=want_t)
+    b_hat, b_hat_t, rinv_b = engine.normalize(b, compute_dtype, want_t=want_t and world == 1 and extra_hat is None)
+    y_hat, y_hat_t = b_hat, b_hat_t
+    if world > 1:
+        y_hat = _all_gather_rows(b_hat, group)
+    if extra_hat is not None:
+        y_hat = torch.cat([y_hat, extra_hat.detach().to(compute_dtype)], dim=0).contiguous()
+    if want_t and y_hat_t is None:
+        y_hat_t = engine.transpose(y_hat)
+
+    row_lse, col_m, col_l, diag = engine.forward(a_hat, y_hat, diag_offset, scale, flags)
+    if world > 1:
+        m_max = col_m.clone()
+        dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=group)
+        l = col_l * torch.exp(col_m - m_max)
+        dist.all_reduce(l, op=dist.ReduceOp.SUM, group=group)
+        col_lse = m_max + torch.log(l)
+    else:
+        col_lse = engine.combine_lse(col_m, col_l)
+    if y_hat.shape[0] > n_global:
+        col_lse[n_global:] = float("inf")   # extra negatives carry no positives: no column loss, no column soft-max
+    loss = engine.loss(row_lse, col_lse, diag, diag_offset, n_global, symmetric)
+    if world > 1:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    st = StepState(a, b, a_hat, a_hat_t, y_hat, y_hat_t, rinv_a, rinv_b, row_lse, col_lse, diag, scale, symmetric,
+                   n_local, n_global, diag_offset, flags, group)
+    return loss, st
+
+
+def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=None, grad_dtype_b=None):
+    """Returns (dA [n,d], dB [n,d], d_scale_sum [1]) for upstream gradient 1; ``grad_scale`` is an optional
+    device scalar multiplied into dA/dB inside the normalise-backward kernel (d_scale_sum is left
+    unscaled -- the caller multiplies that single element)."""
+    n_glob = st.n_global
+    world = dist.get_world_size(st.group) if st.group is not None else 1
+    log_coef = -math.log((2.0 if st.symmetric else 1.0) * n_glob)
+    log_u = engine.log_weights(st.row_lse, log_coef)
+    if st.symmetric:
+        log_v = engine.log_weights(st.col_lse, log_coef)
+    else:
+        log_v = torch.full_like(st.col_lse, float("-inf"))
+    diag_w = 1.0 / n_glob
+
+    # side 1: local rows x all columns -> dA_hat (complete) and sum G.S over the local row block
+    da_hat, ds = engine.backward(st.a_hat, st.y_hat, st.y_hat_t, st.diag_offset, st.scale, log_u, log_v, diag_w, 1.0,
+                                 st.flags, want_dscale=True)
+    # side 2: the positive-carrying columns as rows x local rows as columns -> partial dB_hat [N,d]
+    y_main = st.y_hat[:n_glob]
+    db_part, _ = engine.backward(y_main, st.a_hat, st.a_hat_t, -st.diag_offset, st.scale, log_v[:n_glob].contiguous(),
+                                 log_u, diag_w, 1.0, st.flags, want_dscale=False)
+    if world > 1:
+        db_hat = _reduce_scatter_rows(db_part, st.group)
+        dist.all_reduce(ds, op=dist.ReduceOp.SUM, group=st.group)
+    else:
+        db_hat = db_part
+    da = engine.normalize_backward(st.a, st.rinv_a, da_hat, grad_dtype_a or st.a.dtype, grad_scale)
+    db = engine.normalize_backward(st.b, st.rinv_b, db_hat, grad_dtype_b or st.b.dtype, grad_scale)
+    return da, db, ds

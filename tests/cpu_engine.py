@@ -1,0 +1,89 @@
+"""CPU stand-in for clip_dplm_b200.engine.CudaEngine -- TEST INFRASTRUCTURE ONLY.
+
+Implements the stage contract of include/clipnce.h with dense torch ops (it materialises the logits,
+which the product never does) so that the host-side orchestration in clip_dplm_b200/step.py --
+sharding offsets, LSE combination, collectives, gradient routing -- can be exercised on CPU, including
+world_size-2 gloo runs.  The product path never imports this file.
+"""
+from __future__ import annotations
+
+import torch
+
+EPS = 1e-12
+
+
+class TorchCpuEngine:
+    name = "cpu-test"
+
+    def __init__(self, dtype=torch.float64):
+        self.dt = dtype
+
+    def uses_tensor_cores(self, dtype, d, scale, flags=0):
+        return True   # so that step.py exercises the transposed-operand plumbing too
+
+    def normalize(self, x, out_dtype, want_t=False):
+        xf = x.to(self.dt)
+        denom = xf.norm(dim=1).clamp_min(EPS)
+        xh = xf / denom[:, None]
+        n = x.shape[0]
+        xt = None
+        if want_t:
+            ld = (n + 63) // 64 * 64
+            xt = torch.zeros(x.shape[1], ld, dtype=self.dt)
+            xt[:, :n] = xh.t()
+        return xh, xt, (1.0 / denom)
+
+    def transpose(self, xh):
+        n = xh.shape[0]
+        ld = (n + 63) // 64 * 64
+        xt = torch.zeros(xh.shape[1], ld, dtype=xh.dtype)
+        xt[:, :n] = xh.t()
+        return xt
+
+    def forward(self, x_hat, y_hat, diag_offset, scale, flags=0):
+        S = scale * (x_hat @ y_hat.t())
+        n = x_hat.shape[0]
+        row_lse = torch.logsumexp(S, dim=1)
+        col_m = S.max(dim=0).values
+        col_l = torch.exp(S - col_m[None, :]).sum(dim=0)
+        idx = torch.arange(n)
+        diag = S[idx, idx + diag_offset]
+        return row_lse, col_m, col_l, diag
+
+    def backward(self, x_hat, y_hat, y_hat_t, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
+                 want_dscale=True):
+        if y_hat_t is not None:   # the transposed operand must be the same matrix
+            assert torch.equal(y_hat_t[:, :y_hat.shape[0]].t(), y_hat)
+        S = scale * (x_hat @ y_hat.t())
+        G = torch.exp(S + log_u[:, None])
+        if log_v is not None:
+            G = G + torch.exp(S + log_v[None, :])
+        n_rows, n_cols = S.shape
+        i = torch.arange(n_rows)
+        j = i + diag_offset
+        ok = (j >= 0) & (j < n_cols)
+        G[i[ok], j[ok]] -= diag_w
+        dx = grad_out * scale * (G @ y_hat)
+        ds = (grad_out * (G * S).sum()).reshape(1) if want_dscale else None
+        return dx, ds
+
+    def log_weights(self, lse, log_coef):
+        return log_coef - lse
+
+    def combine_lse(self, m, l):
+        return m + torch.log(l)
+
+    def normalize_backward(self, x, rinv, dx_hat, out_dtype, grad_scale=None):
+        xh = x.to(self.dt) * rinv[:, None]
+        g = dx_hat
+        dx = (g - xh * (xh * g).sum(dim=1, keepdim=True)) * rinv[:, None]
+        if grad_scale is not None:
+            dx = dx * grad_scale.to(self.dt)
+        return dx.to(out_dtype)
+
+    def loss(self, row_lse, col_lse, diag, diag_offset, n_global, symmetric):
+        n = row_lse.numel()
+        tot = (row_lse - diag).sum()
+        if symmetric:
+            tot = tot + (col_lse[diag_offset:diag_offset + n] - diag).sum()
+        return (tot / ((2 if symmetric else 1) * n_global)).reshape(1)
