@@ -30,11 +30,11 @@ SIGNATURES = {
     "clipnce_last_error": [],
     "clipnce_uses_tensor_cores": [_int, _i64, _f32, _int],
     "clipnce_workspace_bytes": [_i64, _i64, _i64, _int, _int, ctypes.POINTER(_sz)],
-    "clipnce_normalize": [_vp, _int, _i64, _i64, _vp, _vp, _i64, _int, _vp, _vp],
-    "clipnce_transpose": [_vp, _i64, _i64, _vp, _i64, _int, _vp],
-    "clipnce_forward": [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
-    "clipnce_backward": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp,
-                         _vp, _sz, _vp],
+    "clipnce_normalize": [_vp, _int, _i64, _i64, _vp, _vp, _int, _vp],
+    "clipnce_stage_operand": [_vp, _int, _i64, _i64, _vp, _vp, _i64, _int, _vp],
+    "clipnce_forward": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "clipnce_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _f32, _f32, _int, _int,
+                         _vp, _vp, _vp, _sz, _vp],
     "clipnce_log_weights": [_vp, _i64, _f32, _vp, _vp],
     "clipnce_combine_lse": [_vp, _vp, _i64, _vp, _vp],
     "clipnce_normalize_backward": [_vp, _int, _vp, _vp, _vp, _i64, _i64, _vp, _int, _vp],

@@ -166,46 +166,56 @@ int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype
   return 0;
 }
 
-int clipnce_normalize(const void* x, int in_dtype, int64_t n, int64_t d, void* x_hat, void* x_hat_t, int64_t ld_t,
-                      int out_dtype, float* rinv, void* stream) {
-  if (!x || !x_hat || !rinv || n < 1 || d < 1) return fail(CLIPNCE_EINVAL, "normalize: null pointer or empty shape");
-  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+int clipnce_normalize(const void* x, int in_dtype, int64_t n, int64_t d, float* rinv, void* x_hat, int hat_dtype,
+                      void* stream) {
+  if (!x || !rinv || n < 1 || d < 1) return fail(CLIPNCE_EINVAL, "normalize: null pointer or empty shape");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) ||
+      (x_hat && hat_dtype != CLIPNCE_BF16 && hat_dtype != CLIPNCE_F32))
     return fail(CLIPNCE_EINVAL, "normalize: bad dtype");
   if (d > (1 << 20)) return fail(CLIPNCE_EINVAL, "normalize: d too large");
   cudaStream_t st = as_stream(stream);
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
   const int di = (int)d;
-  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16)
+  const bool hat_bf16 = x_hat && hat_dtype == CLIPNCE_BF16;
+  if (in_dtype == CLIPNCE_BF16 && hat_bf16)
     aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, (__nv_bfloat16*)x_hat, rinv);
-  else if (in_dtype == CLIPNCE_F32 && out_dtype == CLIPNCE_BF16)
+  else if (in_dtype == CLIPNCE_F32 && hat_bf16)
     aux::normalize_rows<<<grid, block, 0, st>>>((const float*)x, n, di, (__nv_bfloat16*)x_hat, rinv);
-  else if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_F32)
+  else if (in_dtype == CLIPNCE_BF16)
     aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, (float*)x_hat, rinv);
   else
     aux::normalize_rows<<<grid, block, 0, st>>>((const float*)x, n, di, (float*)x_hat, rinv);
   CUDA_TRY(cudaGetLastError());
-  if (x_hat_t) return clipnce_transpose(x_hat, n, d, x_hat_t, ld_t, out_dtype, stream);
   return 0;
 }
 
-int clipnce_transpose(const void* x_hat, int64_t n, int64_t d, void* x_hat_t, int64_t ld_t, int dtype, void* stream) {
-  if (!x_hat || !x_hat_t || n < 1 || d < 1 || ld_t < n) return fail(CLIPNCE_EINVAL, "transpose: bad argument");
-  if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "transpose: bad dtype");
+int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, void* x_c, void* x_c_t, int64_t ld_t,
+                          int c_dtype, void* stream) {
+  if (!x || n < 1 || d < 1) return fail(CLIPNCE_EINVAL, "stage_operand: bad argument");
+  if (!x_c && !x_c_t) return 0;
+  if (x_c_t && (ld_t < n || ld_t % 8 != 0)) return fail(CLIPNCE_EINVAL, "stage_operand: ld_t must be >= n and a multiple of 8");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (c_dtype != CLIPNCE_BF16 && c_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "stage_operand: bad dtype");
+  cudaStream_t st = as_stream(stream);
   dim3 grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(d, 32)), block(32, 8);
-  if (dtype == CLIPNCE_BF16)
-    aux::transpose_tiled<<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)x_hat, n, (int)d,
-                                                                (__nv_bfloat16*)x_hat_t, ld_t);
+  const int di = (int)d;
+  if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_BF16)
+    aux::stage_operand<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, (__nv_bfloat16*)x_c, (__nv_bfloat16*)x_c_t, ld_t);
+  else if (in_dtype == CLIPNCE_F32 && c_dtype == CLIPNCE_BF16)
+    aux::stage_operand<<<grid, block, 0, st>>>((const float*)x, n, di, (__nv_bfloat16*)x_c, (__nv_bfloat16*)x_c_t, ld_t);
+  else if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_F32)
+    aux::stage_operand<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, (float*)x_c, (float*)x_c_t, ld_t);
   else
-    aux::transpose_tiled<<<grid, block, 0, as_stream(stream)>>>((const float*)x_hat, n, (int)d, (float*)x_hat_t, ld_t);
+    aux::stage_operand<<<grid, block, 0, st>>>((const float*)x, n, di, (float*)x_c, (float*)x_c_t, ld_t);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset,
-                    float scale, int dtype, int flags, float* row_lse, float* col_m, float* col_l, float* diag,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x_hat || !y_hat || !row_lse || !col_m || !col_l || !diag || !workspace)
+int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, int dtype, int flags, float* row_lse,
+                    float* col_m, float* col_l, float* diag, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !y || !rinv_x || !rinv_y || !row_lse || !col_m || !col_l || !diag || !workspace)
     return fail(CLIPNCE_EINVAL, "forward: null pointer");
   if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
     return fail(CLIPNCE_EINVAL, "forward: bad shape");
@@ -216,20 +226,21 @@ int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_
   if (rc) return rc;
 
   if (tc_eligible(dtype, d, scale, flags)) {
-    if (!aligned16(x_hat) || !aligned16(y_hat)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
+    if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
     const int bi = fwd_block_i(n_rows, d);
     const int64_t n_ib = ceil_div(n_rows, bi);
     const int64_t col_ld = round_up(n_cols, 32);
     const size_t need = sizeof(float) * 2 * (size_t)n_ib * (size_t)col_ld;
     if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
     CUtensorMap tx, ty;
-    if ((rc = make_tmap(&tx, x_hat, d, n_rows, d, bi))) return rc;
-    if ((rc = make_tmap(&ty, y_hat, d, n_cols, d, tc::BLOCK_J))) return rc;
+    if ((rc = make_tmap(&tx, x, d, n_rows, d, bi))) return rc;
+    if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J))) return rc;
     tc::Params p;
     memset(&p, 0, sizeof p);
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
+    p.rinv_x = rinv_x; p.rinv_y = rinv_y;
     p.row_lse = row_lse; p.col_part = reinterpret_cast<float*>(workspace); p.col_ld = col_ld; p.diag = diag;
     if (bi == 128) rc = launch_tc<0, 128>(0, tx, ty, ty, p, (int)n_ib, st);
     else           rc = launch_tc<0, 64>(1, tx, ty, ty, p, (int)n_ib, st);
@@ -246,12 +257,13 @@ int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_
   if (w.n_it > 65535) return fail(CLIPNCE_EUNSUPPORTED, "forward (exact path): n_rows too large");
   dim3 grid((unsigned)w.n_jt, (unsigned)w.n_it);
   if (dtype == CLIPNCE_BF16)
-    simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x_hat, (const __nv_bfloat16*)y_hat, n_rows,
-                                                     n_cols, (int)d, diag_offset, scale, w.row_pm, w.row_pl, w.col_pm,
-                                                     w.col_pl, diag);
+    simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y,
+                                                     n_rows, n_cols, (int)d, diag_offset, scale, w.row_pm, w.row_pl,
+                                                     w.col_pm, w.col_pl, diag);
   else
-    simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const float*)x_hat, (const float*)y_hat, n_rows, n_cols, (int)d,
-                                                     diag_offset, scale, w.row_pm, w.row_pl, w.col_pm, w.col_pl, diag);
+    simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const float*)x, (const float*)y, rinv_x, rinv_y, n_rows, n_cols,
+                                                     (int)d, diag_offset, scale, w.row_pm, w.row_pl, w.col_pm, w.col_pl,
+                                                     diag);
   CUDA_TRY(cudaGetLastError());
   aux::reduce_ml_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(w.row_pm, w.row_pl, (int)w.n_jt, n_rows,
                                                                              n_rows, 0, row_lse, nullptr);
@@ -261,11 +273,12 @@ int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_
   return 0;
 }
 
-int clipnce_backward(const void* x_hat, const void* y_hat, const void* y_hat_t, int64_t ld_t, int64_t n_rows,
-                     int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* log_u,
-                     const float* log_v, float diag_w, float grad_out, int dtype, int flags, float* dx_hat,
-                     float* d_scale_sum, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x_hat || !y_hat || !log_u || !dx_hat || !workspace) return fail(CLIPNCE_EINVAL, "backward: null pointer");
+int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
+                     const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                     const float* log_u, const float* log_v, float diag_w, float grad_out, int dtype, int flags,
+                     float* dx_hat, float* d_scale_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !y || !rinv_x || !rinv_y || !log_u || !dx_hat || !workspace)
+    return fail(CLIPNCE_EINVAL, "backward: null pointer");
   if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
     return fail(CLIPNCE_EINVAL, "backward: bad shape");
   if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "backward: bad dtype %d", dtype);
@@ -275,22 +288,23 @@ int clipnce_backward(const void* x_hat, const void* y_hat, const void* y_hat_t, 
   if (rc) return rc;
 
   if (tc_eligible(dtype, d, scale, flags)) {
-    if (!y_hat_t) return fail(CLIPNCE_EINVAL, "backward: the tensor-core path needs y_hat_t");
+    if (!y_t) return fail(CLIPNCE_EINVAL, "backward: the tensor-core path needs y_t");
     if (ld_t < n_cols || ld_t % 8 != 0) return fail(CLIPNCE_EINVAL, "backward: ld_t must be >= n_cols and a multiple of 8");
-    if (!aligned16(x_hat) || !aligned16(y_hat) || !aligned16(y_hat_t))
+    if (!aligned16(x) || !aligned16(y) || !aligned16(y_t))
       return fail(CLIPNCE_EINVAL, "backward: operands must be 16-byte aligned");
     const int64_t n_ib = ceil_div(n_rows, 64);
     const size_t need = sizeof(float) * (size_t)n_ib;
     if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
     CUtensorMap tx, ty, tyt;
-    if ((rc = make_tmap(&tx, x_hat, d, n_rows, d, 64))) return rc;
-    if ((rc = make_tmap(&ty, y_hat, d, n_cols, d, tc::BLOCK_J))) return rc;
-    if ((rc = make_tmap(&tyt, y_hat_t, n_cols, d, ld_t, 128))) return rc;
+    if ((rc = make_tmap(&tx, x, d, n_rows, d, 64))) return rc;
+    if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J))) return rc;
+    if ((rc = make_tmap(&tyt, y_t, n_cols, d, ld_t, 128))) return rc;
     tc::Params p;
     memset(&p, 0, sizeof p);
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
+    p.rinv_x = rinv_x; p.rinv_y = rinv_y;
     p.log_u = log_u; p.log_v = log_v; p.diag_w = diag_w; p.out_scale = grad_out * scale;
     p.dx = dx_hat; p.ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
     if ((rc = launch_tc<1, 64>(2, tx, ty, tyt, p, (int)n_ib, st))) return rc;
@@ -308,13 +322,13 @@ int clipnce_backward(const void* x_hat, const void* y_hat, const void* y_hat_t, 
   float* ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
   dim3 grid((unsigned)ceil_div(d, simt::TILE), (unsigned)n_it);
   if (dtype == CLIPNCE_BF16)
-    simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x_hat, (const __nv_bfloat16*)y_hat, n_rows,
-                                                    n_cols, (int)d, diag_offset, scale, log_u, log_v, diag_w,
+    simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y,
+                                                    n_rows, n_cols, (int)d, diag_offset, scale, log_u, log_v, diag_w,
                                                     grad_out * scale, dx_hat, ds_part);
   else
-    simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const float*)x_hat, (const float*)y_hat, n_rows, n_cols, (int)d,
-                                                    diag_offset, scale, log_u, log_v, diag_w, grad_out * scale, dx_hat,
-                                                    ds_part);
+    simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const float*)x, (const float*)y, rinv_x, rinv_y, n_rows, n_cols,
+                                                    (int)d, diag_offset, scale, log_u, log_v, diag_w, grad_out * scale,
+                                                    dx_hat, ds_part);
   CUDA_TRY(cudaGetLastError());
   if (d_scale_sum) {
     aux::reduce_scalar_partials<<<1, 32, 0, st>>>(ds_part, (int)n_it, grad_out, d_scale_sum);

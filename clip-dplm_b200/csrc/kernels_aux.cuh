@@ -22,7 +22,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr float kNormEps = 1e-12f;  // F.normalize default eps
 
-// One warp per row: x_hat = x / max(|x|, eps)   (old/clip.py:63-64).
+// One warp per row: rinv = 1 / max(|x|, eps), optionally x_hat = x / max(|x|, eps)   (old/clip.py:63-64).
 template <typename TI, typename TO>
 __global__ void normalize_rows(const TI* __restrict__ x, int64_t n, int d, TO* __restrict__ xh, float* __restrict__ rinv) {
   const int lane = threadIdx.x & 31;
@@ -36,28 +36,37 @@ __global__ void normalize_rows(const TI* __restrict__ x, int64_t n, int d, TO* _
   }
   ss = warp_sum(ss);
   const float denom = fmaxf(sqrtf(ss), kNormEps);
-  TO* o = xh + row * d;
-  for (int k = lane; k < d; k += 32) st_f(o + k, ld_f(xr + k) / denom);
+  if (xh != nullptr) {
+    TO* o = xh + row * d;
+    for (int k = lane; k < d; k += 32) st_f(o + k, ld_f(xr + k) / denom);
+  }
   if (lane == 0) rinv[row] = 1.f / denom;
 }
 
-// Tiled transpose [n,d] -> [d,ld_t]; padding columns n..ld_t are left untouched (TMA never reads
-// them: the tensor map's extent is n).
-template <typename T>
-__global__ void transpose_tiled(const T* __restrict__ in, int64_t n, int d, T* __restrict__ out, int64_t ld_t) {
-  __shared__ T tile[32][33];
+// Operand staging: out_c = convert(in) [n,d] (optional) and out_t = convert(in)^T [d,ld_t] (optional).
+// Padding columns n..ld_t of out_t are left untouched (TMA never reads them: the map's extent is n).
+template <typename TI, typename TO>
+__global__ void stage_operand(const TI* __restrict__ in, int64_t n, int d, TO* __restrict__ out_c, TO* __restrict__ out_t,
+                              int64_t ld_t) {
+  __shared__ TO tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     int64_t rr = r0 + r;
     int cc = c0 + threadIdx.x;
-    if (rr < n && cc < d) tile[r][threadIdx.x] = in[rr * d + cc];
+    if (rr < n && cc < d) {
+      TO v;
+      st_f(&v, ld_f(in + rr * d + cc));
+      tile[r][threadIdx.x] = v;
+      if (out_c != nullptr) out_c[rr * d + cc] = v;
+    }
   }
+  if (out_t == nullptr) return;
   __syncthreads();
   for (int c = threadIdx.y; c < 32; c += blockDim.y) {
     int cc = c0 + c;
     int64_t rr = r0 + threadIdx.x;
-    if (rr < n && cc < d) out[(int64_t)cc * ld_t + rr] = tile[threadIdx.x][c];
+    if (rr < n && cc < d) out_t[(int64_t)cc * ld_t + rr] = tile[threadIdx.x][c];
   }
 }
 

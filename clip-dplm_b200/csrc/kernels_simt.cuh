@@ -15,16 +15,20 @@ constexpr int TILE = 64;   // logits tile (rows x cols) per block
 constexpr int KT = 16;     // contraction chunk staged in shared memory
 constexpr int THREADS = 256;
 
-// S tile (64x64) = scale * X[i0:i0+64, :] . Y[j0:j0+64, :]^T ; thread (ty,tx) owns rows ty*4.., cols tx*4..
+// S tile (64x64): S_ij = scale * rinv_x[i] rinv_y[j] <x_i, y_j>; thread (ty,tx) owns rows ty*4.., cols tx*4..
+// The dot products are accumulated in fp64 so that the check mode is limited by the fp32 inputs and
+// the fp32 soft-max arithmetic only (the reference's own fp32 noise is ~1e-5 on the gradients).
 template <typename T>
-__device__ __forceinline__ void logits_tile(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows,
-                                            int64_t n_cols, int d, int64_t i0, int64_t j0, float scale,
+__device__ __forceinline__ void logits_tile(const T* __restrict__ x, const T* __restrict__ y,
+                                            const float* __restrict__ rinv_x, const float* __restrict__ rinv_y,
+                                            int64_t n_rows, int64_t n_cols, int d, int64_t i0, int64_t j0, float scale,
                                             float (&s)[4][4], float (*Xs)[TILE + 1], float (*Ys)[TILE + 1]) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) s[a][b] = 0.f;
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
   for (int k0 = 0; k0 < d; k0 += KT) {
     // 64 rows x 16 k per operand = 1024 elements, 4 per thread; stored [k][row] for conflict-free reads
 #pragma unroll
@@ -47,22 +51,27 @@ __device__ __forceinline__ void logits_tile(const T* __restrict__ x, const T* __
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s[a][b] = fmaf(xa[a], yb[b], s[a][b]);
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma((double)xa[a], (double)yb[b], acc[a][b]);
     }
     __syncthreads();
   }
+  float rx[4], ry[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) rx[a] = (i0 + ty * 4 + a < n_rows) ? rinv_x[i0 + ty * 4 + a] : 0.f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) ry[b] = (j0 + tx * 4 + b < n_cols) ? rinv_y[j0 + tx * 4 + b] : 0.f;
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) s[a][b] *= scale;
+    for (int b = 0; b < 4; ++b) s[a][b] = (float)(acc[a][b] * ((double)scale * (double)rx[a] * (double)ry[b]));
 }
 
 // Forward statistics: per-tile (max, sumexp) partials for rows and columns + the diagonal.
 // grid = (col tiles, row tiles).  row_pm/pl: [n_jt][n_rows];  col_pm/pl: [n_it][n_cols].
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-fwd_stats(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows, int64_t n_cols, int d,
-          int64_t diag_offset, float scale, float* __restrict__ row_pm, float* __restrict__ row_pl,
+fwd_stats(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ rinv_x,
+          const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, float* __restrict__ row_pm, float* __restrict__ row_pl,
           float* __restrict__ col_pm, float* __restrict__ col_pl, float* __restrict__ diag) {
   __shared__ float Xs[KT][TILE + 1];
   __shared__ float Ys[KT][TILE + 1];
@@ -70,7 +79,7 @@ fwd_stats(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows, int6
   const int64_t j0 = (int64_t)blockIdx.x * TILE, i0 = (int64_t)blockIdx.y * TILE;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float s[4][4];
-  logits_tile<T>(x, y, n_rows, n_cols, d, i0, j0, scale, s, Xs, Ys);
+  logits_tile<T>(x, y, rinv_x, rinv_y, n_rows, n_cols, d, i0, j0, scale, s, Xs, Ys);
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -106,13 +115,13 @@ fwd_stats(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows, int6
   }
 }
 
-// Backward, one side: dx[i0:i0+64, dd0:dd0+64] = out_scale * sum_j G_ij y_j with
+// Backward, one side: dx[i0:i0+64, dd0:dd0+64] = out_scale * sum_j G_ij rinv_y[j] y_j with
 // G_ij = exp(S_ij + lu_i) + exp(S_ij + lv_j) - diag_w [j == i + diag_offset].
 // grid = (d tiles, row tiles); the x == 0 column of blocks also emits sum G.S partials.
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-bwd_side(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows, int64_t n_cols, int d,
-         int64_t diag_offset, float scale, const float* __restrict__ log_u, const float* __restrict__ log_v,
+bwd_side(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ rinv_x,
+         const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, const float* __restrict__ log_u, const float* __restrict__ log_v,
          float diag_w, float out_scale, float* __restrict__ dx, float* __restrict__ ds_part) {
   __shared__ float Xs[KT][TILE + 1];
   __shared__ float Ys[KT][TILE + 1];
@@ -136,11 +145,12 @@ bwd_side(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows, int64
   float ds = 0.f;
   for (int64_t j0 = 0; j0 < n_cols; j0 += TILE) {
     float s[4][4];
-    logits_tile<T>(x, y, n_rows, n_cols, d, i0, j0, scale, s, Xs, Ys);
+    logits_tile<T>(x, y, rinv_x, rinv_y, n_rows, n_cols, d, i0, j0, scale, s, Xs, Ys);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       int64_t gj = j0 + tx * 4 + b;
       float lv = (log_v != nullptr && gj < n_cols) ? log_v[gj] : -INFINITY;
+      const float ryj = (gj < n_cols) ? rinv_y[gj] : 0.f;
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         int64_t gi = i0 + ty * 4 + a;
@@ -150,7 +160,7 @@ bwd_side(const T* __restrict__ x, const T* __restrict__ y, int64_t n_rows, int64
           if (gj == gi + diag_offset) g -= diag_w;
           ds = fmaf(g, s[a][b], ds);
         }
-        Gs[ty * 4 + a][tx * 4 + b] = g;
+        Gs[ty * 4 + a][tx * 4 + b] = g * ryj;   // dXhat = s * sum_j G_ij (rinv_y[j] y_j)
       }
     }
     // stage Y[j0:j0+64, dd0:dd0+64]

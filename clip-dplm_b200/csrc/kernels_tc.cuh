@@ -44,7 +44,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr int BWD_S_COL0 = 384;                      // S buffers of MODE 1 live at TMEM columns 384..511
-constexpr int SMALL_BYTES = 3072;                    // barriers, tmem pointer, u_i, reduction scratch
+constexpr int SMALL_BYTES = 3584;                    // barriers, tmem pointer, u_i / rinv_i, reduction scratch
 constexpr int SMEM_LIMIT = 232448;                   // 227 KiB opt-in maximum per CTA
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -58,6 +58,8 @@ struct Params {
   long long diag_offset;
   float scale;     // s
   float k2;        // s * log2(e)
+  const float* rinv_x;   // [n_rows]  1 / |x_i|   (the normalise, applied to the fp32 accumulator)
+  const float* rinv_y;   // [n_cols]
   // MODE 0 outputs
   float* row_lse;      // [n_rows]           s + log sum_j exp(S_ij - s)
   float* col_part;     // [2 * gridDim.x][col_ld]  partial sum_i exp(S_ij - s)
@@ -126,8 +128,9 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   constexpr int B_FULL = 0, B_EMPTY = MAX_STAGES, B_XFULL = 2 * MAX_STAGES, B_SFULL = B_XFULL + 1,
                 B_SEMPTY = B_SFULL + 2, B_GFULL = B_SEMPTY + 2, B_GEMPTY = B_GFULL + 2, B_ACCFULL = B_GEMPTY + 2;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + small_off + 256);
-  float* const u_s = reinterpret_cast<float*>(smem + small_off + 512);     // [BLOCK_I]
-  float* const red = reinterpret_cast<float*>(smem + small_off + 1024);    // [8][64]
+  float* const rx_s = reinterpret_cast<float*>(smem + small_off + 512);    // [BLOCK_I] rinv_x of the resident rows
+  float* const u_s = reinterpret_cast<float*>(smem + small_off + 1024);    // [BLOCK_I] (MODE 1)
+  float* const red = reinterpret_cast<float*>(smem + small_off + 1536);    // [8][64]
 
   const int warp = threadIdx.x >> 5;   // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -264,6 +267,13 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const long long dcol0 = (long long)i0 + p.diag_offset;   // column of the positive of block row 0
 
+    if (te < BLOCK_I) {
+      rx_s[te] = (te < i_valid) ? p.rinv_x[i0 + te] : 0.f;
+      // u_i = exp(log_u_i + s): with exp(S - s) <= 1 it gives exp(S + log_u_i) from ONE ex2 per logit
+      if (MODE == 1) u_s[te] = (te < i_valid) ? ex2((p.log_u[i0 + te] + p.scale) * LOG2E) : 0.f;
+    }
+    epi_bar_sync();
+
     if (MODE == 0) {
       float racc[HALF];
 #pragma unroll
@@ -275,6 +285,8 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
+        const float ryj = jvalid ? p.rinv_y[jg] : 0.f;
+        const float cj = ryj * p.k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
         float csum = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -290,15 +302,22 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int ibase = h * HALF + c * 32;
             if (i_valid == BLOCK_I) {
 #pragma unroll
-              for (int x = 0; x < 32; ++x) {
-                const float ev = ex2(fmaf(__uint_as_float(r[x]), p.k2, -p.k2));
-                racc[c * 32 + x] += ev;
-                csum += ev;
+              for (int x4 = 0; x4 < 8; ++x4) {
+                const float4 rx4 = *reinterpret_cast<const float4*>(rx_s + ibase + x4 * 4);
+                const float rxv[4] = {rx4.x, rx4.y, rx4.z, rx4.w};
+#pragma unroll
+                for (int xx = 0; xx < 4; ++xx) {
+                  const int x = x4 * 4 + xx;
+                  const float ev = ex2(fmaf(__uint_as_float(r[x]) * rxv[xx], cj, -p.k2));
+                  racc[c * 32 + x] += ev;
+                  csum += ev;
+                }
               }
             } else {
 #pragma unroll
               for (int x = 0; x < 32; ++x) {
-                const float ev = (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]), p.k2, -p.k2)) : 0.f;
+                const float ev =
+                    (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]) * rx_s[ibase + x], cj, -p.k2)) : 0.f;
                 racc[c * 32 + x] += ev;
                 csum += ev;
               }
@@ -307,7 +326,8 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               const long long id = jg - dcol0 - ibase;   // TMEM column (within this load) holding S_{i,i+off}
 #pragma unroll
               for (int x = 0; x < 32; ++x)
-                if (id == x && ibase + x < i_valid) p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * p.scale;
+                if (id == x && ibase + x < i_valid)
+                  p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * rx_s[ibase + x] * ryj * p.scale;
             }
           }
         }
@@ -325,9 +345,6 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (te < i_valid) p.row_lse[i0 + te] = p.scale + logf(tot);
       }
     } else {
-      // u_i = exp(log_u_i + s): with exp(S - s) <= 1 it gives exp(S + log_u_i) from ONE ex2 per logit
-      if (te < BLOCK_I) u_s[te] = (te < i_valid) ? ex2((p.log_u[i0 + te] + p.scale) * LOG2E) : 0.f;
-      epi_bar_sync();
       float ds = 0.f;
       for (int t = 0; t < p.n_jt; ++t) {
         const int b = t & 1;
@@ -343,6 +360,8 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
         const float vj = (jvalid && p.log_v != nullptr) ? ex2((p.log_v[jg] + p.scale) * LOG2E) : 0.f;
+        const float ryj = jvalid ? p.rinv_y[jg] : 0.f;
+        const float cj = ryj * p.k2;
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
         const bool plain = jvalid && (i_valid == BLOCK_I) && !diag_tile;
         const long long id = jg - dcol0 - h * 32;
@@ -353,7 +372,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           const int i = h * 32 + x;
-          const float y = __uint_as_float(r[x]) * p.k2;      // S_ij * log2(e)
+          const float y = __uint_as_float(r[x]) * rx_s[i] * cj;      // S_ij * log2(e)
           float g = ex2(y - p.k2) * (u_s[i] + vj);
           if (!plain) {
             if (id == x) g -= p.diag_w;
@@ -361,7 +380,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           ds = fmaf(g, y, ds);
           const uint32_t addr = g_row0 + (i >> 3) * 1024 + (i & 7) * 128 + ((((jj >> 3) ^ (i & 7))) << 4);
-          const __nv_bfloat16 gb = __float2bfloat16_rn(g);
+          const __nv_bfloat16 gb = __float2bfloat16_rn(g * ryj);   // contracted against the RAW y_j
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&gb)) : "memory");
         }
         ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)

@@ -22,8 +22,13 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def padded_ld(n: int) -> int:
+    """Leading dimension of a transposed operand [d, ld]: rows stay 128-byte aligned for TMA."""
+    return (n + 63) // 64 * 64
+
+
 class CudaEngine:
-    """One instance per device; caches the scratch workspace per shape."""
+    """One instance per process; caches the scratch workspace per shape and stream."""
 
     name = "cuda"
 
@@ -58,59 +63,62 @@ class CudaEngine:
         return ws
 
     # ------------------------------------------------------------------ stages
-    def normalize(self, x, out_dtype, want_t=False):
-        """-> (x_hat [n,d], x_hat_t [d,ld] or None, rinv [n])   (F.normalize, old/clip.py:63-64)"""
+    def normalize(self, x, want_hat=None):
+        """-> (rinv [n] f32, x_hat [n,d] in dtype `want_hat` or None)   (F.normalize, old/clip.py:63-64)"""
         self._chk(x, (torch.bfloat16, torch.float32), "embedding")
         n, d = x.shape
-        xh = torch.empty((n, d), dtype=out_dtype, device=x.device)
         rinv = torch.empty((n,), dtype=torch.float32, device=x.device)
+        xh = torch.empty((n, d), dtype=want_hat, device=x.device) if want_hat is not None else None
+        _lib.check(self.lib.clipnce_normalize(_p(x), _DT[x.dtype], n, d, _p(rinv), _p(xh),
+                                              _DT[want_hat] if want_hat is not None else 0, _stream()), "normalize")
+        return rinv, xh
+
+    def stage(self, x, c_dtype, want_t=False):
+        """-> (x_c [n,d] raw rows in the compute dtype (x itself when it already has it),
+               x_c_t [d,ld] transposed copy or None)"""
+        self._chk(x, (torch.bfloat16, torch.float32), "embedding")
+        n, d = x.shape
+        xc = x if x.dtype == c_dtype else torch.empty((n, d), dtype=c_dtype, device=x.device)
         xt, ld = None, 0
         if want_t:
-            ld = (n + 63) // 64 * 64
-            xt = torch.empty((d, ld), dtype=out_dtype, device=x.device)
-        _lib.check(self.lib.clipnce_normalize(_p(x), _DT[x.dtype], n, d, _p(xh), _p(xt), ld, _DT[out_dtype], _p(rinv),
-                                              _stream()), "normalize")
-        return xh, xt, rinv
+            ld = padded_ld(n)
+            xt = torch.empty((d, ld), dtype=c_dtype, device=x.device)
+        if xc is not x or xt is not None:
+            _lib.check(self.lib.clipnce_stage_operand(_p(x), _DT[x.dtype], n, d, _p(xc) if xc is not x else None, _p(xt),
+                                                      ld, _DT[c_dtype], _stream()), "stage_operand")
+        return xc, xt
 
-    def transpose(self, xh):
-        self._chk(xh, (torch.bfloat16, torch.float32), "normalised embedding")
-        n, d = xh.shape
-        ld = (n + 63) // 64 * 64
-        xt = torch.empty((d, ld), dtype=xh.dtype, device=xh.device)
-        _lib.check(self.lib.clipnce_transpose(_p(xh), n, d, _p(xt), ld, _DT[xh.dtype], _stream()), "transpose")
-        return xt
-
-    def forward(self, x_hat, y_hat, diag_offset, scale, flags=0):
+    def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0):
         """-> row_lse [n_rows], col_m [n_cols], col_l [n_cols], diag [n_rows]"""
-        self._chk(x_hat, (torch.bfloat16, torch.float32), "x_hat")
-        self._chk(y_hat, (x_hat.dtype,), "y_hat")
-        n_rows, d = x_hat.shape
-        n_cols = y_hat.shape[0]
-        dev = x_hat.device
-        ws = self.workspace(n_rows, n_cols, d, x_hat.dtype, flags, dev)
+        self._chk(x, (torch.bfloat16, torch.float32), "x")
+        self._chk(y, (x.dtype,), "y")
+        n_rows, d = x.shape
+        n_cols = y.shape[0]
+        dev = x.device
+        ws = self.workspace(n_rows, n_cols, d, x.dtype, flags, dev)
         row_lse = torch.empty(n_rows, dtype=torch.float32, device=dev)
         col_m = torch.empty(n_cols, dtype=torch.float32, device=dev)
         col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
         diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
-        _lib.check(self.lib.clipnce_forward(_p(x_hat), _p(y_hat), n_rows, n_cols, d, int(diag_offset), float(scale),
-                                            _DT[x_hat.dtype], flags, _p(row_lse), _p(col_m), _p(col_l), _p(diag),
-                                            _p(ws), ws.numel(), _stream()), "forward")
+        _lib.check(self.lib.clipnce_forward(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n_rows, n_cols, d, int(diag_offset),
+                                            float(scale), _DT[x.dtype], flags, _p(row_lse), _p(col_m), _p(col_l),
+                                            _p(diag), _p(ws), ws.numel(), _stream()), "forward")
         return row_lse, col_m, col_l, diag
 
-    def backward(self, x_hat, y_hat, y_hat_t, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
+    def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
                  want_dscale=True):
         """-> dx_hat [n_rows,d] f32, d_scale_sum [1] f32 (or None)"""
-        n_rows, d = x_hat.shape
-        n_cols = y_hat.shape[0]
-        dev = x_hat.device
-        ws = self.workspace(n_rows, n_cols, d, x_hat.dtype, flags, dev)
+        n_rows, d = x.shape
+        n_cols = y.shape[0]
+        dev = x.device
+        ws = self.workspace(n_rows, n_cols, d, x.dtype, flags, dev)
         dx = torch.empty((n_rows, d), dtype=torch.float32, device=dev)
         ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
-        ld_t = y_hat_t.shape[1] if y_hat_t is not None else 0
-        _lib.check(self.lib.clipnce_backward(_p(x_hat), _p(y_hat), _p(y_hat_t), ld_t, n_rows, n_cols, d,
+        ld_t = y_t.shape[1] if y_t is not None else 0
+        _lib.check(self.lib.clipnce_backward(_p(x), _p(y), _p(y_t), ld_t, _p(rinv_x), _p(rinv_y), n_rows, n_cols, d,
                                              int(diag_offset), float(scale), _p(log_u), _p(log_v), float(diag_w),
-                                             float(grad_out), _DT[x_hat.dtype], flags, _p(dx), _p(ds), _p(ws),
-                                             ws.numel(), _stream()), "backward")
+                                             float(grad_out), _DT[x.dtype], flags, _p(dx), _p(ds), _p(ws), ws.numel(),
+                                             _stream()), "backward")
         return dx, ds
 
     def log_weights(self, lse, log_coef):
@@ -126,8 +134,8 @@ class CudaEngine:
     def normalize_backward(self, x, rinv, dx_hat, out_dtype, grad_scale=None):
         n, d = x.shape
         dx = torch.empty((n, d), dtype=out_dtype, device=x.device)
-        _lib.check(self.lib.clipnce_normalize_backward(_p(x), _DT[x.dtype], _p(rinv), _p(dx_hat), _p(grad_scale), n, d, _p(dx),
-                                                       _DT[out_dtype], _stream()), "normalize_backward")
+        _lib.check(self.lib.clipnce_normalize_backward(_p(x), _DT[x.dtype], _p(rinv), _p(dx_hat), _p(grad_scale), n, d,
+                                                       _p(dx), _DT[out_dtype], _stream()), "normalize_backward")
         return dx
 
     def loss(self, row_lse, col_lse, diag, diag_offset, n_global, symmetric):

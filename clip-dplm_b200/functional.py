@@ -33,7 +33,7 @@ class _FusedClipLoss(torch.autograd.Function):
         t, s, clamped = _scale_value(logit_scale, scale_is_log, clamp_max)
         need_grad = a.requires_grad or b.requires_grad or (torch.is_tensor(logit_scale) and logit_scale.requires_grad)
         loss, st = _step.contrastive_forward(engine, a.detach().contiguous(), b.detach().contiguous(), s,
-                                             symmetric=symmetric, extra_hat=extra, group=group,
+                                             symmetric=symmetric, extra=extra, group=group,
                                              compute_dtype=compute_dtype, flags=flags, need_grad=need_grad)
         ctx.st, ctx.engine = st, engine
         ctx.scale_info = (s, clamped, scale_is_log)

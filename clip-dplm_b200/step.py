@@ -53,14 +53,15 @@ def _reduce_scatter_rows(x, group):
 
 @dataclass
 class StepState:
-    a: torch.Tensor
+    a: torch.Tensor                 # caller's embeddings (for the normalise backward)
     b: torch.Tensor
-    a_hat: torch.Tensor
-    a_hat_t: Optional[torch.Tensor]
-    y_hat: torch.Tensor            # all columns: gathered B (+ extra negatives)
-    y_hat_t: Optional[torch.Tensor]
+    a_c: torch.Tensor               # raw rows in the compute dtype
+    a_c_t: Optional[torch.Tensor]
+    y: torch.Tensor                 # all columns: gathered B (+ extra negatives), raw, compute dtype
+    y_t: Optional[torch.Tensor]
     rinv_a: torch.Tensor
     rinv_b: torch.Tensor
+    rinv_y: torch.Tensor
     row_lse: torch.Tensor
     col_lse: torch.Tensor
     diag: torch.Tensor
@@ -73,7 +74,7 @@ class StepState:
     group: object
 
 
-def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra_hat=None, group=None,
+def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra=None, group=None,
                         compute_dtype=torch.bfloat16, flags=0, need_grad=True):
     """Returns (loss [1] f32 -- the GLOBAL mean loss, identical on every rank --, StepState)."""
     if a.dim() != 2 or b.dim() != 2 or a.shape != b.shape:
@@ -86,17 +87,21 @@ def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra_hat
 
     tc = engine.uses_tensor_cores(compute_dtype, a.shape[1], scale, flags)
     want_t = need_grad and tc
-    a_hat, a_hat_t, rinv_a = engine.normalize(a, compute_dtype, want_t=want_t)
-    b_hat, b_hat_t, rinv_b = engine.normalize(b, compute_dtype, want_t=want_t and world == 1 and extra_hat is None)
-    y_hat, y_hat_t = b_hat, b_hat_t
+    rinv_a, _ = engine.normalize(a)
+    rinv_b, _ = engine.normalize(b)
+    a_c, a_c_t = engine.stage(a, compute_dtype, want_t=want_t)
+    b_c, b_c_t = engine.stage(b, compute_dtype, want_t=want_t and world == 1 and extra is None)
+    y, y_t, rinv_y = b_c, b_c_t, rinv_b
     if world > 1:
-        y_hat = _all_gather_rows(b_hat, group)
-    if extra_hat is not None:
-        y_hat = torch.cat([y_hat, extra_hat.detach().to(compute_dtype)], dim=0).contiguous()
-    if want_t and y_hat_t is None:
-        y_hat_t = engine.transpose(y_hat)
+        y = _all_gather_rows(b_c, group)
+        rinv_y = _all_gather_rows(rinv_b, group)
+    if extra is not None:   # used as stored (old/clip_opt.py:118-121, tong/utils/losses.py:10-11): rinv = 1
+        y = torch.cat([y, extra.detach().to(compute_dtype)], dim=0).contiguous()
+        rinv_y = torch.cat([rinv_y, torch.ones(extra.shape[0], dtype=rinv_y.dtype, device=rinv_y.device)])
+    if want_t and y_t is None:
+        _, y_t = engine.stage(y, compute_dtype, want_t=True)
 
-    row_lse, col_m, col_l, diag = engine.forward(a_hat, y_hat, diag_offset, scale, flags)
+    row_lse, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags)
     if world > 1:
         m_max = col_m.clone()
         dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=group)
@@ -105,12 +110,12 @@ def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra_hat
         col_lse = m_max + torch.log(l)
     else:
         col_lse = engine.combine_lse(col_m, col_l)
-    if y_hat.shape[0] > n_global:
+    if y.shape[0] > n_global:
         col_lse[n_global:] = float("inf")   # extra negatives carry no positives: no column loss, no column soft-max
     loss = engine.loss(row_lse, col_lse, diag, diag_offset, n_global, symmetric)
     if world > 1:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-    st = StepState(a, b, a_hat, a_hat_t, y_hat, y_hat_t, rinv_a, rinv_b, row_lse, col_lse, diag, scale, symmetric,
+    st = StepState(a, b, a_c, a_c_t, y, y_t, rinv_a, rinv_b, rinv_y, row_lse, col_lse, diag, scale, symmetric,
                    n_local, n_global, diag_offset, flags, group)
     return loss, st
 
@@ -130,12 +135,12 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     diag_w = 1.0 / n_glob
 
     # side 1: local rows x all columns -> dA_hat (complete) and sum G.S over the local row block
-    da_hat, ds = engine.backward(st.a_hat, st.y_hat, st.y_hat_t, st.diag_offset, st.scale, log_u, log_v, diag_w, 1.0,
-                                 st.flags, want_dscale=True)
+    da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, st.diag_offset, st.scale, log_u, log_v,
+                                 diag_w, 1.0, st.flags, want_dscale=True)
     # side 2: the positive-carrying columns as rows x local rows as columns -> partial dB_hat [N,d]
-    y_main = st.y_hat[:n_glob]
-    db_part, _ = engine.backward(y_main, st.a_hat, st.a_hat_t, -st.diag_offset, st.scale, log_v[:n_glob].contiguous(),
-                                 log_u, diag_w, 1.0, st.flags, want_dscale=False)
+    db_part, _ = engine.backward(st.y[:n_glob], st.a_c, st.a_c_t, st.rinv_y[:n_glob].contiguous(), st.rinv_a,
+                                 -st.diag_offset, st.scale, log_v[:n_glob].contiguous(), log_u, diag_w, 1.0, st.flags,
+                                 want_dscale=False)
     if world > 1:
         db_hat = _reduce_scatter_rows(db_part, st.group)
         dist.all_reduce(ds, op=dist.ReduceOp.SUM, group=st.group)

@@ -56,43 +56,49 @@ int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags);
 int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, int flags, size_t* out);
 
 /*
- * L2-normalise rows.  Replaces F.normalize(x, dim=-1):
+ * Row norms (and, optionally, the normalised rows).  Replaces F.normalize(x, dim=-1):
  *   old/clip.py:63-64,100-101  run1/full.py:47-48,73-74  old/clip_opt.py:93-94
  *   current/rna_clip_codes.ipynb:1948-1949  current/tf_clip_codes (1).ipynb:13146-13148
  *   tong/utils/losses.py:6-7
- * x        [n,d]  in_dtype (BF16 or F32)
- * x_hat    [n,d]  out_dtype            normalised rows (what the reference returns as "*_embeds")
- * x_hat_t  [d,ld_t] out_dtype or NULL  the same matrix transposed (ld_t >= n, ld_t % 8 == 0); the
- *                                      tensor-core backward streams it as its second MMA operand
- * rinv     [n]    f32                  1 / max(|x_i|, 1e-12)
+ * x      [n,d]  in_dtype (BF16 or F32)
+ * rinv   [n]    f32   1 / max(|x_i|, 1e-12)
+ * x_hat  [n,d]  hat_dtype or NULL: normalised rows (what the reference returns as "*_embeds").
+ * The contraction kernels do NOT consume x_hat: they take the raw rows plus rinv and apply
+ * rinv_x[i] * rinv_y[j] to the fp32 accumulator ("normalise fused into the GEMM"), so the
+ * tensor cores see the caller's exact bf16 values and no second rounding enters the logits.
  */
-int clipnce_normalize(const void* x, int in_dtype, int64_t n, int64_t d,
-                      void* x_hat, void* x_hat_t, int64_t ld_t, int out_dtype,
-                      float* rinv, void* stream);
-
-/* Transpose an already-normalised [n,d] matrix into [d,ld_t] (used after the all-gather of
- * normalised embeddings, old/clip_opt.py:102-112 / run1/full.py:77-84). */
-int clipnce_transpose(const void* x_hat, int64_t n, int64_t d, void* x_hat_t, int64_t ld_t,
-                      int dtype, void* stream);
+int clipnce_normalize(const void* x, int in_dtype, int64_t n, int64_t d, float* rinv,
+                      void* x_hat, int hat_dtype, void* stream);
 
 /*
- * Forward statistics of S = s * Xhat Yhat^T without materialising S.  Replaces
+ * Operand staging for the contraction kernels: x_c = x converted to c_dtype ([n,d], or NULL when x
+ * already has that type) and x_c_t = the same values transposed ([d,ld_t], ld_t >= n, ld_t % 8 == 0,
+ * or NULL).  The tensor-core backward streams the transposed copy as its second MMA operand; it is
+ * also what is built from the all-gathered embeddings (old/clip_opt.py:102-112, run1/full.py:77-84).
+ */
+int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, void* x_c, void* x_c_t,
+                          int64_t ld_t, int c_dtype, void* stream);
+
+/*
+ * Forward statistics of S_ij = s * rinv_x[i] rinv_y[j] <x_i, y_j> without materialising S.  Replaces
  *   torch.matmul(a, b.t()) * logit_scale            old/clip.py:67,104  run1/full.py:50,85
  *                                                   old/clip_opt.py:115-121  rna_clip_codes.ipynb:1951
  *                                                   tf_clip_codes (1).ipynb:13152-13154  tong/utils/losses.py:14
  *   F.cross_entropy(S, arange) / F.cross_entropy(S.t(), arange)   (the log-sum-exp halves of it)
  *                                                   rna_clip_codes.ipynb:1952-1953  old/clip_opt.py:148-149
  *                                                   run1/full.py:98-99,133  tong/utils/losses.py:17-19
- * x_hat [n_rows,d], y_hat [n_cols,d]   rows local to this rank / all (gathered) columns
+ * x [n_rows,d], y [n_cols,d]   raw rows in `dtype`: the rows local to this rank / all (gathered) columns
+ * rinv_x [n_rows], rinv_y [n_cols]   from clipnce_normalize
  * diag_offset   column of row 0's positive: the positive of local row i is column i + diag_offset
  *               (0 on one GPU, rank * n_rows under the row-sharded global batch)
  * scale         s = exp(logit_scale), already clamped by the caller (old/clip_opt.py:100)
  * row_lse [n_rows]  r_i, complete (every column is seen locally)
- * col_m, col_l [n_cols]  partial column statistics over the LOCAL rows: c_j = col_m_j + log(sum over
- *               ranks of col_l_j * exp(col_m_j - max col_m_j)); on one GPU c_j = col_m_j + log col_l_j
+ * col_m, col_l [n_cols]  partial column statistics over the LOCAL rows: c_j = M_j + log(sum over
+ *               ranks of col_l_j * exp(col_m_j - M_j)), M_j = max over ranks of col_m_j
  * diag [n_rows]     S_{i, i+diag_offset}
  */
-int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_t n_cols, int64_t d,
+int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
+                    int64_t n_rows, int64_t n_cols, int64_t d,
                     int64_t diag_offset, float scale, int dtype, int flags,
                     float* row_lse, float* col_m, float* col_l, float* diag,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -102,18 +108,19 @@ int clipnce_forward(const void* x_hat, const void* y_hat, int64_t n_rows, int64_
  * rna_clip_codes.ipynb:2074, run1/full.py:134, old/clip_opt.py:167, old/ablation.py:16-17).
  * The logit tiles are recomputed; with
  *     G_ij = exp(S_ij + log_u_i) + exp(S_ij + log_v_j) - diag_w * [j == i + diag_offset]
- * it returns  dx_hat = grad_out * s * G Yhat  ([n_rows,d] f32)  and
+ * it returns  dx_hat = grad_out * s * G Yhat  ([n_rows,d] f32; Yhat_j = rinv_y[j] y_j)  and
  *             *d_scale_sum += grad_out * sum_ij G_ij S_ij   (= dL/dlogit_scale when s = exp(logit_scale)).
  * Symmetric InfoNCE over a global batch N:
  *     log_u_i = -log(2N) - r_i,  log_v_j = -log(2N) - c_j,  diag_w = 1/N
  * one-directional (run1/full.py:133, tong/utils/losses.py:19): log_u_i = -log(N) - r_i, log_v = NULL.
  * Columns without positives (hard-negative cache, old/clip_opt.py:118-121) carry log_v_j = -inf.
- * Call it once as (Ahat, Bhat, Bhat^T, log_u, log_v, +offset) for dAhat and once as
- * (Bhat, Ahat, Ahat^T, log_v, log_u, -offset) for dBhat.
- * y_hat_t [d,ld_t] is only read by the tensor-core path (may be NULL for the exact path).
+ * Call it once as (A, B, B^T, rinv_a, rinv_b, log_u, log_v, +offset) for dAhat and once as
+ * (B, A, A^T, rinv_b, rinv_a, log_v, log_u, -offset) for dBhat.
+ * y_t [d,ld_t] (clipnce_stage_operand) is only read by the tensor-core path (NULL for the exact path).
  * log_v and d_scale_sum may be NULL.
  */
-int clipnce_backward(const void* x_hat, const void* y_hat, const void* y_hat_t, int64_t ld_t,
+int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t,
+                     const float* rinv_x, const float* rinv_y,
                      int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
                      const float* log_u, const float* log_v, float diag_w, float grad_out,
                      int dtype, int flags, float* dx_hat, float* d_scale_sum,

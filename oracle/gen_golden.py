@@ -149,7 +149,7 @@ def main():
         ("n32_d128", 32, 128, None, True, O.LOGIT_SCALE_INIT, {}),                          # notebook batch 32
         ("ragged_n333_d192", 333, 192, None, True, O.LOGIT_SCALE_INIT, {}),
         ("d768_n192", 192, 768, None, True, O.LOGIT_SCALE_INIT, {}),                        # config 3 width
-        ("clamp100_n256_d128", 256, 128, None, True, 5.0, {"clamp_max": 100}),              # e^5 > 100 -> clamped
+        ("clamp100_n256_d128", 256, 128, None, True, 5.0, {"clamp_max": 100, "mix": 0.12}),  # e^5 > 100 -> clamped
         ("tong_t0p1_n256_d128", 256, 128, None, True, 10.0, {"symmetric": False, "scale_is_log": False}),
         ("onedir_n256_d128", 256, 128, None, True, O.LOGIT_SCALE_INIT, {"symmetric": False}),
         ("cache_n256_d128", 256, 128, 256 + 96, True, O.LOGIT_SCALE_INIT, {"clamp_max": 100, "cache": 96}),
@@ -157,7 +157,7 @@ def main():
     for name, n, d, n_cols, corr, ls, kw in cases:
         kw = dict(kw)
         n_cache = kw.pop("cache", 0)
-        a, b = O.make_inputs(n, d, seed=1234, correlated=corr, n_cols=n_cols)
+        a, b = O.make_inputs(n, d, seed=1234, correlated=corr, n_cols=n_cols, mix=kw.pop("mix", 0.5))
         extra = None
         if n_cache:
             extra = F.normalize(b[n:], dim=-1).to(torch.bfloat16).to(torch.float32)  # cache rows are stored normalised

@@ -140,7 +140,9 @@ def closed_form(a: np.ndarray, b: np.ndarray, scale: float, *, symmetric=True, n
 # Synthetic inputs shared by tests and bench.
 # ----------------------------------------------------------------------------------------------
 
-def make_inputs(n, d, seed=1234, correlated=True, dtype=torch.float32, round_bf16=True, n_cols=None):
+def make_inputs(n, d, seed=1234, correlated=True, dtype=torch.float32, round_bf16=True, n_cols=None, mix=0.5):
+    """a = randn; b = mix*a + (1-mix)*randn (positives on the diagonal) or b = randn; values are rounded
+    to bf16 once so the bf16 CUDA path and the fp32/fp64 reference see identical inputs."""
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(n, d, generator=g)
     m = n if n_cols is None else n_cols
@@ -148,7 +150,7 @@ def make_inputs(n, d, seed=1234, correlated=True, dtype=torch.float32, round_bf1
         nb = torch.randn(m, d, generator=g)
         b = nb.clone()
         k = min(n, m)
-        b[:k] = 0.5 * a[:k] + 0.5 * nb[:k]
+        b[:k] = mix * a[:k] + (1.0 - mix) * nb[:k]
     else:
         b = torch.randn(m, d, generator=g)
     if round_bf16:

@@ -21,28 +21,28 @@ class TorchCpuEngine:
     def uses_tensor_cores(self, dtype, d, scale, flags=0):
         return True   # so that step.py exercises the transposed-operand plumbing too
 
-    def normalize(self, x, out_dtype, want_t=False):
+    def normalize(self, x, want_hat=None):
         xf = x.to(self.dt)
         denom = xf.norm(dim=1).clamp_min(EPS)
-        xh = xf / denom[:, None]
-        n = x.shape[0]
+        xh = (xf / denom[:, None]).to(want_hat) if want_hat is not None else None
+        return 1.0 / denom, xh
+
+    def stage(self, x, c_dtype, want_t=False):
+        xc = x.to(self.dt)
         xt = None
         if want_t:
+            n = x.shape[0]
             ld = (n + 63) // 64 * 64
             xt = torch.zeros(x.shape[1], ld, dtype=self.dt)
-            xt[:, :n] = xh.t()
-        return xh, xt, (1.0 / denom)
+            xt[:, :n] = xc.t()
+        return xc, xt
 
-    def transpose(self, xh):
-        n = xh.shape[0]
-        ld = (n + 63) // 64 * 64
-        xt = torch.zeros(xh.shape[1], ld, dtype=xh.dtype)
-        xt[:, :n] = xh.t()
-        return xt
+    def _logits(self, x, y, rinv_x, rinv_y, scale):
+        return scale * ((x * rinv_x[:, None]) @ (y * rinv_y[:, None]).t())
 
-    def forward(self, x_hat, y_hat, diag_offset, scale, flags=0):
-        S = scale * (x_hat @ y_hat.t())
-        n = x_hat.shape[0]
+    def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0):
+        S = self._logits(x, y, rinv_x, rinv_y, scale)
+        n = x.shape[0]
         row_lse = torch.logsumexp(S, dim=1)
         col_m = S.max(dim=0).values
         col_l = torch.exp(S - col_m[None, :]).sum(dim=0)
@@ -50,11 +50,11 @@ class TorchCpuEngine:
         diag = S[idx, idx + diag_offset]
         return row_lse, col_m, col_l, diag
 
-    def backward(self, x_hat, y_hat, y_hat_t, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
+    def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
                  want_dscale=True):
-        if y_hat_t is not None:   # the transposed operand must be the same matrix
-            assert torch.equal(y_hat_t[:, :y_hat.shape[0]].t(), y_hat)
-        S = scale * (x_hat @ y_hat.t())
+        if y_t is not None:   # the transposed operand must be the same matrix
+            assert torch.equal(y_t[:, :y.shape[0]].t(), y)
+        S = self._logits(x, y, rinv_x, rinv_y, scale)
         G = torch.exp(S + log_u[:, None])
         if log_v is not None:
             G = G + torch.exp(S + log_v[None, :])
@@ -63,7 +63,7 @@ class TorchCpuEngine:
         j = i + diag_offset
         ok = (j >= 0) & (j < n_cols)
         G[i[ok], j[ok]] -= diag_w
-        dx = grad_out * scale * (G @ y_hat)
+        dx = grad_out * scale * (G @ (y * rinv_y[:, None]))
         ds = (grad_out * (G * S).sum()).reshape(1) if want_dscale else None
         return dx, ds
 

@@ -37,10 +37,12 @@ def check_aux():
     eng = CudaEngine()
     a, b, cf = setup(300, 192)
     for dt in (torch.bfloat16, torch.float32):
-        xh, xt, rinv = eng.normalize(a.cuda().to(dt), dt, want_t=True)
+        x = a.cuda().to(dt)
+        rinv, xh = eng.normalize(x, want_hat=dt)
+        xc, xt = eng.stage(a.cuda(), dt, want_t=True)
         torch.cuda.synchronize()
         print(f"normalize {dt}: xhat rel {rel(xh, cf['a_hat']):.2e} rinv rel {rel(rinv, cf['rinv_a']):.2e} "
-              f"xt ok {bool(torch.equal(xt[:, :300].t().contiguous(), xh))}")
+              f"stage ok {bool(torch.equal(xt[:, :300].t().contiguous(), xc))} conv ok {bool(torch.equal(xc, x))}")
 
 
 def check_exact(dtype_name="f32"):
@@ -50,9 +52,11 @@ def check_exact(dtype_name="f32"):
     dt = torch.float32 if dtype_name == "f32" else torch.bfloat16
     for (n, d, scale) in [(256, 128, 14.29), (333, 192, 14.29), (200, 64, 100.0)]:
         a, b, cf = setup(n, d, scale=scale)
-        ah, _, _ = eng.normalize(a.cuda(), dt)
-        bh, _, _ = eng.normalize(b.cuda(), dt)
-        row_lse, col_m, col_l, diag = eng.forward(ah, bh, 0, scale, flags=1)
+        ah, _ = eng.stage(a.cuda(), dt)
+        bh, _ = eng.stage(b.cuda(), dt)
+        ra, _ = eng.normalize(ah)
+        rb, _ = eng.normalize(bh)
+        row_lse, col_m, col_l, diag = eng.forward(ah, bh, ra, rb, 0, scale, flags=1)
         col_lse = eng.combine_lse(col_m, col_l)
         loss = eng.loss(row_lse, col_lse, diag, 0, n, True)
         torch.cuda.synchronize()
@@ -60,8 +64,8 @@ def check_exact(dtype_name="f32"):
               f"{rel(col_lse, cf['col_lse']):.2e} diag {rel(diag, cf['diag']):.2e} loss {float(loss):.6f} vs {cf['loss']:.6f}")
         lc = -math.log(2 * n)
         lu, lv = eng.log_weights(row_lse, lc), eng.log_weights(col_lse, lc)
-        da, ds = eng.backward(ah, bh, None, 0, scale, lu, lv, 1.0 / n, 1.0, flags=1)
-        db, _ = eng.backward(bh, ah, None, 0, scale, lv, lu, 1.0 / n, 1.0, flags=1, want_dscale=False)
+        da, ds = eng.backward(ah, bh, None, ra, rb, 0, scale, lu, lv, 1.0 / n, 1.0, flags=1)
+        db, _ = eng.backward(bh, ah, None, rb, ra, 0, scale, lv, lu, 1.0 / n, 1.0, flags=1, want_dscale=False)
         torch.cuda.synchronize()
         print(f"    d_a_hat {rel(da, cf['d_a_hat']):.2e} d_b_hat {rel(db, cf['d_b_hat']):.2e} dscale {float(ds):.6e} vs "
               f"{cf['d_scale_sum']:.6e}")
@@ -71,10 +75,12 @@ def _tc_case(eng, n, d, scale, n_cols=None, corr=True, bwd=True):
     import torch
     a, b, cf = setup(n, d, n_cols=n_cols, scale=scale, corr=corr)
     m = b.shape[0]
-    ah, aht, _ = eng.normalize(a.cuda().bfloat16(), torch.bfloat16, want_t=True)
-    bh, bht, _ = eng.normalize(b.cuda().bfloat16(), torch.bfloat16, want_t=True)
+    ah, aht = eng.stage(a.cuda().bfloat16(), torch.bfloat16, want_t=True)
+    bh, bht = eng.stage(b.cuda().bfloat16(), torch.bfloat16, want_t=True)
+    ra, _ = eng.normalize(ah)
+    rb, _ = eng.normalize(bh)
     assert eng.uses_tensor_cores(torch.bfloat16, d, scale)
-    row_lse, col_m, col_l, diag = eng.forward(ah, bh, 0, scale)
+    row_lse, col_m, col_l, diag = eng.forward(ah, bh, ra, rb, 0, scale)
     col_lse = eng.combine_lse(col_m, col_l)
     torch.cuda.synchronize()
     msg = (f"tc n={n} m={m} d={d} s={scale:.2f}: row_lse {rel(row_lse, cf['row_lse']):.2e} col_lse "
@@ -86,12 +92,12 @@ def _tc_case(eng, n, d, scale, n_cols=None, corr=True, bwd=True):
     print(msg, flush=True)
     if bwd and n == m:
         lc = -math.log(2 * n)
-        lu = eng.log_weights(torch.as_tensor(cf["row_lse"], dtype=torch.float32).cuda(), lc)
-        lv = eng.log_weights(torch.as_tensor(cf["col_lse"], dtype=torch.float32).cuda(), lc)
-        da, ds = eng.backward(ah, bh, bht, 0, scale, lu, lv, 1.0 / n, 1.0)
+        lu = eng.log_weights(row_lse, lc)
+        lv = eng.log_weights(col_lse, lc)
+        da, ds = eng.backward(ah, bh, bht, ra, rb, 0, scale, lu, lv, 1.0 / n, 1.0)
         torch.cuda.synchronize()
         print(f"    d_a_hat {rel(da, cf['d_a_hat']):.2e} dscale {float(ds):.6e} vs {cf['d_scale_sum']:.6e}", flush=True)
-        db, _ = eng.backward(bh, ah, aht, 0, scale, lv, lu, 1.0 / n, 1.0, want_dscale=False)
+        db, _ = eng.backward(bh, ah, aht, rb, ra, 0, scale, lv, lu, 1.0 / n, 1.0, want_dscale=False)
         torch.cuda.synchronize()
         print(f"    d_b_hat {rel(db, cf['d_b_hat']):.2e}", flush=True)
 
@@ -120,12 +126,19 @@ def check_tc_big():
     g = torch.Generator(device="cuda").manual_seed(1)
     a = torch.randn(n, d, device="cuda", generator=g).bfloat16()
     b = (0.5 * a.float() + 0.5 * torch.randn(n, d, device="cuda", generator=g)).bfloat16()
-    ah, aht, _ = eng.normalize(a, torch.bfloat16, want_t=True)
-    bh, bht, _ = eng.normalize(b, torch.bfloat16, want_t=True)
-    row_lse, col_m, col_l, diag = eng.forward(ah, bh, 0, scale)
+    ah, aht = eng.stage(a, torch.bfloat16, want_t=True)
+    bh, bht = eng.stage(b, torch.bfloat16, want_t=True)
+    ra, _ = eng.normalize(ah)
+    rb, _ = eng.normalize(bh)
+    for _ in range(2):
+        t0 = time.time()
+        row_lse, col_m, col_l, diag = eng.forward(ah, bh, ra, rb, 0, scale)
+        torch.cuda.synchronize()
+        print(f"    fwd wall {1e3 * (time.time() - t0):.2f} ms", flush=True)
     col_lse = eng.combine_lse(col_m, col_l)
     torch.cuda.synchronize()
-    S = scale * (ah.float() @ bh.float().t())
+    an, bn = ah.float() * ra[:, None], bh.float() * rb[:, None]
+    S = scale * (an @ bn.t())
     r_ref, c_ref = torch.logsumexp(S, 1), torch.logsumexp(S, 0)
     print(f"tc big n={n}: row_lse {rel(row_lse, r_ref):.2e} col_lse {rel(col_lse, c_ref):.2e} diag {rel(diag, S.diagonal()):.2e}",
           flush=True)
@@ -133,14 +146,14 @@ def check_tc_big():
     lu, lv = lc - r_ref, lc - c_ref
     G = torch.exp(S + lu[:, None]) + torch.exp(S + lv[None, :])
     G.diagonal().sub_(1.0 / n)
-    da_ref = scale * (G @ bh.float())
-    db_ref = scale * (G.t() @ ah.float())
+    da_ref = scale * (G @ bn)
+    db_ref = scale * (G.t() @ an)
     ds_ref = float((G * S).sum())
     del G, S
     for _ in range(2):
         t0 = time.time()
-        da, ds = eng.backward(ah, bh, bht, 0, scale, lu.contiguous(), lv.contiguous(), 1.0 / n, 1.0)
-        db, _ = eng.backward(bh, ah, aht, 0, scale, lv.contiguous(), lu.contiguous(), 1.0 / n, 1.0, want_dscale=False)
+        da, ds = eng.backward(ah, bh, bht, ra, rb, 0, scale, lu.contiguous(), lv.contiguous(), 1.0 / n, 1.0)
+        db, _ = eng.backward(bh, ah, aht, rb, ra, 0, scale, lv.contiguous(), lu.contiguous(), 1.0 / n, 1.0, want_dscale=False)
         torch.cuda.synchronize()
         print(f"    bwd wall {1e3 * (time.time() - t0):.2f} ms", flush=True)
     print(f"    d_a_hat {rel(da, da_ref):.2e} d_b_hat {rel(db, db_ref):.2e} dscale {float(ds):.5e} vs {ds_ref:.5e}", flush=True)
