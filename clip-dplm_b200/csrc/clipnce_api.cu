@@ -213,9 +213,10 @@ int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, voi
 }
 
 int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
-                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, int dtype, int flags, float* row_lse,
-                    float* col_m, float* col_l, float* diag, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x || !y || !rinv_x || !rinv_y || !row_lse || !col_m || !col_l || !diag || !workspace)
+                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, int dtype, int flags, float* row_m,
+                    float* row_l, float* col_m, float* col_l, float* diag, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_l || !col_m || !col_l || !diag || !workspace)
     return fail(CLIPNCE_EINVAL, "forward: null pointer");
   if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
     return fail(CLIPNCE_EINVAL, "forward: bad shape");
@@ -241,7 +242,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
     p.rinv_x = rinv_x; p.rinv_y = rinv_y;
-    p.row_lse = row_lse; p.col_part = reinterpret_cast<float*>(workspace); p.col_ld = col_ld; p.diag = diag;
+    p.row_m = row_m; p.row_l = row_l; p.col_part = reinterpret_cast<float*>(workspace); p.col_ld = col_ld; p.diag = diag;
     if (bi == 128) rc = launch_tc<0, 128>(0, tx, ty, ty, p, (int)n_ib, st);
     else           rc = launch_tc<0, 64>(1, tx, ty, ty, p, (int)n_ib, st);
     if (rc) return rc;
@@ -266,19 +267,21 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
                                                      diag);
   CUDA_TRY(cudaGetLastError());
   aux::reduce_ml_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(w.row_pm, w.row_pl, (int)w.n_jt, n_rows,
-                                                                             n_rows, 0, row_lse, nullptr);
+                                                                             n_rows, row_m, row_l);
   aux::reduce_ml_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(w.col_pm, w.col_pl, (int)w.n_it, n_cols,
-                                                                             n_cols, 1, col_m, col_l);
+                                                                             n_cols, col_m, col_l);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
                      const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
-                     const float* log_u, const float* log_v, float diag_w, float grad_out, int dtype, int flags,
-                     float* dx_hat, float* d_scale_sum, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x || !y || !rinv_x || !rinv_y || !log_u || !dx_hat || !workspace)
+                     const float* row_m, const float* row_w, const float* col_m, const float* col_w, float diag_w,
+                     float grad_out, int dtype, int flags, float* dx_hat, float* d_scale_sum, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !dx_hat || !workspace)
     return fail(CLIPNCE_EINVAL, "backward: null pointer");
+  if ((col_m == nullptr) != (col_w == nullptr)) return fail(CLIPNCE_EINVAL, "backward: col_m and col_w go together");
   if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
     return fail(CLIPNCE_EINVAL, "backward: bad shape");
   if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "backward: bad dtype %d", dtype);
@@ -305,7 +308,7 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
     p.rinv_x = rinv_x; p.rinv_y = rinv_y;
-    p.log_u = log_u; p.log_v = log_v; p.diag_w = diag_w; p.out_scale = grad_out * scale;
+    p.row_m_in = row_m; p.row_w = row_w; p.col_m_in = col_m; p.col_w = col_w; p.diag_w = diag_w; p.out_scale = grad_out * scale;
     p.dx = dx_hat; p.ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
     if ((rc = launch_tc<1, 64>(2, tx, ty, tyt, p, (int)n_ib, st))) return rc;
     if (d_scale_sum) {
@@ -323,12 +326,12 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
   dim3 grid((unsigned)ceil_div(d, simt::TILE), (unsigned)n_it);
   if (dtype == CLIPNCE_BF16)
     simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y,
-                                                    n_rows, n_cols, (int)d, diag_offset, scale, log_u, log_v, diag_w,
-                                                    grad_out * scale, dx_hat, ds_part);
+                                                    n_rows, n_cols, (int)d, diag_offset, scale, row_m, row_w, col_m, col_w,
+                                                    diag_w, grad_out * scale, dx_hat, ds_part);
   else
     simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const float*)x, (const float*)y, rinv_x, rinv_y, n_rows, n_cols,
-                                                    (int)d, diag_offset, scale, log_u, log_v, diag_w, grad_out * scale,
-                                                    dx_hat, ds_part);
+                                                    (int)d, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w,
+                                                    grad_out * scale, dx_hat, ds_part);
   CUDA_TRY(cudaGetLastError());
   if (d_scale_sum) {
     aux::reduce_scalar_partials<<<1, 32, 0, st>>>(ds_part, (int)n_it, grad_out, d_scale_sum);
@@ -337,9 +340,9 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
   return 0;
 }
 
-int clipnce_log_weights(const float* lse, int64_t n, float log_coef, float* out, void* stream) {
-  if (!lse || !out || n < 1) return fail(CLIPNCE_EINVAL, "log_weights: bad argument");
-  aux::log_weights<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(lse, n, log_coef, out);
+int clipnce_softmax_weights(const float* l, int64_t n, float coef, float* w, void* stream) {
+  if (!l || !w || n < 1) return fail(CLIPNCE_EINVAL, "softmax_weights: bad argument");
+  aux::softmax_weights<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(l, n, coef, w);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -372,12 +375,13 @@ int clipnce_normalize_backward(const void* x, int in_dtype, const float* rinv, c
   return 0;
 }
 
-int clipnce_loss(const float* row_lse, const float* col_lse, const float* diag, int64_t n_rows, int64_t diag_offset,
-                 int64_t n_global, int symmetric, float* loss, void* stream) {
-  if (!row_lse || !diag || !loss || n_rows < 1 || n_global < 1) return fail(CLIPNCE_EINVAL, "loss: bad argument");
-  if (symmetric && !col_lse) return fail(CLIPNCE_EINVAL, "loss: symmetric loss needs col_lse");
+int clipnce_loss(const float* row_m, const float* row_l, const float* col_m, const float* col_l, const float* diag,
+                 int64_t n_rows, int64_t diag_offset, int64_t n_global, int symmetric, float* loss, void* stream) {
+  if (!row_m || !row_l || !diag || !loss || n_rows < 1 || n_global < 1) return fail(CLIPNCE_EINVAL, "loss: bad argument");
+  if (symmetric && (!col_m || !col_l)) return fail(CLIPNCE_EINVAL, "loss: symmetric loss needs column statistics");
   const double inv = 1.0 / ((symmetric ? 2.0 : 1.0) * (double)n_global);
-  aux::loss_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_lse, col_lse, diag, n_rows, diag_offset, inv, symmetric, loss);
+  aux::loss_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_m, row_l, col_m, col_l, diag, n_rows, diag_offset, inv,
+                                                       symmetric, loss);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -95,9 +95,9 @@ __global__ void normalize_rows_bwd(const TI* __restrict__ x, const float* __rest
   }
 }
 
-__global__ void log_weights(const float* __restrict__ lse, int64_t n, float log_coef, float* __restrict__ out) {
+__global__ void softmax_weights(const float* __restrict__ l, int64_t n, float coef, float* __restrict__ w) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = log_coef - lse[i];
+  if (i < n) w[i] = coef / l[i];   // l = +inf (column without positives) -> 0
 }
 
 __global__ void combine_lse(const float* __restrict__ m, const float* __restrict__ l, int64_t n, float* __restrict__ lse) {
@@ -105,16 +105,17 @@ __global__ void combine_lse(const float* __restrict__ m, const float* __restrict
   if (i < n) lse[i] = m[i] + logf(l[i]);
 }
 
-// Deterministic single-block loss reduction (double accumulators, fixed order).
-__global__ void loss_reduce(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+// Deterministic single-block loss reduction (fp64 accumulators, fixed order).
+__global__ void loss_reduce(const float* __restrict__ row_m, const float* __restrict__ row_l,
+                            const float* __restrict__ col_m, const float* __restrict__ col_l,
                             const float* __restrict__ diag, int64_t n_rows, int64_t diag_offset, double inv_denom,
                             int symmetric, float* __restrict__ loss) {
   __shared__ double sh[1024];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < n_rows; i += blockDim.x) {
-    double dg = diag[i];
-    acc += (double)row_lse[i] - dg;
-    if (symmetric) acc += (double)col_lse[i + diag_offset] - dg;
+    const double dg = diag[i];
+    acc += ((double)row_m[i] - dg) + log((double)row_l[i]);
+    if (symmetric) acc += ((double)col_m[i + diag_offset] - dg) + log((double)col_l[i + diag_offset]);
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -138,9 +139,8 @@ __global__ void reduce_col_partials(const float* __restrict__ part, int n_part, 
 }
 
 // Combine (m,l) partial pairs: out over `n` entries, `n_part` partials with leading dimension ld.
-// mode 0: write lse = M + log L;  mode 1: write (M, L).
 __global__ void reduce_ml_partials(const float* __restrict__ pm, const float* __restrict__ pl, int n_part, int64_t ld,
-                                   int64_t n, int mode, float* __restrict__ out0, float* __restrict__ out1) {
+                                   int64_t n, float* __restrict__ out_m, float* __restrict__ out_l) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float M = -INFINITY;
@@ -150,12 +150,8 @@ __global__ void reduce_ml_partials(const float* __restrict__ pm, const float* __
     float m = pm[(int64_t)p * ld + i];
     if (m > -INFINITY) L += pl[(int64_t)p * ld + i] * expf(m - M);
   }
-  if (mode == 0) {
-    out0[i] = M + logf(L);
-  } else {
-    out0[i] = M;
-    out1[i] = L;
-  }
+  out_m[i] = M;
+  out_l[i] = L;
 }
 
 // *dst += coef * sum_p part[p]   (single thread, fixed order -> deterministic).

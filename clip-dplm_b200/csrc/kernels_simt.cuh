@@ -116,13 +116,13 @@ fwd_stats(const T* __restrict__ x, const T* __restrict__ y, const float* __restr
 }
 
 // Backward, one side: dx[i0:i0+64, dd0:dd0+64] = out_scale * sum_j G_ij rinv_y[j] y_j with
-// G_ij = exp(S_ij + lu_i) + exp(S_ij + lv_j) - diag_w [j == i + diag_offset].
+// G_ij = exp(S_ij - rm_i) rw_i + exp(S_ij - cm_j) cw_j - diag_w [j == i + diag_offset].
 // grid = (d tiles, row tiles); the x == 0 column of blocks also emits sum G.S partials.
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
 bwd_side(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ rinv_x,
-         const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, const float* __restrict__ log_u, const float* __restrict__ log_v,
-         float diag_w, float out_scale, float* __restrict__ dx, float* __restrict__ ds_part) {
+         const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, const float* __restrict__ row_m, const float* __restrict__ row_w,
+         const float* __restrict__ col_m, const float* __restrict__ col_w, float diag_w, float out_scale, float* __restrict__ dx, float* __restrict__ ds_part) {
   __shared__ float Xs[KT][TILE + 1];
   __shared__ float Ys[KT][TILE + 1];
   __shared__ float Gs[TILE][TILE + 1];
@@ -131,11 +131,12 @@ bwd_side(const T* __restrict__ x, const T* __restrict__ y, const float* __restri
   const int64_t i0 = (int64_t)blockIdx.y * TILE;
   const int dd0 = blockIdx.x * TILE;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float lu[4];
+  float rm[4], rw[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     int64_t gi = i0 + ty * 4 + a;
-    lu[a] = (gi < n_rows) ? log_u[gi] : -INFINITY;
+    rm[a] = (gi < n_rows) ? row_m[gi] : 0.f;
+    rw[a] = (gi < n_rows) ? row_w[gi] : 0.f;
   }
   float acc[4][4];
 #pragma unroll
@@ -149,14 +150,17 @@ bwd_side(const T* __restrict__ x, const T* __restrict__ y, const float* __restri
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       int64_t gj = j0 + tx * 4 + b;
-      float lv = (log_v != nullptr && gj < n_cols) ? log_v[gj] : -INFINITY;
+      const bool has_c = col_w != nullptr && gj < n_cols;
+      const float cm = has_c ? col_m[gj] : 0.f;
+      const float cw = has_c ? col_w[gj] : 0.f;
       const float ryj = (gj < n_cols) ? rinv_y[gj] : 0.f;
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         int64_t gi = i0 + ty * 4 + a;
         float g = 0.f;
         if (gi < n_rows && gj < n_cols) {
-          g = expf(s[a][b] + lu[a]) + expf(s[a][b] + lv);
+          g = expf(s[a][b] - rm[a]) * rw[a];
+          if (cw != 0.f) g = fmaf(expf(s[a][b] - cm), cw, g);
           if (gj == gi + diag_offset) g -= diag_w;
           ds = fmaf(g, s[a][b], ds);
         }

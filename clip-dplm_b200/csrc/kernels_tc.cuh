@@ -61,13 +61,16 @@ struct Params {
   const float* rinv_x;   // [n_rows]  1 / |x_i|   (the normalise, applied to the fp32 accumulator)
   const float* rinv_y;   // [n_cols]
   // MODE 0 outputs
-  float* row_lse;      // [n_rows]           s + log sum_j exp(S_ij - s)
+  float* row_m;        // [n_rows]           = s (the fixed shift)
+  float* row_l;        // [n_rows]           sum_j exp(S_ij - s)
   float* col_part;     // [2 * gridDim.x][col_ld]  partial sum_i exp(S_ij - s)
   long long col_ld;
   float* diag;         // [n_rows]
   // MODE 1 inputs / outputs
-  const float* log_u;  // [n_rows]
-  const float* log_v;  // [n_cols] or nullptr
+  const float* row_m_in;  // [n_rows]  G_ij = exp(S_ij - row_m_i) row_w_i + exp(S_ij - col_m_j) col_w_j - ...
+  const float* row_w;     // [n_rows]
+  const float* col_m_in;  // [n_cols] or nullptr
+  const float* col_w;     // [n_cols] or nullptr
   float diag_w;
   float out_scale;     // grad_out * s
   float* dx;           // [n_rows, d] f32
@@ -269,8 +272,9 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
     if (te < BLOCK_I) {
       rx_s[te] = (te < i_valid) ? p.rinv_x[i0 + te] : 0.f;
-      // u_i = exp(log_u_i + s): with exp(S - s) <= 1 it gives exp(S + log_u_i) from ONE ex2 per logit
-      if (MODE == 1) u_s[te] = (te < i_valid) ? ex2((p.log_u[i0 + te] + p.scale) * LOG2E) : 0.f;
+      // u_i = row_w_i exp(s - row_m_i): exp(S - s) u_i = exp(S - row_m_i) row_w_i from ONE ex2 per logit
+      // (row_m_i == s when the statistics come from the MODE 0 kernel, so u_i = row_w_i exactly)
+      if (MODE == 1) u_s[te] = (te < i_valid) ? p.row_w[i0 + te] * ex2((p.scale - p.row_m_in[i0 + te]) * LOG2E) : 0.f;
     }
     epi_bar_sync();
 
@@ -342,7 +346,10 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int hh = te / HALF, ii = te % HALF;
         const float tot = red[(hh * 4 + 0) * 64 + ii] + red[(hh * 4 + 1) * 64 + ii] + red[(hh * 4 + 2) * 64 + ii] +
                           red[(hh * 4 + 3) * 64 + ii];
-        if (te < i_valid) p.row_lse[i0 + te] = p.scale + logf(tot);
+        if (te < i_valid) {
+          p.row_m[i0 + te] = p.scale;
+          p.row_l[i0 + te] = tot;
+        }
       }
     } else {
       float ds = 0.f;
@@ -359,7 +366,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
-        const float vj = (jvalid && p.log_v != nullptr) ? ex2((p.log_v[jg] + p.scale) * LOG2E) : 0.f;
+        const float vj = (jvalid && p.col_w != nullptr) ? p.col_w[jg] * ex2((p.scale - p.col_m_in[jg]) * LOG2E) : 0.f;
         const float ryj = jvalid ? p.rinv_y[jg] : 0.f;
         const float cj = ryj * p.k2;
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;

@@ -89,24 +89,25 @@ class CudaEngine:
         return xc, xt
 
     def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0):
-        """-> row_lse [n_rows], col_m [n_cols], col_l [n_cols], diag [n_rows]"""
+        """-> row_m, row_l [n_rows], col_m, col_l [n_cols], diag [n_rows]   (LSE = m + log l, kept as pairs)"""
         self._chk(x, (torch.bfloat16, torch.float32), "x")
         self._chk(y, (x.dtype,), "y")
         n_rows, d = x.shape
         n_cols = y.shape[0]
         dev = x.device
         ws = self.workspace(n_rows, n_cols, d, x.dtype, flags, dev)
-        row_lse = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        row_m = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
         col_m = torch.empty(n_cols, dtype=torch.float32, device=dev)
         col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
         diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
         _lib.check(self.lib.clipnce_forward(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n_rows, n_cols, d, int(diag_offset),
-                                            float(scale), _DT[x.dtype], flags, _p(row_lse), _p(col_m), _p(col_l),
-                                            _p(diag), _p(ws), ws.numel(), _stream()), "forward")
-        return row_lse, col_m, col_l, diag
+                                            float(scale), _DT[x.dtype], flags, _p(row_m), _p(row_l), _p(col_m),
+                                            _p(col_l), _p(diag), _p(ws), ws.numel(), _stream()), "forward")
+        return row_m, row_l, col_m, col_l, diag
 
-    def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
-                 want_dscale=True):
+    def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, grad_out,
+                 flags=0, want_dscale=True):
         """-> dx_hat [n_rows,d] f32, d_scale_sum [1] f32 (or None)"""
         n_rows, d = x.shape
         n_cols = y.shape[0]
@@ -116,14 +117,14 @@ class CudaEngine:
         ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
         ld_t = y_t.shape[1] if y_t is not None else 0
         _lib.check(self.lib.clipnce_backward(_p(x), _p(y), _p(y_t), ld_t, _p(rinv_x), _p(rinv_y), n_rows, n_cols, d,
-                                             int(diag_offset), float(scale), _p(log_u), _p(log_v), float(diag_w),
-                                             float(grad_out), _DT[x.dtype], flags, _p(dx), _p(ds), _p(ws), ws.numel(),
-                                             _stream()), "backward")
+                                             int(diag_offset), float(scale), _p(row_m), _p(row_w), _p(col_m), _p(col_w),
+                                             float(diag_w), float(grad_out), _DT[x.dtype], flags, _p(dx), _p(ds),
+                                             _p(ws), ws.numel(), _stream()), "backward")
         return dx, ds
 
-    def log_weights(self, lse, log_coef):
-        out = torch.empty_like(lse)
-        _lib.check(self.lib.clipnce_log_weights(_p(lse), lse.numel(), float(log_coef), _p(out), _stream()), "log_weights")
+    def softmax_weights(self, l, coef):
+        out = torch.empty_like(l)
+        _lib.check(self.lib.clipnce_softmax_weights(_p(l), l.numel(), float(coef), _p(out), _stream()), "softmax_weights")
         return out
 
     def combine_lse(self, m, l):
@@ -138,10 +139,11 @@ class CudaEngine:
                                                        _p(dx), _DT[out_dtype], _stream()), "normalize_backward")
         return dx
 
-    def loss(self, row_lse, col_lse, diag, diag_offset, n_global, symmetric):
-        out = torch.empty(1, dtype=torch.float32, device=row_lse.device)
-        _lib.check(self.lib.clipnce_loss(_p(row_lse), _p(col_lse), _p(diag), row_lse.numel(), int(diag_offset),
-                                         int(n_global), int(bool(symmetric)), _p(out), _stream()), "loss")
+    def loss(self, row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric):
+        out = torch.empty(1, dtype=torch.float32, device=row_m.device)
+        _lib.check(self.lib.clipnce_loss(_p(row_m), _p(row_l), _p(col_m), _p(col_l), _p(diag), row_m.numel(),
+                                         int(diag_offset), int(n_global), int(bool(symmetric)), _p(out), _stream()),
+                   "loss")
         return out
 
 

@@ -38,8 +38,10 @@ class _FusedClipLoss(torch.autograd.Function):
         ctx.st, ctx.engine = st, engine
         ctx.scale_info = (s, clamped, scale_is_log)
         ctx.ls_meta = (logit_scale.dtype, logit_scale.device) if torch.is_tensor(logit_scale) else None
-        ctx.mark_non_differentiable(st.row_lse, st.col_lse, st.diag)
-        return loss.reshape(()), st.row_lse, st.col_lse, st.diag
+        row_lse = engine.combine_lse(st.row_m, st.row_l)
+        col_lse = engine.combine_lse(st.col_m, st.col_l)
+        ctx.mark_non_differentiable(row_lse, col_lse, st.diag)
+        return loss.reshape(()), row_lse, col_lse, st.diag
 
     @staticmethod
     def backward(ctx, g_loss, _g1, _g2, _g3):

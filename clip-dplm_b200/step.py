@@ -62,8 +62,10 @@ class StepState:
     rinv_a: torch.Tensor
     rinv_b: torch.Tensor
     rinv_y: torch.Tensor
-    row_lse: torch.Tensor
-    col_lse: torch.Tensor
+    row_m: torch.Tensor             # log-sum-exp kept as (shift, sum) pairs: r = row_m + log(row_l)
+    row_l: torch.Tensor
+    col_m: torch.Tensor             # globally combined column statistics
+    col_l: torch.Tensor
     diag: torch.Tensor
     scale: float
     symmetric: bool
@@ -101,22 +103,20 @@ def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra=Non
     if want_t and y_t is None:
         _, y_t = engine.stage(y, compute_dtype, want_t=True)
 
-    row_lse, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags)
+    row_m, row_l, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags)
     if world > 1:
         m_max = col_m.clone()
         dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=group)
-        l = col_l * torch.exp(col_m - m_max)
-        dist.all_reduce(l, op=dist.ReduceOp.SUM, group=group)
-        col_lse = m_max + torch.log(l)
-    else:
-        col_lse = engine.combine_lse(col_m, col_l)
+        col_l = col_l * torch.exp(col_m - m_max)
+        dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=group)
+        col_m = m_max
     if y.shape[0] > n_global:
-        col_lse[n_global:] = float("inf")   # extra negatives carry no positives: no column loss, no column soft-max
-    loss = engine.loss(row_lse, col_lse, diag, diag_offset, n_global, symmetric)
+        col_l[n_global:] = float("inf")   # extra negatives carry no positives: no column loss, no column soft-max
+    loss = engine.loss(row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric)
     if world > 1:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-    st = StepState(a, b, a_c, a_c_t, y, y_t, rinv_a, rinv_b, rinv_y, row_lse, col_lse, diag, scale, symmetric,
-                   n_local, n_global, diag_offset, flags, group)
+    st = StepState(a, b, a_c, a_c_t, y, y_t, rinv_a, rinv_b, rinv_y, row_m, row_l, col_m, col_l, diag, scale,
+                   symmetric, n_local, n_global, diag_offset, flags, group)
     return loss, st
 
 
@@ -126,21 +126,21 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     unscaled -- the caller multiplies that single element)."""
     n_glob = st.n_global
     world = dist.get_world_size(st.group) if st.group is not None else 1
-    log_coef = -math.log((2.0 if st.symmetric else 1.0) * n_glob)
-    log_u = engine.log_weights(st.row_lse, log_coef)
+    coef = 1.0 / ((2.0 if st.symmetric else 1.0) * n_glob)
+    row_w = engine.softmax_weights(st.row_l, coef)
     if st.symmetric:
-        log_v = engine.log_weights(st.col_lse, log_coef)
+        col_m, col_w = st.col_m, engine.softmax_weights(st.col_l, coef)
     else:
-        log_v = torch.full_like(st.col_lse, float("-inf"))
+        col_m, col_w = st.col_m, torch.zeros_like(st.col_l)
     diag_w = 1.0 / n_glob
 
     # side 1: local rows x all columns -> dA_hat (complete) and sum G.S over the local row block
-    da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, st.diag_offset, st.scale, log_u, log_v,
-                                 diag_w, 1.0, st.flags, want_dscale=True)
+    da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, st.diag_offset, st.scale, st.row_m, row_w,
+                                 col_m, col_w, diag_w, 1.0, st.flags, want_dscale=True)
     # side 2: the positive-carrying columns as rows x local rows as columns -> partial dB_hat [N,d]
     db_part, _ = engine.backward(st.y[:n_glob], st.a_c, st.a_c_t, st.rinv_y[:n_glob].contiguous(), st.rinv_a,
-                                 -st.diag_offset, st.scale, log_v[:n_glob].contiguous(), log_u, diag_w, 1.0, st.flags,
-                                 want_dscale=False)
+                                 -st.diag_offset, st.scale, col_m[:n_glob].contiguous(), col_w[:n_glob].contiguous(),
+                                 st.row_m, row_w, diag_w, 1.0, st.flags, want_dscale=False)
     if world > 1:
         db_hat = _reduce_scatter_rows(db_part, st.group)
         dist.all_reduce(ds, op=dist.ReduceOp.SUM, group=st.group)

@@ -92,44 +92,50 @@ int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, voi
  * diag_offset   column of row 0's positive: the positive of local row i is column i + diag_offset
  *               (0 on one GPU, rank * n_rows under the row-sharded global batch)
  * scale         s = exp(logit_scale), already clamped by the caller (old/clip_opt.py:100)
- * row_lse [n_rows]  r_i, complete (every column is seen locally)
- * col_m, col_l [n_cols]  partial column statistics over the LOCAL rows: c_j = M_j + log(sum over
- *               ranks of col_l_j * exp(col_m_j - M_j)), M_j = max over ranks of col_m_j
+ * Log-sum-exps are returned as (max-like shift m, sum l = sum exp(S - m)) PAIRS and never collapsed
+ * to a single float inside the library: r_i = row_m_i + log(row_l_i).  Keeping the pair is what lets the
+ * backward form soft-max probabilities as exp(S - m) / l with full fp32 relative accuracy (the way
+ * ATen's log_softmax does) -- a rounded r_i ~ 14 would cost 1e-6 absolute, i.e. 1e-4 relative on
+ * 1 - p_ii once the model separates the positives.
+ * row_m, row_l [n_rows]  complete (every column is seen locally)
+ * col_m, col_l [n_cols]  partial column statistics over the LOCAL rows; across ranks:
+ *               M_j = max col_m_j,  L_j = sum col_l_j * exp(col_m_j - M_j)
  * diag [n_rows]     S_{i, i+diag_offset}
  */
 int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
                     int64_t n_rows, int64_t n_cols, int64_t d,
                     int64_t diag_offset, float scale, int dtype, int flags,
-                    float* row_lse, float* col_m, float* col_l, float* diag,
+                    float* row_m, float* row_l, float* col_m, float* col_l, float* diag,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * One side of the backward.  Replaces autograd through cross_entropy + matmul (loss.backward():
  * rna_clip_codes.ipynb:2074, run1/full.py:134, old/clip_opt.py:167, old/ablation.py:16-17).
  * The logit tiles are recomputed; with
- *     G_ij = exp(S_ij + log_u_i) + exp(S_ij + log_v_j) - diag_w * [j == i + diag_offset]
+ *     G_ij = exp(S_ij - row_m_i) row_w_i + exp(S_ij - col_m_j) col_w_j - diag_w * [j == i + diag_offset]
  * it returns  dx_hat = grad_out * s * G Yhat  ([n_rows,d] f32; Yhat_j = rinv_y[j] y_j)  and
  *             *d_scale_sum += grad_out * sum_ij G_ij S_ij   (= dL/dlogit_scale when s = exp(logit_scale)).
  * Symmetric InfoNCE over a global batch N:
- *     log_u_i = -log(2N) - r_i,  log_v_j = -log(2N) - c_j,  diag_w = 1/N
- * one-directional (run1/full.py:133, tong/utils/losses.py:19): log_u_i = -log(N) - r_i, log_v = NULL.
- * Columns without positives (hard-negative cache, old/clip_opt.py:118-121) carry log_v_j = -inf.
- * Call it once as (A, B, B^T, rinv_a, rinv_b, log_u, log_v, +offset) for dAhat and once as
- * (B, A, A^T, rinv_b, rinv_a, log_v, log_u, -offset) for dBhat.
+ *     row_w_i = 1 / (2N row_l_i),  col_w_j = 1 / (2N col_l_j),  diag_w = 1/N      (clipnce_softmax_weights)
+ * one-directional (run1/full.py:133, tong/utils/losses.py:19): row_w_i = 1 / (N row_l_i), col_m = col_w = NULL.
+ * Columns without positives (hard-negative cache, old/clip_opt.py:118-121) carry col_w_j = 0.
+ * Call it once as (A, B, B^T, rinv_a, rinv_b, row, col, +offset) for dAhat and once as
+ * (B, A, A^T, rinv_b, rinv_a, col, row, -offset) for dBhat.
  * y_t [d,ld_t] (clipnce_stage_operand) is only read by the tensor-core path (NULL for the exact path).
- * log_v and d_scale_sum may be NULL.
+ * col_m/col_w (together) and d_scale_sum may be NULL.
  */
 int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t,
                      const float* rinv_x, const float* rinv_y,
                      int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
-                     const float* log_u, const float* log_v, float diag_w, float grad_out,
+                     const float* row_m, const float* row_w, const float* col_m, const float* col_w,
+                     float diag_w, float grad_out,
                      int dtype, int flags, float* dx_hat, float* d_scale_sum,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* out_i = log_coef - lse_i  (lse = +inf -> -inf).  Builds log_u / log_v from row / column LSE. */
-int clipnce_log_weights(const float* lse, int64_t n, float log_coef, float* out, void* stream);
+/* w_i = coef / l_i  (l = +inf -> 0).  Builds row_w / col_w from the forward's sums. */
+int clipnce_softmax_weights(const float* l, int64_t n, float coef, float* w, void* stream);
 
-/* c_j = M_j + log(l_j * exp(m_j - M_j)) helper for one GPU: col_lse_j = col_m_j + log(col_l_j). */
+/* lse_i = m_i + log(l_i)  (reporting only; the kernels consume the pairs). */
 int clipnce_combine_lse(const float* m, const float* l, int64_t n, float* lse, void* stream);
 
 /* Backward of the normalise: dx_i = rinv_i * (g_i - xhat_i (xhat_i . g_i)), xhat_i = x_i * rinv_i
@@ -141,11 +147,13 @@ int clipnce_normalize_backward(const void* x, int in_dtype, const float* rinv, c
                                const float* grad_scale, int64_t n, int64_t d, void* dx, int out_dtype,
                                void* stream);
 
-/* loss = [ sum_i (row_lse_i - diag_i) + (symmetric ? sum_i (col_lse_{i+diag_offset} - diag_i) : 0) ]
- *        / (symmetric ? 2 n_global : n_global), accumulated into *loss (f32, caller zeroes it).
- * Mean reduction of F.cross_entropy (rna_clip_codes.ipynb:1953). Deterministic (single block). */
-int clipnce_loss(const float* row_lse, const float* col_lse, const float* diag, int64_t n_rows,
-                 int64_t diag_offset, int64_t n_global, int symmetric, float* loss, void* stream);
+/* loss[0] = [ sum_i (r_i - diag_i) + (symmetric ? sum_i (c_{i+diag_offset} - diag_i) : 0) ]
+ *           / (symmetric ? 2 n_global : n_global)   with r = row_m + log row_l, c = col_m + log col_l,
+ * summed in fp64 in a fixed order (deterministic).  Mean reduction of F.cross_entropy
+ * (rna_clip_codes.ipynb:1953); under row sharding every rank contributes its rows' part. */
+int clipnce_loss(const float* row_m, const float* row_l, const float* col_m, const float* col_l,
+                 const float* diag, int64_t n_rows, int64_t diag_offset, int64_t n_global, int symmetric,
+                 float* loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,21 +43,22 @@ class TorchCpuEngine:
     def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0):
         S = self._logits(x, y, rinv_x, rinv_y, scale)
         n = x.shape[0]
-        row_lse = torch.logsumexp(S, dim=1)
+        row_m = S.max(dim=1).values
+        row_l = torch.exp(S - row_m[:, None]).sum(dim=1)
         col_m = S.max(dim=0).values
         col_l = torch.exp(S - col_m[None, :]).sum(dim=0)
         idx = torch.arange(n)
         diag = S[idx, idx + diag_offset]
-        return row_lse, col_m, col_l, diag
+        return row_m, row_l, col_m, col_l, diag
 
-    def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, log_u, log_v, diag_w, grad_out, flags=0,
-                 want_dscale=True):
+    def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, grad_out,
+                 flags=0, want_dscale=True):
         if y_t is not None:   # the transposed operand must be the same matrix
             assert torch.equal(y_t[:, :y.shape[0]].t(), y)
         S = self._logits(x, y, rinv_x, rinv_y, scale)
-        G = torch.exp(S + log_u[:, None])
-        if log_v is not None:
-            G = G + torch.exp(S + log_v[None, :])
+        G = torch.exp(S - row_m[:, None]) * row_w[:, None]
+        if col_w is not None:
+            G = G + torch.exp(S - col_m[None, :]) * col_w[None, :]
         n_rows, n_cols = S.shape
         i = torch.arange(n_rows)
         j = i + diag_offset
@@ -67,8 +68,8 @@ class TorchCpuEngine:
         ds = (grad_out * (G * S).sum()).reshape(1) if want_dscale else None
         return dx, ds
 
-    def log_weights(self, lse, log_coef):
-        return log_coef - lse
+    def softmax_weights(self, l, coef):
+        return coef / l
 
     def combine_lse(self, m, l):
         return m + torch.log(l)
@@ -81,7 +82,8 @@ class TorchCpuEngine:
             dx = dx * grad_scale.to(self.dt)
         return dx.to(out_dtype)
 
-    def loss(self, row_lse, col_lse, diag, diag_offset, n_global, symmetric):
+    def loss(self, row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric):
+        row_lse, col_lse = row_m + torch.log(row_l), col_m + torch.log(col_l)
         n = row_lse.numel()
         tot = (row_lse - diag).sum()
         if symmetric:

@@ -1,0 +1,183 @@
+"""CPU suite (`pytest -m "not gpu"`): oracle vs golden fixtures, closed-form identities, host logic
+through a CPU stand-in engine (incl. world_size-2 gloo), and the C-ABI surface (load + exports only --
+no compute call is made without a GPU)."""
+import ctypes
+import glob
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ref_step as O
+from tests.cpu_engine import TorchCpuEngine
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+
+
+def rel(x, ref):
+    x, ref = torch.as_tensor(x).double(), torch.as_tensor(ref).double()
+    return float((x - ref).norm() / ref.norm().clamp_min(1e-300))
+
+
+def from_bits(bits):
+    return torch.from_numpy(bits.astype(np.int16)).view(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ oracle
+def test_oracle_is_pinned_to_reference():
+    pinned = json.load(open(os.path.join(HERE, "golden", "PINNED.json")))
+    checks = pinned["checks"]
+    for key in ("old/clip.py forward tail", "rna_clip_codes.ipynb RNARBPCLIPModel loss", "old/clip_opt.py optimized_clip_loss"):
+        assert checks[key] == "exact"
+    assert checks["param count 71,646,299"] == "reproduced"
+    assert len(GOLDEN) >= 8
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(path):
+    z = np.load(path)
+    a, b = from_bits(z["a_bits"]).float(), from_bits(z["b_bits"]).float()
+    kw = json.loads(str(z["meta"]))
+    if "extra_bits" in z:
+        kw["extra_cols"] = from_bits(z["extra_bits"]).float()
+    ls = float(z["logit_scale"])
+    r64 = O.ref_step(a.double(), b.double(), ls, **{k: (v.double() if torch.is_tensor(v) else v) for k, v in kw.items()})
+    assert abs(float(r64["loss"]) - float(z["loss64"])) <= 1e-12 * max(1.0, abs(float(z["loss64"])))
+    assert rel(r64["d_a"].float(), z["d_a64"]) < 1e-6 and rel(r64["d_b"].float(), z["d_b64"]) < 1e-6
+    r32 = O.ref_step(a, b, ls, **kw)
+    assert abs(float(r32["loss"]) - float(z["loss32"])) <= 2e-6 * max(1.0, abs(float(z["loss32"])))
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_closed_form_matches_autograd(symmetric):
+    a, b = O.make_inputs(96, 40, seed=5)
+    s = 1 / 0.07
+    cf = O.closed_form(a.numpy(), b.numpy(), s, symmetric=symmetric)
+    ref = O.ref_step(a.double(), b.double(), math.log(s), symmetric=symmetric)
+    assert abs(cf["loss"] - float(ref["loss"])) < 1e-12
+    assert rel(cf["d_a"], ref["d_a"]) < 1e-12 and rel(cf["d_b"], ref["d_b"]) < 1e-12
+    assert abs(cf["d_scale_sum"] - float(ref["d_logit_scale"])) < 1e-12
+
+
+def test_known_answers():
+    # untrained model, batch 32: loss ~ ln 32 (rna_clip_codes.ipynb:2333 records 3.5013 at s = 14.3 on real data)
+    a, b = O.make_inputs(32, 512, seed=7, correlated=False)
+    assert abs(float(O.ref_loss(a, b, torch.tensor(0.0))) - math.log(32)) < 0.05
+    # perfectly aligned pairs: loss -> log(1 + (N-1) exp(-s (1 - cos)))  with cos ~ 0 off the diagonal
+    n, s = 64, 5.0
+    a = torch.eye(n, 128)
+    l = float(O.ref_loss(a, a.clone(), torch.tensor(math.log(s))))
+    assert abs(l - math.log(1 + (n - 1) * math.exp(-s))) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI surface
+def test_library_exports_every_declared_symbol():
+    from clip_dplm_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "clipnce.h")).read()
+    declared = set(re.findall(r"\b(clipnce_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.clipnce_version() == 100
+
+
+def test_host_only_entry_points():
+    from clip_dplm_b200 import _lib
+    lib = _lib.load()
+    nbytes = ctypes.c_size_t(0)
+    assert lib.clipnce_workspace_bytes(65536, 65536, 512, _lib.BF16, 0, ctypes.byref(nbytes)) == 0
+    assert nbytes.value >= 2 * 1024 * 65536 * 4          # [2 x 1024 row blocks][65536] fp32 column partials
+    assert lib.clipnce_workspace_bytes(0, 10, 512, _lib.BF16, 0, ctypes.byref(nbytes)) == -1
+    assert b"bad shape" in lib.clipnce_last_error()
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 14.3, 0) == 1
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 100.0, 0) == 0      # exp(S - s) would leave fp32
+    assert lib.clipnce_uses_tensor_cores(_lib.F32, 512, 14.3, 0) == 0        # check mode
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 516, 14.3, 0) == 0       # d % 8
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 14.3, _lib.FLAG_FORCE_EXACT) == 0
+
+
+def test_product_path_refuses_cpu_tensors():
+    from clip_dplm_b200 import fused_clip_loss
+    a, b = O.make_inputs(16, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fused_clip_loss(a, b, 2.0)
+
+
+# ------------------------------------------------------------------------------------------------ host logic
+CASES = [({}, 0), ({"symmetric": False}, 0), ({"clamp_max": 100.0, "ls": 5.0, "mix": 0.12}, 0),
+         ({"scale_is_log": False, "ls": 10.0, "symmetric": False}, 0), ({}, 40), ({"symmetric": False}, 24)]
+
+
+@pytest.mark.parametrize("kw,n_extra", CASES)
+def test_step_logic_matches_oracle(kw, n_extra):
+    from clip_dplm_b200 import fused_clip_loss
+    kw = dict(kw)
+    ls = kw.pop("ls", O.LOGIT_SCALE_INIT)
+    a, b = O.make_inputs(100, 48, n_cols=100 + n_extra, mix=kw.pop("mix", 0.5))
+    extra = None
+    if n_extra:
+        extra = torch.nn.functional.normalize(b[100:].double(), dim=-1)
+        b = b[:100]
+    okw = dict(kw, **({"extra_cols": extra} if extra is not None else {}))
+    ref = O.ref_step(a.double(), b.double(), ls, **okw)
+    ac, bc = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    t = torch.tensor(ls, dtype=torch.float64, requires_grad=True)
+    loss = fused_clip_loss(ac, bc, t, engine=TorchCpuEngine(), compute_dtype=torch.float64, extra_cols=extra, **kw)
+    (2.5 * loss).backward()                     # a non-trivial upstream gradient
+    assert abs(float(loss.detach()) - float(ref["loss"])) < 1e-12
+    assert rel(ac.grad / 2.5, ref["d_a"]) < 1e-9 and rel(bc.grad / 2.5, ref["d_b"]) < 1e-9
+    assert abs(float(t.grad) / 2.5 - float(ref["d_logit_scale"])) < 1e-9
+
+
+def _gloo_worker(rank, world, port, n, d, symmetric, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clip_dplm_b200 import fused_clip_loss
+        torch.set_num_threads(1)
+        a, b = O.make_inputs(n, d, seed=21)
+        nl = n // world
+        ac = a[rank * nl:(rank + 1) * nl].double().requires_grad_(True)
+        bc = b[rank * nl:(rank + 1) * nl].double().requires_grad_(True)
+        t = torch.tensor(O.LOGIT_SCALE_INIT, dtype=torch.float64, requires_grad=True)
+        loss = fused_clip_loss(ac, bc, t, engine=TorchCpuEngine(), compute_dtype=torch.float64, group=dist.group.WORLD,
+                               symmetric=symmetric)
+        loss.backward()
+        q.put((rank, float(loss.detach()), ac.grad.numpy(), bc.grad.numpy(), float(t.grad)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_row_sharded_global_batch_gloo(symmetric):
+    """world_size 2 over gloo: global negatives, exact gradients through the gather (reduce-scatter),
+    compared with the single-process reference on the concatenated batch."""
+    world, n, d = 2, 96, 32
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, d, symmetric, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, b = O.make_inputs(n, d, seed=21)
+    ref = O.ref_step(a.double(), b.double(), O.LOGIT_SCALE_INIT, symmetric=symmetric)
+    nl = n // world
+    for rank, loss, da, db, dt in out:
+        assert abs(loss - float(ref["loss"])) < 1e-12
+        assert rel(da, ref["d_a"][rank * nl:(rank + 1) * nl]) < 1e-9
+        assert rel(db, ref["d_b"][rank * nl:(rank + 1) * nl]) < 1e-9
+        assert abs(dt - float(ref["d_logit_scale"])) < 1e-9

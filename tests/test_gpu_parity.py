@@ -1,0 +1,224 @@
+"""GPU parity tests (run with `pytest -m gpu` on a B200).
+
+Everything goes through the C-ABI (clip_dplm_b200.engine.CudaEngine -> libclipnce.so) and is compared
+with the CPU oracle (oracle/ref_step.py) and the committed golden fixtures (tests/golden/*.npz, which
+were generated from the reference's own code by oracle/gen_golden.py).
+
+Tolerances (BASELINE.json north_star): bf16 tensor-core path -- loss 1e-3 relative, embedding
+gradients 2e-2 Frobenius-relative; fp32 check mode -- 1e-5, widened only to 3x the fp32 PyTorch
+reference's own distance from the fp64 truth when that is larger (the reference is not exact either).
+"""
+import glob
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_step as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+LOSS_RTOL_BF16, GRAD_RTOL_BF16, RTOL_F32 = 1e-3, 2e-2, 1e-5
+
+
+def rel(x, ref):
+    x = torch.as_tensor(x).double().cpu()
+    ref = torch.as_tensor(ref).double().cpu()
+    return float((x - ref).norm() / ref.norm().clamp_min(1e-300))
+
+
+def from_bits(bits):
+    return torch.from_numpy(bits.astype(np.int16)).view(torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from clip_dplm_b200.engine import CudaEngine
+    return CudaEngine()
+
+
+def run_fused(a, b, ls, compute_dtype, **kw):
+    from clip_dplm_b200 import fused_clip_loss
+    in_dt = torch.bfloat16 if compute_dtype == torch.bfloat16 else torch.float32
+    ac = a.cuda().to(in_dt).requires_grad_(True)
+    bc = b.cuda().to(in_dt).requires_grad_(True)
+    t = torch.tensor(float(ls), device="cuda", dtype=torch.float32, requires_grad=True)
+    if "extra_cols" in kw:
+        kw = dict(kw, extra_cols=kw["extra_cols"].cuda().to(in_dt))
+    loss = fused_clip_loss(ac, bc, t, compute_dtype=compute_dtype, **kw)
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss.detach()), ac.grad.float().cpu(), bc.grad.float().cpu(), float(t.grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures generated from the reference itself
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_golden(path, mode):
+    z = np.load(path)
+    a, b = from_bits(z["a_bits"]).float(), from_bits(z["b_bits"]).float()
+    kw = json.loads(str(z["meta"]))
+    if "extra_bits" in z:
+        kw["extra_cols"] = from_bits(z["extra_bits"]).float()
+    ls = float(z["logit_scale"])
+    cd = torch.bfloat16 if mode == "bf16" else torch.float32
+    loss, da, db, dt = run_fused(a, b, ls, cd, **kw)
+    l64, da64, db64, dt64 = float(z["loss64"]), z["d_a64"], z["d_b64"], float(z["d_ls64"])
+    if mode == "bf16":
+        assert abs(loss - l64) <= LOSS_RTOL_BF16 * abs(l64) + 1e-7
+        assert rel(da, da64) <= GRAD_RTOL_BF16 and rel(db, db64) <= GRAD_RTOL_BF16
+        assert abs(dt - dt64) <= 2e-2 * abs(dt64) + 1e-6
+    else:
+        # fp32 reference's own distance from fp64 on this fixture
+        ref32 = O.ref_step(a, b, ls, **kw)
+        own = max(rel(ref32["d_a"], da64), rel(ref32["d_b"], db64))
+        tol = max(RTOL_F32, 3 * own)
+        assert abs(loss - l64) <= RTOL_F32 * abs(l64) + 1e-7
+        assert rel(da, da64) <= tol and rel(db, db64) <= tol, (rel(da, da64), rel(db, db64), own)
+        assert abs(dt - dt64) <= 1e-4 * abs(dt64) + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-level checks through the C-ABI against the float64 closed form
+# ------------------------------------------------------------------------------------------------
+SHAPES = [(128, 128, 64), (64, 64, 128), (256, 256, 512), (333, 333, 192), (1000, 1000, 512), (192, 192, 768),
+          (200, 333, 128), (130, 70, 256), (1, 1, 64), (65, 129, 8)]
+
+
+@pytest.mark.parametrize("n,m,d", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_forward_stats(eng, n, m, d, dtype):
+    scale = 1 / 0.07
+    a, b = O.make_inputs(max(n, m), d, seed=7)
+    a, b = a[:n], b[:m]
+    if n > m:   # every row needs its positive column inside the matrix for the diagonal read
+        a = a[:m]
+        n = m
+    cf = O.closed_form(a.numpy(), b.numpy(), scale)
+    x, _ = eng.stage(a.cuda(), dtype)
+    y, _ = eng.stage(b.cuda(), dtype)
+    rx, _ = eng.normalize(x)
+    ry, _ = eng.normalize(y)
+    row_m, row_l, col_m, col_l, diag = eng.forward(x, y, rx, ry, 0, scale)
+    torch.cuda.synchronize()
+    row_lse = (row_m.double() + row_l.double().log()).cpu()
+    col_lse = (col_m.double() + col_l.double().log()).cpu()
+    assert eng.uses_tensor_cores(dtype, d, scale) == (dtype == torch.bfloat16)
+    tol = 5e-6
+    assert torch.allclose(row_lse, torch.from_numpy(cf["row_lse"]), rtol=0, atol=tol * 15)
+    assert torch.allclose(col_lse, torch.from_numpy(cf["col_lse"]), rtol=0, atol=tol * 15)
+    assert torch.allclose(diag.double().cpu(), torch.from_numpy(cf["diag"]), rtol=0, atol=tol * 15)
+    assert rel(rx, cf["rinv_a"]) < 1e-6
+
+
+@pytest.mark.parametrize("n,d,scale,corr", [(256, 128, 14.2857, True), (333, 192, 10.0, True), (512, 256, 10.0, False),
+                                            (1000, 512, 14.2857, True), (192, 768, 30.0, True), (200, 64, 100.0, False)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_backward_sides(eng, n, d, scale, corr, dtype):
+    a, b = O.make_inputs(n, d, seed=11, correlated=corr, mix=0.3)
+    cf = O.closed_form(a.numpy(), b.numpy(), scale)
+    tc = eng.uses_tensor_cores(dtype, d, scale)
+    x, xt = eng.stage(a.cuda(), dtype, want_t=tc)
+    y, yt = eng.stage(b.cuda(), dtype, want_t=tc)
+    rx, _ = eng.normalize(x)
+    ry, _ = eng.normalize(y)
+    row_m, row_l, col_m, col_l, diag = eng.forward(x, y, rx, ry, 0, scale)
+    coef = 1.0 / (2 * n)
+    rw, cw = eng.softmax_weights(row_l, coef), eng.softmax_weights(col_l, coef)
+    da, ds = eng.backward(x, y, yt, rx, ry, 0, scale, row_m, rw, col_m, cw, 1.0 / n, 1.0)
+    db, _ = eng.backward(y, x, xt, ry, rx, 0, scale, col_m, cw, row_m, rw, 1.0 / n, 1.0, want_dscale=False)
+    torch.cuda.synchronize()
+    tol = GRAD_RTOL_BF16 if dtype == torch.bfloat16 else 2e-5
+    assert rel(da, cf["d_a_hat"]) <= tol, rel(da, cf["d_a_hat"])
+    assert rel(db, cf["d_b_hat"]) <= tol, rel(db, cf["d_b_hat"])
+    assert abs(float(ds) - cf["d_scale_sum"]) <= (2e-2 if dtype == torch.bfloat16 else 1e-4) * abs(cf["d_scale_sum"]) + 1e-6
+
+
+def test_row_shard_offsets(eng):
+    """Row-sharded layout on one device: rank r's rows against all columns with diag_offset = r * n_local
+    must reproduce the single-process statistics and gradients."""
+    n, d, world, scale = 384, 128, 3, 1 / 0.07
+    a, b = O.make_inputs(n, d, seed=3)
+    cf = O.closed_form(a.numpy(), b.numpy(), scale)
+    y, yt = eng.stage(b.cuda().bfloat16(), torch.bfloat16, want_t=True)
+    ry, _ = eng.normalize(y)
+    nl = n // world
+    col_parts, rows = [], []
+    for r in range(world):
+        x, _ = eng.stage(a[r * nl:(r + 1) * nl].cuda().bfloat16(), torch.bfloat16)
+        rx, _ = eng.normalize(x)
+        row_m, row_l, col_m, col_l, diag = eng.forward(x, y, rx, ry, r * nl, scale)
+        rows.append((x, rx, row_m, row_l, diag))
+        col_parts.append((col_m, col_l))
+    M = torch.stack([c[0] for c in col_parts]).max(0).values
+    L = sum(c[1] * torch.exp(c[0] - M) for c in col_parts)
+    col_lse = (M.double() + L.double().log()).cpu()
+    assert torch.allclose(col_lse, torch.from_numpy(cf["col_lse"]), atol=1e-4, rtol=0)
+    cw = eng.softmax_weights(L, 1.0 / (2 * n))
+    for r, (x, rx, row_m, row_l, diag) in enumerate(rows):
+        sl = slice(r * nl, (r + 1) * nl)
+        assert torch.allclose(diag.double().cpu(), torch.from_numpy(cf["diag"][sl]), atol=1e-4, rtol=0)
+        rw = eng.softmax_weights(row_l, 1.0 / (2 * n))
+        da, _ = eng.backward(x, y, yt, rx, ry, r * nl, scale, row_m, rw, M, cw, 1.0 / n, 1.0)
+        torch.cuda.synchronize()
+        assert rel(da, cf["d_a_hat"][sl]) <= GRAD_RTOL_BF16
+
+
+def test_large_properties(eng):
+    """Size-independent properties at a many-tile size the dense oracle does not reach cheaply:
+    sum_j softmax_row = 1 via the gradient identity sum_ij G_ij = 0, symmetry under swapping the two
+    sides, and agreement between the tensor-core and the exact kernels on a row sample."""
+    n, d, scale = 8192, 512, 1 / 0.07
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(n, d, device="cuda", generator=g).bfloat16()
+    b = (0.4 * a.float() + 0.6 * torch.randn(n, d, device="cuda", generator=g)).bfloat16()
+    ra, _ = eng.normalize(a)
+    rb, _ = eng.normalize(b)
+    _, bt = eng.stage(b, torch.bfloat16, want_t=True)
+    row_m, row_l, col_m, col_l, diag = eng.forward(a, b, ra, rb, 0, scale)
+    # swapping the operands swaps row and column statistics
+    row_m2, row_l2, col_m2, col_l2, diag2 = eng.forward(b, a, rb, ra, 0, scale)
+    r1 = row_m + row_l.log()
+    c2 = col_m2 + col_l2.log()
+    assert torch.allclose(r1, c2, atol=2e-5, rtol=0)
+    assert torch.allclose(diag, diag2, atol=2e-5, rtol=0)
+    # exact kernels on the first 256 rows agree with the tensor-core statistics
+    rm_e, rl_e, _, _, dg_e = eng.forward(a[:256].contiguous(), b, ra[:256].contiguous(), rb, 0, scale, flags=1)
+    assert torch.allclose(rm_e + rl_e.log(), r1[:256], atol=2e-5, rtol=0)
+    assert torch.allclose(dg_e, diag[:256], atol=2e-5, rtol=0)
+    # gradient identity: rows of G sum to (p_row - 1)/2N + sum_j p_col/2N  ->  total sum is 0  =>  sum_i dA_hat_i . 0 ...
+    coef = 1.0 / (2 * n)
+    rw, cw = eng.softmax_weights(row_l, coef), eng.softmax_weights(col_l, coef)
+    da, ds = eng.backward(a, b, bt, ra, rb, 0, scale, row_m, rw, col_m, cw, 1.0 / n, 1.0)
+    da_e, _ = eng.backward(a[:128].contiguous(), b, None, ra[:128].contiguous(), rb, 0, scale, row_m[:128].contiguous(),
+                           rw[:128].contiguous(), col_m, cw, 1.0 / n, 1.0, flags=1, want_dscale=False)
+    torch.cuda.synchronize()
+    assert rel(da[:128], da_e) <= GRAD_RTOL_BF16
+    assert torch.isfinite(da).all() and math.isfinite(float(ds))
+
+
+def test_errors_are_loud(eng):
+    x = torch.zeros(8, 64, device="cuda", dtype=torch.bfloat16)
+    r = torch.ones(8, device="cuda")
+    with pytest.raises(RuntimeError):
+        eng.forward(x, x, r, r, 0, float("nan"))
+    with pytest.raises(RuntimeError):
+        eng.normalize(torch.zeros(8, 64))          # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        eng.backward(x, x, None, r, r, 0, 10.0, r, r, r, r, 0.1, 1.0)   # tensor-core path without y_t
+
+
+def test_zero_row_is_clamped_like_F_normalize():
+    a, b = O.make_inputs(64, 64, seed=2)
+    a[5] = 0
+    ref = O.ref_step(a.double(), b.double(), O.LOGIT_SCALE_INIT)
+    loss, da, db, dt = run_fused(a, b, O.LOGIT_SCALE_INIT, torch.float32)
+    assert abs(loss - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    assert rel(db, ref["d_b"]) <= 5e-5
+    assert torch.isfinite(da).all()
