@@ -1,0 +1,332 @@
+"""Benchmark of the hot path: contrastive fwd+bwd pairs/sec @ global batch 65536, d=512, bf16.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 65536] [--d 512]
+
+One JSON line on rank 0 (see the task contract): `value` = pairs/s with inputs resident in HBM,
+`e2e` = the same through the public API from pinned HOST buffers (H2D of the embeddings + D2H of the
+loss inside the timed region), `roofline` for the dominant kernel (tcgen05 backward side), and a
+`cpu_baseline` (the reference's op sequence on the box's host cores, bounded sample).
+
+N > 1 (torchrun, one rank per GPU, NCCL): the global batch is row-sharded -- strong scaling at the
+named global batch (BASELINE.json: "65536 ... at 1/2/4/8 GPU").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "contrastive_fwd_bwd_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p["bf16_tflops_sustained"]), "hbm": float(p["hbm_gbs"]),
+                "src": "measured"}
+    except Exception:
+        return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of this rank's GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def visible_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_step_sample(n_global, d, rows, steps, warmup, threads):
+    """The reference's own op sequence (oracle/ref_step.py == old/clip.py:63-67 + rna_clip_codes.ipynb:
+    1952-1953 + loss.backward()) on the host cores, on a bounded sample of the workload: a block of
+    `rows` rows of the global batch against ALL n_global columns, so every sampled pair costs what it costs
+    in the full problem (the full 65536^2 fp32 logits + autograd buffers need ~86 GB and do not fit)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import ref_step as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    a = torch.randn(rows, d, generator=g).to(torch.bfloat16).float()
+    b = torch.randn(n_global, d, generator=g).to(torch.bfloat16).float()
+    b[:rows] = (0.5 * a + 0.5 * b[:rows]).to(torch.bfloat16).float()
+    t = torch.tensor(O.LOGIT_SCALE_INIT)
+    times = []
+    for it in range(warmup + steps):
+        ar, br, tr = a.clone().requires_grad_(True), b.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        sim, _, _ = O.ref_logits(ar, br, tr)                      # [rows, n_global]
+        labels = torch.arange(rows)
+        loss = (F.cross_entropy(sim, labels) + F.cross_entropy(sim[:, :rows].t(), labels)) / 2
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t_med = sorted(times)[len(times) // 2]
+    return rows / t_med, t_med
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = args.ref_rows
+    value, t_med = reference_step_sample(args.n, args.d, rows, args.steps, max(args.warmup, 1), threads)
+    sample = (f"{rows} rows of the global batch x all {args.n} columns per step (per-pair cost identical to the full "
+              f"problem; full N^2 fp32 logits do not fit in host RAM), fp32, torch CPU {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_med, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"symmetric InfoNCE fwd+bwd, global batch {args.n}, d={args.d}", "global_batch": args.n,
+                       "d": args.d},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from clip_dplm_b200 import fused_clip_loss
+    from clip_dplm_b200.engine import CudaEngine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = dist.group.WORLD if world > 1 else None
+    n_global, d = args.n, args.d
+    assert n_global % world == 0
+    n_local = n_global // world
+    peaks = load_peaks()
+
+    class TimedEngine(CudaEngine):
+        """Records CUDA events around the two contraction entry points and counts kernel launches."""
+
+        def __init__(self):
+            super().__init__()
+            self.ev, self.launches, self.on = {"fwd": [], "bwd": []}, 0, False
+
+        def _timed(self, key, fn, *a, **k):
+            if not self.on:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            self.ev[key].append((e0, e1))
+            return out
+
+        def forward(self, *a, **k):
+            self.launches += 2          # contraction kernel + column-partial reduction
+            return self._timed("fwd", super().forward, *a, **k)
+
+        def backward(self, *a, **k):
+            self.launches += 2 if k.get("want_dscale", True) else 1
+            return self._timed("bwd", super().backward, *a, **k)
+
+        def normalize(self, *a, **k):
+            self.launches += 1
+            return super().normalize(*a, **k)
+
+        def stage(self, x, c_dtype, want_t=False):
+            self.launches += 1 if (want_t or x.dtype != c_dtype) else 0
+            return super().stage(x, c_dtype, want_t)
+
+        def softmax_weights(self, *a, **k):
+            self.launches += 1
+            return super().softmax_weights(*a, **k)
+
+        def combine_lse(self, *a, **k):
+            self.launches += 1
+            return super().combine_lse(*a, **k)
+
+        def normalize_backward(self, *a, **k):
+            self.launches += 1
+            return super().normalize_backward(*a, **k)
+
+        def loss(self, *a, **k):
+            self.launches += 1
+            return super().loss(*a, **k)
+
+    eng = TimedEngine()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    a = torch.randn(n_local, d, device=dev, generator=g)
+    b = (0.5 * a + 0.5 * torch.randn(n_local, d, device=dev, generator=g)).to(torch.bfloat16)
+    a = a.to(torch.bfloat16)
+    logit_scale = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+    a_host = a.cpu().pin_memory()
+    b_host = b.cpu().pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        ar, br = a.detach().requires_grad_(True), b.detach().requires_grad_(True)
+        loss = fused_clip_loss(ar, br, logit_scale, group=group, engine=eng)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        ar = a_host.to(dev, non_blocking=True).requires_grad_(True)
+        br = b_host.to(dev, non_blocking=True).requires_grad_(True)
+        loss = fused_clip_loss(ar, br, logit_scale, group=group, engine=eng)
+        loss.backward()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(visible_gpu_index(local_rank))
+    sampler.start()
+    eng.on, eng.launches = True, 0
+    ms_total = timed(step_resident, args.steps)
+    launches = eng.launches
+    eng.on = False
+    clocks = sampler.finish()
+    t_fwd = sum(e0.elapsed_time(e1) for e0, e1 in eng.ev["fwd"]) / max(1, len(eng.ev["fwd"]))
+    t_bwd = sum(e0.elapsed_time(e1) for e0, e1 in eng.ev["bwd"]) / max(1, len(eng.ev["bwd"]))
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    ms_step = ms_total / args.steps
+    value = n_global / (ms_step * 1e-3)
+    e2e_value = n_global / (ms_e2e / args.steps * 1e-3)
+    flops_step = 6.0 * n_global * n_global * d
+    # dominant kernel: one backward side = recompute S tile + gradient GEMM; algorithmic work of the launch is
+    # its gradient GEMM, 2 * rows * cols * d (the three launches of a step add up to 6 N^2 d)
+    flops_bwd_launch = 2.0 * n_local * n_global * d
+    achieved = flops_bwd_launch / (t_bwd * 1e-3) / 1e12
+    peak = peaks["sustained"]           # the kernel is timed inside a long, power-capped step
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, t_med = reference_step_sample(n_global, d, args.ref_rows, 3, 1, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.ref_rows} rows x all {n_global} columns per step, fp32 torch CPU, median of 3 ({t_med:.2f} s/step)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"symmetric InfoNCE fwd+bwd, global batch {n_global}, d={d}, bf16 embeddings "
+                               f"(b = 0.5a + 0.5 noise), logit_scale = ln(1/0.07)", "global_batch": n_global, "d": d,
+                   "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                   "l2": "operands+outputs per step (>= 450 MB at N=65536) exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_local * d * 2, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "tc::clip_tc_kernel<1,64> (backward side)", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_kind": f"{peaks['src']} sustained bf16 cuBLAS", "frac_of_burst": achieved / peaks["burst"],
+                     "ms_per_launch": t_bwd, "fwd_ms_per_launch": t_fwd,
+                     "fwd_achieved": 2.0 * n_local * n_global * d / (t_fwd * 1e-3) / 1e12,
+                     "step_tflops": flops_step / world / (ms_step * 1e-3) / 1e12,
+                     "step_frac_of_burst": flops_step / world / (ms_step * 1e-3) / 1e12 / peaks["burst"]},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=65536, help="global batch")
+    ap.add_argument("--d", type=int, default=512)
+    ap.add_argument("--ref-rows", type=int, default=1024, help="row block of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -134,7 +134,8 @@ def test_backward_sides(eng, n, d, scale, corr, dtype):
     da, ds = eng.backward(x, y, yt, rx, ry, 0, scale, row_m, rw, col_m, cw, 1.0 / n, 1.0)
     db, _ = eng.backward(y, x, xt, ry, rx, 0, scale, col_m, cw, row_m, rw, 1.0 / n, 1.0, want_dscale=False)
     torch.cuda.synchronize()
-    tol = GRAD_RTOL_BF16 if dtype == torch.bfloat16 else 2e-5
+    # fp32: 1 - p_ii is formed from fp32 logits (abs. rounding ~ s * 6e-8); at s = 30 that alone is ~2e-5 relative
+    tol = GRAD_RTOL_BF16 if dtype == torch.bfloat16 else 5e-5
     assert rel(da, cf["d_a_hat"]) <= tol, rel(da, cf["d_a_hat"])
     assert rel(db, cf["d_b_hat"]) <= tol, rel(db, cf["d_b_hat"])
     assert abs(float(ds) - cf["d_scale_sum"]) <= (2e-2 if dtype == torch.bfloat16 else 1e-4) * abs(cf["d_scale_sum"]) + 1e-6
