@@ -170,95 +170,110 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   if (warp == 0) {
     // ======================================================================= TMA producer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loops and waits; one elected lane issues the copies.
+    // Keeping control flow convergent lets ptxas hold addresses/descriptors in uniform registers;
+    // issuing from inside an `if (lane == 0)` region costs a waterfall loop around every UTMALDG.
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar(B_XFULL), p.nkc * X_CHUNK);
       for (int kc = 0; kc < p.nkc; ++kc)
         ptx::tma_load_2d(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * BLOCK_K, i0);
-      int stage = 0;
-      uint32_t phase = 0;
-      auto push = [&](const CUtensorMap* m, int c0, int c1) {
-        ptx::mbar_wait(bar(B_EMPTY + stage), phase ^ 1u);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    auto push = [&](const CUtensorMap* m, int c0, int c1) {
+      ptx::mbar_wait(bar(B_EMPTY + stage), phase ^ 1u);
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(bar(B_FULL + stage), STAGE_BYTES);
         ptx::tma_load_2d(ring_smem + stage * STAGE_BYTES, m, bar(B_FULL + stage), c0, c1);
-        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-      };
-      auto load_y = [&](int t) {   // Yhat[t*128 .. +128, :] as nkc K-major chunks
-        for (int kc = 0; kc < p.nkc; ++kc) push(&tmap_y, kc * BLOCK_K, t * BLOCK_J);
-      };
-      auto load_yt = [&](int t) {  // Yhat^T[:, t*128 .. +128] as nq x 2 chunks [128 d][64 j]
-        for (int q = 0; q < p.nq; ++q)
-          for (int kk = 0; kk < 2; ++kk) push(&tmap_yt, t * BLOCK_J + kk * BLOCK_K, q * 128);
-      };
-      if (MODE == 0) {
-        for (int t = 0; t < p.n_jt; ++t) load_y(t);
-      } else {
-        load_y(0);
-        for (int t = 0; t < p.n_jt; ++t) {
-          if (t + 1 < p.n_jt) load_y(t + 1);
-          load_yt(t);
-        }
+      }
+      __syncwarp();
+      if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+    };
+    auto load_y = [&](int t) {   // Y[t*128 .. +128, :] as nkc K-major chunks
+      for (int kc = 0; kc < p.nkc; ++kc) push(&tmap_y, kc * BLOCK_K, t * BLOCK_J);
+    };
+    auto load_yt = [&](int t) {  // Y^T[:, t*128 .. +128] as nq x 2 chunks [128 d][64 j]
+      for (int q = 0; q < p.nq; ++q)
+        for (int kk = 0; kk < 2; ++kk) push(&tmap_yt, t * BLOCK_J + kk * BLOCK_K, q * 128);
+    };
+    if (MODE == 0) {
+      for (int t = 0; t < p.n_jt; ++t) load_y(t);
+    } else {
+      load_y(0);
+      for (int t = 0; t < p.n_jt; ++t) {
+        if (t + 1 < p.n_jt) load_y(t + 1);
+        load_yt(t);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
-      constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, 64);
-      int stage = 0;
-      uint32_t phase = 0;
-      ptx::mbar_wait(bar(B_XFULL), 0);
-      auto mma_s = [&](int t) {
-        const int b = t & 1;
-        ptx::mbar_wait(bar(B_SEMPTY + b), ((t >> 1) & 1) ^ 1u);
+    // Same structure: warp-uniform loops, all lanes wait on the barriers, one elected lane (always
+    // the same one, so tcgen05.commit tracks its own MMAs) issues.
+    constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
+    constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, 64);
+    const uint64_t desc_hi = ptx::smem_desc_k_sw128(0) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
+    auto desc = [&](uint32_t addr) -> uint64_t {
+      return desc_hi | (1ull << 16) | static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    ptx::mbar_wait(bar(B_XFULL), 0);
+    auto mma_s = [&](int t) {
+      const int b = t & 1;
+      ptx::mbar_wait(bar(B_SEMPTY + b), ((t >> 1) & 1) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + S_COL0 + b * BLOCK_I;
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        ptx::mbar_wait(bar(B_FULL + stage), phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + S_COL0 + b * BLOCK_I;
-        for (int kc = 0; kc < p.nkc; ++kc) {
+        if (ptx::elect_one()) {
+          const uint64_t a0 = desc(ring_smem + stage * STAGE_BYTES);
+          const uint64_t b0 = desc(x_smem + kc * X_CHUNK);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
+            ptx::mma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc_s, (kc | k) != 0);
+          ptx::mma_commit(bar(B_EMPTY + stage));
+          if (kc == p.nkc - 1) ptx::mma_commit(bar(B_SFULL + b));
+        }
+        __syncwarp();
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    };
+    auto mma_g = [&](int t) {
+      const int b = t & 1;
+      ptx::mbar_wait(bar(B_GFULL + b), (t >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int q = 0; q < p.nq; ++q) {
+        for (int kk = 0; kk < 2; ++kk) {
           ptx::mbar_wait(bar(B_FULL + stage), phase);
           ptx::tc_fence_after();
-          const uint32_t a0 = ring_smem + stage * STAGE_BYTES;
-          const uint32_t b0 = x_smem + kc * X_CHUNK;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            ptx::mma_f16(d_tmem, ptx::smem_desc_k_sw128(a0 + k * 32), ptx::smem_desc_k_sw128(b0 + k * 32), idesc_s,
-                         (kc | k) != 0);
-          ptx::mma_commit(bar(B_EMPTY + stage));
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-        }
-        ptx::mma_commit(bar(B_SFULL + b));
-      };
-      auto mma_g = [&](int t) {
-        const int b = t & 1;
-        ptx::mbar_wait(bar(B_GFULL + b), (t >> 1) & 1);
-        ptx::tc_fence_after();
-        for (int q = 0; q < p.nq; ++q) {
-          for (int kk = 0; kk < 2; ++kk) {
-            ptx::mbar_wait(bar(B_FULL + stage), phase);
-            ptx::tc_fence_after();
-            const uint32_t a0 = ring_smem + stage * STAGE_BYTES;          // Yhat^T chunk [128 d][64 j]
-            const uint32_t b0 = g_smem + b * G_BYTES + kk * (G_BYTES / 2);  // G chunk     [ 64 i][64 j]
+          if (ptx::elect_one()) {
+            const uint64_t a0 = desc(ring_smem + stage * STAGE_BYTES);                // Y^T chunk [128 d][64 j]
+            const uint64_t b0 = desc(g_smem + b * G_BYTES + kk * (G_BYTES / 2));      // G chunk   [ 64 i][64 j]
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              ptx::mma_f16(tmem_base + q * 64, ptx::smem_desc_k_sw128(a0 + k * 32),
-                           ptx::smem_desc_k_sw128(b0 + k * 32), idesc_g, (t | kk | k) != 0);
+              ptx::mma_f16(tmem_base + q * 64, a0 + 2 * k, b0 + 2 * k, idesc_g, (t | kk | k) != 0);
             ptx::mma_commit(bar(B_EMPTY + stage));
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            if (q == p.nq - 1 && kk == 1) {
+              ptx::mma_commit(bar(B_GEMPTY + b));
+              if (t == p.n_jt - 1) ptx::mma_commit(bar(B_ACCFULL));
+            }
           }
+          __syncwarp();
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(bar(B_GEMPTY + b));
-      };
-      if (MODE == 0) {
-        for (int t = 0; t < p.n_jt; ++t) mma_s(t);
-      } else {
-        mma_s(0);
-        for (int t = 0; t < p.n_jt; ++t) {
-          if (t + 1 < p.n_jt) mma_s(t + 1);   // keeps the tensor core busy while tile t is in the epilogue
-          mma_g(t);
-        }
-        ptx::mma_commit(bar(B_ACCFULL));
+      }
+    };
+    if (MODE == 0) {
+      for (int t = 0; t < p.n_jt; ++t) mma_s(t);
+    } else {
+      mma_s(0);
+      for (int t = 0; t < p.n_jt; ++t) {
+        if (t + 1 < p.n_jt) mma_s(t + 1);   // keeps the tensor core busy while tile t is in the epilogue
+        mma_g(t);
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ======================================================================= epilogue
     const int e = warp - 4;        // 0..7
