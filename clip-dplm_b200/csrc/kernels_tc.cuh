@@ -37,14 +37,15 @@ namespace tc {
 constexpr int BLOCK_J = 128;                         // streamed rows per tile == UMMA M == TMEM lanes
 constexpr int BLOCK_K = 64;                          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGE_BYTES = BLOCK_J * BLOCK_K * 2;   // 16 KiB per ring stage
+constexpr int BOX_BYTES = BLOCK_J * BLOCK_K * 2;     // one TMA box [128 rows][64 elems] = 16 KiB
+constexpr int STAGE_BYTES = 2 * BOX_BYTES;           // a ring stage = two boxes (K = 128): 8 MMAs per barrier round trip
 constexpr int G_BYTES = 64 * BLOCK_J * 2;            // one bf16 gradient tile [64 i][128 j]
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 4;                        // per ring
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr int BWD_S_COL0 = 384;                      // S buffers of MODE 1 live at TMEM columns 384..511
-constexpr int SMALL_BYTES = 3584;                    // barriers, tmem pointer, u_i / rinv_i, reduction scratch
+__host__ __device__ constexpr int small_bytes(int mode) { return mode == 1 ? 1536 : 3584; }  // barriers, tmem ptr, u/rinv, scratch
 constexpr int SMEM_LIMIT = 232448;                   // 227 KiB opt-in maximum per CTA
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -54,7 +55,9 @@ struct Params {
   int nkc;         // ceil(d / 64)   contraction chunks of the logits MMA
   int nq;          // ceil(d / 128)  accumulator chunks of the gradient MMA
   int n_jt;        // ceil(n_cols / 128)
-  int num_stages;
+  int stages_a;    // ring A: streamed Y boxes for the logits MMA
+  int stages_b;    // ring B: streamed Y^T boxes for the gradient MMA (MODE 1)
+  int cluster;     // CTAs per cluster sharing the streamed tiles through TMA multicast (1, 2, 4 or 8)
   long long diag_offset;
   float scale;     // s
   float k2;        // s * log2(e)
@@ -78,7 +81,7 @@ struct Params {
 };
 
 __host__ __device__ constexpr int smem_bytes(int mode, int block_i, int nkc, int stages) {
-  return 1024 + nkc * block_i * 128 + stages * STAGE_BYTES + (mode == 1 ? 2 * G_BYTES : 0) + SMALL_BYTES;
+  return nkc * block_i * 128 + stages * STAGE_BYTES + (mode == 1 ? 2 * G_BYTES : 0) + small_bytes(mode);
 }
 
 __device__ __forceinline__ float ex2(float x) {
@@ -117,27 +120,34 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   constexpr int NCH = HALF / 32;                // 32-column TMEM loads per tile per warp
   constexpr int S_COL0 = (MODE == 0) ? 0 : BWD_S_COL0;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
-  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
-  uint8_t* const smem = smem_raw + (base - raw_u32);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = ptx::smem_u32(smem);
+  if ((base & 1023u) != 0) __trap();   // SWIZZLE_128B operands need 1 KiB alignment (dynamic smem starts at 1 KiB)
 
   const uint32_t x_smem = base;
-  const uint32_t ring_smem = x_smem + p.nkc * X_CHUNK;
-  const uint32_t g_smem = ring_smem + p.num_stages * STAGE_BYTES;
+  const uint32_t ring_a = x_smem + p.nkc * X_CHUNK;
+  const uint32_t ring_b = ring_a + p.stages_a * STAGE_BYTES;
+  const uint32_t g_smem = ring_b + (MODE == 1 ? p.stages_b : 0) * STAGE_BYTES;
   const uint32_t small_off = (g_smem - base) + (MODE == 1 ? 2 * G_BYTES : 0);
   const uint32_t bars = base + small_off;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
-  constexpr int B_FULL = 0, B_EMPTY = MAX_STAGES, B_XFULL = 2 * MAX_STAGES, B_SFULL = B_XFULL + 1,
-                B_SEMPTY = B_SFULL + 2, B_GFULL = B_SEMPTY + 2, B_GEMPTY = B_GFULL + 2, B_ACCFULL = B_GEMPTY + 2;
+  constexpr int B_FULL_A = 0, B_EMPTY_A = MAX_STAGES, B_FULL_B = 2 * MAX_STAGES, B_EMPTY_B = 3 * MAX_STAGES,
+                B_XFULL = 4 * MAX_STAGES, B_SFULL = B_XFULL + 1, B_SEMPTY = B_SFULL + 2, B_GFULL = B_SEMPTY + 2,
+                B_GEMPTY = B_GFULL + 2, B_ACCFULL = B_GEMPTY + 2;
+  static_assert((B_ACCFULL + 1) * 8 <= 256, "barrier block");
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + small_off + 256);
-  float* const rx_s = reinterpret_cast<float*>(smem + small_off + 512);    // [BLOCK_I] rinv_x of the resident rows
-  float* const u_s = reinterpret_cast<float*>(smem + small_off + 1024);    // [BLOCK_I] (MODE 1)
-  float* const red = reinterpret_cast<float*>(smem + small_off + 1536);    // [8][64]
+  float* const rx_s = reinterpret_cast<float*>(smem + small_off + 512);                           // [BLOCK_I] rinv_x
+  float* const u_s = reinterpret_cast<float*>(smem + small_off + 512 + BLOCK_I * 4);              // [BLOCK_I] (MODE 1)
+  float* const red = reinterpret_cast<float*>(smem + small_off + (MODE == 1 ? 1024 : 1536));      // [8][64] / [8]
 
   const int warp = threadIdx.x >> 5;   // warp-uniform
   const int lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * BLOCK_I;
+  const int i0 = blockIdx.x * BLOCK_I;   // may lie beyond n_rows for the CTAs that pad the last cluster
+  const int csize = p.cluster;
+  const uint32_t crank = (csize > 1) ? ptx::cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  const int slice_rows = BLOCK_J / csize;            // rows of every streamed box this CTA fetches (for all)
+  const int nks = (p.nkc + 1) >> 1;                  // ring-A stages per logits tile (two K chunks each)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
@@ -146,8 +156,10 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      ptx::mbar_init(bar(B_FULL + s), 1);
-      ptx::mbar_init(bar(B_EMPTY + s), 1);
+      ptx::mbar_init(bar(B_FULL_A + s), 1);
+      ptx::mbar_init(bar(B_EMPTY_A + s), csize);   // every CTA of the cluster releases every stage everywhere
+      ptx::mbar_init(bar(B_FULL_B + s), 1);
+      ptx::mbar_init(bar(B_EMPTY_B + s), csize);
     }
     ptx::mbar_init(bar(B_XFULL), 1);
     for (int b = 0; b < 2; ++b) {
@@ -164,15 +176,30 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (csize > 1) ptx::cluster_sync(); else __syncthreads();   // peers' barriers must exist before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Issue-side design notes.  (1) Every issuing warp runs warp-uniform loops; all lanes wait on the
+  // barriers and one elected lane issues (inside an `if (lane == 0)` region ptxas wraps each
+  // UTCHMMA/UTMALDG in a waterfall loop).  (2) A ring stage carries K = 128 (two TMA boxes) so that one
+  // barrier round trip feeds 8 MMAs.  (3) The logits MMAs and the gradient MMAs are issued by two
+  // different warps from two different rings: with 128x64x16 instructions (32 tensor-clocks each) a
+  // single issuing thread, not the tensor pipe, was the limiter.
+  const uint32_t desc_hi = static_cast<uint32_t>(ptx::smem_desc_k_sw128(0) >> 32);   // SBO, version, swizzle mode
+  auto desc = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+  auto desc_lo = [&](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+  // one multicast-aware box load into `dst` (this CTA fetches its row slice for every CTA of the cluster)
+  auto load_box = [&](uint32_t dst, const CUtensorMap* m, uint32_t full_bar, int c0, int c1) {
+    if (csize == 1) ptx::tma_load_2d(dst, m, full_bar, c0, c1);
+    else ptx::tma_load_2d_mc(dst + crank * slice_rows * 128, m, full_bar, c0, c1 + crank * slice_rows, cmask);
+  };
+  auto commit_empty = [&](uint32_t b) {
+    if (csize == 1) ptx::mma_commit(b); else ptx::mma_commit_mc(b, cmask);
+  };
+
   if (warp == 0) {
-    // ======================================================================= TMA producer
-    // The whole warp runs the (warp-uniform) loops and waits; one elected lane issues the copies.
-    // Keeping control flow convergent lets ptxas hold addresses/descriptors in uniform registers;
-    // issuing from inside an `if (lane == 0)` region costs a waterfall loop around every UTMALDG.
+    // ======================================================================= producer A: X panel, then Y tiles
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar(B_XFULL), p.nkc * X_CHUNK);
       for (int kc = 0; kc < p.nkc; ++kc)
@@ -181,97 +208,102 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    auto push = [&](const CUtensorMap* m, int c0, int c1) {
-      ptx::mbar_wait(bar(B_EMPTY + stage), phase ^ 1u);
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(bar(B_FULL + stage), STAGE_BYTES);
-        ptx::tma_load_2d(ring_smem + stage * STAGE_BYTES, m, bar(B_FULL + stage), c0, c1);
+    for (int t = 0; t < p.n_jt; ++t) {
+      for (int ks = 0; ks < nks; ++ks) {
+        ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);   // free in EVERY CTA of the cluster
+        if (ptx::elect_one()) {
+          const int nsub = min(2, p.nkc - 2 * ks);
+          ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), nsub * BOX_BYTES);
+          for (int sub = 0; sub < nsub; ++sub)
+            load_box(ring_a + stage * STAGE_BYTES + sub * BOX_BYTES, &tmap_y, bar(B_FULL_A + stage),
+                     (2 * ks + sub) * BLOCK_K, t * BLOCK_J);
+        }
+        __syncwarp();
+        if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-    };
-    auto load_y = [&](int t) {   // Y[t*128 .. +128, :] as nkc K-major chunks
-      for (int kc = 0; kc < p.nkc; ++kc) push(&tmap_y, kc * BLOCK_K, t * BLOCK_J);
-    };
-    auto load_yt = [&](int t) {  // Y^T[:, t*128 .. +128] as nq x 2 chunks [128 d][64 j]
-      for (int q = 0; q < p.nq; ++q)
-        for (int kk = 0; kk < 2; ++kk) push(&tmap_yt, t * BLOCK_J + kk * BLOCK_K, q * 128);
-    };
-    if (MODE == 0) {
-      for (int t = 0; t < p.n_jt; ++t) load_y(t);
-    } else {
-      load_y(0);
-      for (int t = 0; t < p.n_jt; ++t) {
-        if (t + 1 < p.n_jt) load_y(t + 1);
-        load_yt(t);
+    }
+  } else if (warp == 2 && MODE == 1) {
+    // ======================================================================= producer B: Y^T tiles [128 d][128 j]
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < p.n_jt; ++t) {
+      for (int q = 0; q < p.nq; ++q) {
+        ptx::mbar_wait(bar(B_EMPTY_B + stage), phase ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), STAGE_BYTES);
+          for (int kk = 0; kk < 2; ++kk)
+            load_box(ring_b + stage * STAGE_BYTES + kk * BOX_BYTES, &tmap_yt, bar(B_FULL_B + stage),
+                     t * BLOCK_J + kk * BLOCK_K, q * 128);
+        }
+        __syncwarp();
+        if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ======================================================================= MMA issuer
-    // Same structure: warp-uniform loops, all lanes wait on the barriers, one elected lane (always
-    // the same one, so tcgen05.commit tracks its own MMAs) issues.
+    // ======================================================================= logits MMA issuer
     constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
-    constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, 64);
-    const uint64_t desc_hi = ptx::smem_desc_k_sw128(0) & 0xFFFFFFFF00000000ull;   // SBO, version, swizzle mode
-    auto desc = [&](uint32_t addr) -> uint64_t {
-      return desc_hi | (1ull << 16) | static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
-    };
+    const uint32_t a_lo0 = desc_lo(ring_a), x_lo0 = desc_lo(x_smem);
     int stage = 0;
     uint32_t phase = 0;
     ptx::mbar_wait(bar(B_XFULL), 0);
-    auto mma_s = [&](int t) {
+    for (int t = 0; t < p.n_jt; ++t) {
       const int b = t & 1;
-      ptx::mbar_wait(bar(B_SEMPTY + b), ((t >> 1) & 1) ^ 1u);
+      ptx::mbar_wait(bar(B_SEMPTY + b), ((t >> 1) & 1) ^ 1u);   // epilogue drained this S buffer (tile t-2)
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + S_COL0 + b * BLOCK_I;
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        ptx::mbar_wait(bar(B_FULL + stage), phase);
+      for (int ks = 0; ks < nks; ++ks) {
+        ptx::mbar_wait(bar(B_FULL_A + stage), phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint64_t a0 = desc(ring_smem + stage * STAGE_BYTES);
-          const uint64_t b0 = desc(x_smem + kc * X_CHUNK);
+          const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);
+          const uint32_t b_lo = x_lo0 + ks * (2 * X_CHUNK >> 4);
+          const int nsub = min(2, p.nkc - 2 * ks);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
-            ptx::mma_f16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc_s, (kc | k) != 0);
-          ptx::mma_commit(bar(B_EMPTY + stage));
-          if (kc == p.nkc - 1) ptx::mma_commit(bar(B_SFULL + b));
-        }
-        __syncwarp();
-        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
-      }
-    };
-    auto mma_g = [&](int t) {
-      const int b = t & 1;
-      ptx::mbar_wait(bar(B_GFULL + b), (t >> 1) & 1);
-      ptx::tc_fence_after();
-      for (int q = 0; q < p.nq; ++q) {
-        for (int kk = 0; kk < 2; ++kk) {
-          ptx::mbar_wait(bar(B_FULL + stage), phase);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t a0 = desc(ring_smem + stage * STAGE_BYTES);                // Y^T chunk [128 d][64 j]
-            const uint64_t b0 = desc(g_smem + b * G_BYTES + kk * (G_BYTES / 2));      // G chunk   [ 64 i][64 j]
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub < nsub) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              ptx::mma_f16(tmem_base + q * 64, a0 + 2 * k, b0 + 2 * k, idesc_g, (t | kk | k) != 0);
-            ptx::mma_commit(bar(B_EMPTY + stage));
-            if (q == p.nq - 1 && kk == 1) {
-              ptx::mma_commit(bar(B_GEMPTY + b));
-              if (t == p.n_jt - 1) ptx::mma_commit(bar(B_ACCFULL));
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
+                ptx::mma_f16(d_tmem, desc(a_lo + sub * (BOX_BYTES >> 4) + 2 * k),
+                             desc(b_lo + sub * (X_CHUNK >> 4) + 2 * k), idesc_s, (ks | sub | k) != 0);
             }
           }
-          __syncwarp();
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          commit_empty(bar(B_EMPTY_A + stage));
+          if (ks == nks - 1) ptx::mma_commit(bar(B_SFULL + b));
         }
+        __syncwarp();
+        if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
       }
-    };
-    if (MODE == 0) {
-      for (int t = 0; t < p.n_jt; ++t) mma_s(t);
-    } else {
-      mma_s(0);
-      for (int t = 0; t < p.n_jt; ++t) {
-        if (t + 1 < p.n_jt) mma_s(t + 1);   // keeps the tensor core busy while tile t is in the epilogue
-        mma_g(t);
+    }
+  } else if (warp == 3 && MODE == 1) {
+    // ======================================================================= gradient MMA issuer
+    constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, 64);
+    const uint32_t a_lo0 = desc_lo(ring_b), g_lo0 = desc_lo(g_smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < p.n_jt; ++t) {
+      const int b = t & 1;
+      ptx::mbar_wait(bar(B_GFULL + b), (t >> 1) & 1);            // epilogue wrote the bf16 gradient tile t
+      ptx::tc_fence_after();
+      for (int q = 0; q < p.nq; ++q) {
+        ptx::mbar_wait(bar(B_FULL_B + stage), phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);     // Y^T boxes  [128 d][64 j] x 2
+          const uint32_t b_lo = g_lo0 + b * (G_BYTES >> 4);             // G chunks   [ 64 i][64 j] x 2
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              ptx::mma_f16(tmem_base + q * 64, desc(a_lo + kk * (BOX_BYTES >> 4) + 2 * k),
+                           desc(b_lo + kk * (G_BYTES >> 5) + 2 * k), idesc_g, (t | kk | k) != 0);
+          commit_empty(bar(B_EMPTY_B + stage));
+          if (q == p.nq - 1) {
+            ptx::mma_commit(bar(B_GEMPTY + b));
+            if (t == p.n_jt - 1) ptx::mma_commit(bar(B_ACCFULL));
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
@@ -281,7 +313,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int h = e >> 2;          // which half of the tile's columns
     const int j_local = q * 32 + lane;
     const int te = threadIdx.x - 128;
-    const int i_valid = min(BLOCK_I, p.n_rows - i0);
+    const int i_valid = max(0, min(BLOCK_I, p.n_rows - i0));
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const long long dcol0 = (long long)i0 + p.diag_offset;   // column of the positive of block row 0
 
@@ -368,6 +400,20 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     } else {
       float ds = 0.f;
+      // Per-row constants of this thread's 32 TMEM columns live in registers for the whole sweep, and the
+      // element loop is straight-line code (the rare diagonal / ragged tiles take a separate masked loop):
+      // 32 independent chains the scheduler can interleave, no shared-memory loads, one ex2 per logit.
+      float rxk[32], u_r[32];
+#pragma unroll
+      for (int x = 0; x < 32; ++x) {
+        rxk[x] = rx_s[h * 32 + x];
+        u_r[x] = u_s[h * 32 + x];
+      }
+      const int jj = j_local & 63;
+      uint32_t row_off[8];   // byte offset of (row i, column jj) inside an 8-row swizzle group, i & 7 = k
+#pragma unroll
+      for (int k = 0; k < 8; ++k) row_off[k] = k * 128 + (((jj >> 3) ^ k) << 4) + (jj & 7) * 2;
+      uint8_t* const g_gen = smem + (g_smem - base) + (j_local >> 6) * (G_BYTES / 2) + h * 4096;
       for (int t = 0; t < p.n_jt; ++t) {
         const int b = t & 1;
         ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
@@ -385,26 +431,32 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const float ryj = jvalid ? p.rinv_y[jg] : 0.f;
         const float cj = ryj * p.k2;
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
-        const bool plain = jvalid && (i_valid == BLOCK_I) && !diag_tile;
-        const long long id = jg - dcol0 - h * 32;
-
-        ptx::mbar_wait(bar(B_GEMPTY + b), ((t >> 1) & 1) ^ 1u);   // gradient MMA of tile t-2 has read this buffer
-        const int jj = j_local & 63;
-        const uint32_t g_row0 = g_smem + b * G_BYTES + (j_local >> 6) * (G_BYTES / 2) + (jj & 7) * 2;
+        const bool plain = (i_valid == BLOCK_I) && !diag_tile && (long long)(t + 1) * BLOCK_J <= p.n_cols;  // warp-uniform
+        float g[32];
+        if (plain) {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const int i = h * 32 + x;
-          const float y = __uint_as_float(r[x]) * rx_s[i] * cj;      // S_ij * log2(e)
-          float g = ex2(y - p.k2) * (u_s[i] + vj);
-          if (!plain) {
-            if (id == x) g -= p.diag_w;
-            if (!(jvalid && i < i_valid)) g = 0.f;
+          for (int x = 0; x < 32; ++x) {
+            const float y = __uint_as_float(r[x]) * rxk[x] * cj;      // S_ij * log2(e)
+            g[x] = ex2(y - p.k2) * (u_r[x] + vj);
+            ds = fmaf(g[x], y, ds);
           }
-          ds = fmaf(g, y, ds);
-          const uint32_t addr = g_row0 + (i >> 3) * 1024 + (i & 7) * 128 + ((((jj >> 3) ^ (i & 7))) << 4);
-          const __nv_bfloat16 gb = __float2bfloat16_rn(g * ryj);   // contracted against the RAW y_j
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&gb)) : "memory");
+        } else {
+          const long long id = jg - dcol0 - h * 32;
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const float y = __uint_as_float(r[x]) * rxk[x] * cj;
+            float gv = ex2(y - p.k2) * (u_r[x] + vj);
+            if (id == x) gv -= p.diag_w;
+            if (!(jvalid && h * 32 + x < i_valid)) gv = 0.f;
+            g[x] = gv;
+            ds = fmaf(gv, y, ds);
+          }
         }
+        ptx::mbar_wait(bar(B_GEMPTY + b), ((t >> 1) & 1) ^ 1u);   // gradient MMA of tile t-2 has read this buffer
+        uint8_t* const gb_base = g_gen + b * G_BYTES;
+#pragma unroll
+        for (int x = 0; x < 32; ++x)   // contracted against the RAW y_j -> fold rinv_y[j] into G
+          *reinterpret_cast<__nv_bfloat16*>(gb_base + (x >> 3) * 1024 + row_off[x & 7]) = __float2bfloat16_rn(g[x] * ryj);
         ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar(B_GFULL + b));
@@ -441,7 +493,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (csize > 1) ptx::cluster_sync(); else __syncthreads();   // no CTA may exit while peers still multicast into it
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
