@@ -54,7 +54,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
-bool g_attr_done[3] = {false, false, false};
+bool g_attr_done[4] = {false, false, false, false};
 
 int get_encode(EncodeTiledFn* out) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -101,7 +101,7 @@ int check_device_sm100() {
 int cluster_size(int64_t n_blocks) {
   const char* e = getenv("CLIPNCE_CLUSTER");
   const int v = e ? atoi(e) : 0;
-  int c = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+  int c = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 1;   // measured: the kernels are not L2-bound, multicast does not pay
   while (c > 1 && n_blocks < 2 * c) c >>= 1;   // tiny problems: do not pad the grid with idle CTAs
   return c;
 }
@@ -111,16 +111,19 @@ int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const
               int grid, cudaStream_t st) {
   auto kern = tc::clip_tc_kernel<MODE, BLOCK_I>;
   const int fixed = tc::smem_bytes(MODE, BLOCK_I, p.nkc, 0);
-  int stages = (tc::SMEM_LIMIT - fixed) / tc::STAGE_BYTES;   // 32 KiB stages shared by the two rings
-  if (stages < (MODE == 1 ? 2 : 1)) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for a TMA ring", p.d);
+  const int total_boxes = (tc::SMEM_LIMIT - fixed) / tc::BOX_BYTES;   // 16 KiB TMA boxes the ring(s) can hold
+  if (total_boxes < (MODE == 1 ? 2 : 1)) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for a TMA ring", p.d);
+  p.boxes = total_boxes >= 8 ? 2 : 1;          // K = 128 per stage when the rings stay >= 4 stages deep in total
+  int stages = total_boxes / p.boxes;
+  auto cap = [](int v) { return v > tc::MAX_STAGES ? tc::MAX_STAGES : v; };
   if (MODE == 1) {
-    p.stages_b = stages / 2 > tc::MAX_STAGES ? tc::MAX_STAGES : stages / 2;
-    p.stages_a = stages - p.stages_b > tc::MAX_STAGES ? tc::MAX_STAGES : stages - p.stages_b;
+    p.stages_b = cap(stages / 2);
+    p.stages_a = cap(stages - stages / 2);
   } else {
-    p.stages_a = stages > tc::MAX_STAGES ? tc::MAX_STAGES : stages;
+    p.stages_a = cap(stages);
     p.stages_b = 0;
   }
-  const int smem = tc::smem_bytes(MODE, BLOCK_I, p.nkc, p.stages_a + p.stages_b);
+  const int smem = tc::smem_bytes(MODE, BLOCK_I, p.nkc, (p.stages_a + p.stages_b) * p.boxes);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_attr_done[attr_slot]) {
@@ -146,6 +149,13 @@ int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const
 }
 
 int fwd_block_i(int64_t n_rows, int64_t d) { return (d <= 512 && n_rows >= 128 * 148) ? 128 : 64; }
+// 64 rows (two logits buffers, deeper rings) measured faster than 96 rows (one buffer, 16 KiB stages) on B200
+// (9.6 vs 11.4 ms per side at N = 65536, d = 512); CLIPNCE_BWD_ROWS=96 selects the wider variant.
+int bwd_block_i(int64_t d) {
+  const char* e = getenv("CLIPNCE_BWD_ROWS");
+  if (e && atoi(e) == 96 && d <= 512) return 96;
+  return 64;
+}
 
 struct SimtFwdWs {
   float *row_pm, *row_pl, *col_pm, *col_pl;
@@ -324,12 +334,15 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     if (ld_t < n_cols || ld_t % 8 != 0) return fail(CLIPNCE_EINVAL, "backward: ld_t must be >= n_cols and a multiple of 8");
     if (!aligned16(x) || !aligned16(y) || !aligned16(y_t))
       return fail(CLIPNCE_EINVAL, "backward: operands must be 16-byte aligned");
-    const int64_t n_ib = ceil_div(n_rows, 64);
+    // rows per CTA: the gradient accumulators (ceil(d/128) * BLOCK_I TMEM columns) plus the logits buffer(s) share
+    // the 512 TMEM columns -> 96 rows with one logits buffer up to d = 512, else 64 rows with two
+    const int bi = bwd_block_i(d);
+    const int64_t n_ib = ceil_div(n_rows, bi);
     const size_t need = sizeof(float) * (size_t)n_ib;
     if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
     const int cl = cluster_size(n_ib);
     CUtensorMap tx, ty, tyt;
-    if ((rc = make_tmap(&tx, x, d, n_rows, d, 64))) return rc;
+    if ((rc = make_tmap(&tx, x, d, n_rows, d, bi))) return rc;
     if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J / cl))) return rc;
     if ((rc = make_tmap(&tyt, y_t, n_cols, d, ld_t, 128 / cl))) return rc;
     tc::Params p;
@@ -341,7 +354,9 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     p.rinv_x = rinv_x; p.rinv_y = rinv_y;
     p.row_m_in = row_m; p.row_w = row_w; p.col_m_in = col_m; p.col_w = col_w; p.diag_w = diag_w; p.out_scale = grad_out * scale;
     p.dx = dx_hat; p.ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
-    if ((rc = launch_tc<1, 64>(2, tx, ty, tyt, p, (int)n_ib, st))) return rc;
+    if (bi == 96) rc = launch_tc<1, 96>(3, tx, ty, tyt, p, (int)n_ib, st);
+    else          rc = launch_tc<1, 64>(2, tx, ty, tyt, p, (int)n_ib, st);
+    if (rc) return rc;
     if (d_scale_sum) {
       aux::reduce_scalar_partials<<<1, 32, 0, st>>>(p.ds_part, (int)n_ib, grad_out, d_scale_sum);
       CUDA_TRY(cudaGetLastError());

@@ -1,30 +1,36 @@
 // tcgen05 / TMEM / TMA kernels for the contrastive hot path (sm_100a only).
 //
-// One kernel template, two modes, both sweeping the logits S = s * Xhat Yhat^T tile by tile without
-// ever writing S (or G) to HBM:
+// One kernel template, two modes, both sweeping the logits S_ij = s rinv_x[i] rinv_y[j] <x_i, y_j>
+// tile by tile without ever writing S (or its gradient G) to HBM:
 //
 //   MODE 0  forward statistics   row sums  sum_j exp(S_ij - s),  column partial sums, diagonal
 //   MODE 1  backward, one side   dXhat = s * G Yhat,  G_ij = exp(S_ij - s)(u_i + v_j) - w [j == i+off]
 //
-// Orientation.  A CTA owns BLOCK_I rows of Xhat (resident in shared memory for the whole sweep) and
-// streams 128-row tiles of Yhat.  The logits tile is computed TRANSPOSED,
-//       St[j (128 TMEM lanes), i (BLOCK_I TMEM columns)] = Yhat_J . Xhat_I^T        (UMMA 128 x BLOCK_I x 16)
-// so that epilogue thread <-> lane <-> column j of S:  per-column quantities (v_j, the column
-// partial sum) are thread-local scalars, per-row quantities (u_i, the row sums) are register arrays
+// Orientation.  A CTA owns BLOCK_I rows of X (resident in shared memory for the whole sweep) and
+// streams 128-row tiles of Y.  The logits tile is computed TRANSPOSED,
+//       St[j (128 TMEM lanes), i (BLOCK_I TMEM columns)] = Y_J . X_I^T               (UMMA 128 x BLOCK_I x 16)
+// so that epilogue thread <-> lane <-> column j of S:  per-column quantities (rinv_y[j], v_j, the
+// column partial sum) are thread-local scalars, per-row quantities (rinv_x[i], u_i, the row sums) are
 // indexed by the TMEM column, accumulated thread-locally over the whole sweep and reduced across
-// lanes once per CTA.  No shuffle, no shared-memory traffic in the per-element path.
+// lanes once per CTA.  No shuffle in the per-element path.  The normalise is fused here: the tensor
+// cores see the caller's raw bf16 rows and rinv_x[i] * rinv_y[j] scales the fp32 accumulator.
 //
 // In MODE 1 the gradient tile is rounded to bf16, written to shared memory as the K-major B operand
 // of a second MMA and contracted against the TRANSPOSED streamed operand:
-//       dXhat^T[d (128 lanes, nq chunks), i (64 columns)] += Yhat^T[d, j] . G^T[j, i]   (UMMA 128 x 64 x 16)
-// The accumulators (nq * 64 <= 384 TMEM columns) stay resident for the whole sweep; the two S
-// buffers use the remaining 128 columns.  Every MMA operand is the same canonical layout: K-major,
-// 128-byte rows, SWIZZLE_128B (what a TMA box {64 elems, R rows} writes), so one descriptor builder
-// serves all of them.
+//       dXhat^T[d (128 lanes, nq chunks), i (BLOCK_I columns)] += Y^T[d, j] . G^T[j, i]  (UMMA 128 x BLOCK_I x 16)
+// The accumulators (nq * BLOCK_I TMEM columns) stay resident for the whole sweep; the S buffer(s) use
+// the remaining columns: BLOCK_I = 96 with one S buffer when d <= 512, else 64 with two.  Every MMA
+// operand is the same canonical layout: K-major, 128-byte rows, SWIZZLE_128B (what a TMA box
+// {64 elems, R rows} writes), so one descriptor builder serves all of them.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM
-// allocator, warp 3 idle, warps 4-11 epilogue (two warps per TMEM lane quarter, each taking half of
-// the tile's columns).
+// What bounds it (ncu, profiles/): with 128 x BLOCK_I x 16 instructions the operands stream through
+// shared memory faster than they are consumed per byte -- TMA writes + UMMA operand reads saturate the
+// 128 B/clk shared-memory port before the tensor pipe fills.  Hence the largest BLOCK_I that TMEM
+// allows, separate issue warps (a single issuing thread was the first limiter), and K = 128 stages.
+//
+// Warp roles (384 threads): warp 0 TMA producer A (X panel, Y boxes), warp 1 logits-MMA issuer,
+// warp 2 TMEM allocator + TMA producer B (Y^T boxes), warp 3 gradient-MMA issuer, warps 4-11 epilogue
+// (two warps per TMEM lane quarter, each taking half of the tile's columns).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -38,23 +44,23 @@ constexpr int BLOCK_J = 128;                         // streamed rows per tile =
 constexpr int BLOCK_K = 64;                          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int BOX_BYTES = BLOCK_J * BLOCK_K * 2;     // one TMA box [128 rows][64 elems] = 16 KiB
-constexpr int STAGE_BYTES = 2 * BOX_BYTES;           // a ring stage = two boxes (K = 128): 8 MMAs per barrier round trip
-constexpr int G_BYTES = 64 * BLOCK_J * 2;            // one bf16 gradient tile [64 i][128 j]
-constexpr int MAX_STAGES = 4;                        // per ring
+constexpr int MAX_STAGES = 5;                        // per ring
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr int BWD_S_COL0 = 384;                      // S buffers of MODE 1 live at TMEM columns 384..511
-__host__ __device__ constexpr int small_bytes(int mode) { return mode == 1 ? 1536 : 3584; }  // barriers, tmem ptr, u/rinv, scratch
 constexpr int SMEM_LIMIT = 232448;                   // 227 KiB opt-in maximum per CTA
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
+__host__ __device__ constexpr int small_bytes(int mode) { return mode == 1 ? 1536 : 3584; }  // barriers, tmem ptr, u/rinv, scratch
+__host__ __device__ constexpr int g_bytes(int block_i) { return block_i * BLOCK_J * 2; }     // bf16 gradient tile [i][128 j]
+__host__ __device__ constexpr int num_s_buffers(int mode, int block_i) { return (mode == 1 && block_i > 64) ? 1 : 2; }
 
 struct Params {
   int n_rows, n_cols, d;
-  int nkc;         // ceil(d / 64)   contraction chunks of the logits MMA
+  int nkc;         // ceil(d / 64)   K boxes per logits tile
   int nq;          // ceil(d / 128)  accumulator chunks of the gradient MMA
   int n_jt;        // ceil(n_cols / 128)
+  int boxes;       // TMA boxes per ring stage (1 or 2): K = 64 or 128 per barrier round trip
   int stages_a;    // ring A: streamed Y boxes for the logits MMA
   int stages_b;    // ring B: streamed Y^T boxes for the gradient MMA (MODE 1)
   int cluster;     // CTAs per cluster sharing the streamed tiles through TMA multicast (1, 2, 4 or 8)
@@ -80,8 +86,8 @@ struct Params {
   float* ds_part;      // [gridDim.x]  sum G.S of this CTA
 };
 
-__host__ __device__ constexpr int smem_bytes(int mode, int block_i, int nkc, int stages) {
-  return nkc * block_i * 128 + stages * STAGE_BYTES + (mode == 1 ? 2 * G_BYTES : 0) + small_bytes(mode);
+__host__ __device__ constexpr int smem_bytes(int mode, int block_i, int nkc, int ring_boxes) {
+  return nkc * block_i * 128 + ring_boxes * BOX_BYTES + (mode == 1 ? 2 * g_bytes(block_i) : 0) + small_bytes(mode);
 }
 
 __device__ __forceinline__ float ex2(float x) {
@@ -113,21 +119,24 @@ template <int MODE, int BLOCK_I>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                const __grid_constant__ CUtensorMap tmap_yt, const Params p) {
-  static_assert(BLOCK_I == 64 || BLOCK_I == 128, "BLOCK_I");
-  static_assert(MODE == 0 || BLOCK_I == 64, "backward keeps 64 rows per CTA");
+  static_assert(BLOCK_I == 64 || BLOCK_I == 96 || BLOCK_I == 128, "BLOCK_I");
+  static_assert(MODE == 1 || BLOCK_I != 96, "forward uses 64 or 128 rows per CTA");
+  static_assert(MODE == 0 || BLOCK_I != 128, "backward: accumulators + logits must fit 512 TMEM columns");
   constexpr int X_CHUNK = BLOCK_I * 128;        // bytes of one [BLOCK_I rows x 64 k] chunk of the resident panel
   constexpr int HALF = BLOCK_I / 2;             // TMEM columns per epilogue warp
-  constexpr int NCH = HALF / 32;                // 32-column TMEM loads per tile per warp
-  constexpr int S_COL0 = (MODE == 0) ? 0 : BWD_S_COL0;
+  constexpr int NSBUF = num_s_buffers(MODE, BLOCK_I);
+  constexpr int S_COL0 = (MODE == 0) ? 0 : TMEM_COLS - NSBUF * BLOCK_I;
+  constexpr int G_BYTES = g_bytes(BLOCK_I);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ptx::smem_u32(smem);
   if ((base & 1023u) != 0) __trap();   // SWIZZLE_128B operands need 1 KiB alignment (dynamic smem starts at 1 KiB)
 
+  const int stage_bytes = p.boxes * BOX_BYTES;
   const uint32_t x_smem = base;
   const uint32_t ring_a = x_smem + p.nkc * X_CHUNK;
-  const uint32_t ring_b = ring_a + p.stages_a * STAGE_BYTES;
-  const uint32_t g_smem = ring_b + (MODE == 1 ? p.stages_b : 0) * STAGE_BYTES;
+  const uint32_t ring_b = ring_a + p.stages_a * stage_bytes;
+  const uint32_t g_smem = ring_b + (MODE == 1 ? p.stages_b : 0) * stage_bytes;
   const uint32_t small_off = (g_smem - base) + (MODE == 1 ? 2 * G_BYTES : 0);
   const uint32_t bars = base + small_off;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
@@ -136,9 +145,10 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 B_GEMPTY = B_GFULL + 2, B_ACCFULL = B_GEMPTY + 2;
   static_assert((B_ACCFULL + 1) * 8 <= 256, "barrier block");
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + small_off + 256);
-  float* const rx_s = reinterpret_cast<float*>(smem + small_off + 512);                           // [BLOCK_I] rinv_x
-  float* const u_s = reinterpret_cast<float*>(smem + small_off + 512 + BLOCK_I * 4);              // [BLOCK_I] (MODE 1)
-  float* const red = reinterpret_cast<float*>(smem + small_off + (MODE == 1 ? 1024 : 1536));      // [8][64] / [8]
+  float* const rx_s = reinterpret_cast<float*>(smem + small_off + 512);                            // [BLOCK_I] rinv_x
+  float* const u_s = reinterpret_cast<float*>(smem + small_off + 512 + BLOCK_I * 4);               // [BLOCK_I] (MODE 1)
+  float* const red = reinterpret_cast<float*>(smem + small_off + (MODE == 1 ? 512 + BLOCK_I * 8 : 1536));  // [8] / [8][64]
+  static_assert(MODE == 0 || 512 + BLOCK_I * 8 + 64 <= small_bytes(1), "small block");
 
   const int warp = threadIdx.x >> 5;   // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -147,7 +157,8 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const uint32_t crank = (csize > 1) ? ptx::cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
   const int slice_rows = BLOCK_J / csize;            // rows of every streamed box this CTA fetches (for all)
-  const int nks = (p.nkc + 1) >> 1;                  // ring-A stages per logits tile (two K chunks each)
+  const int nga = p.nkc;                             // ring-A boxes per tile (K chunks of the logits MMA)
+  const int ngb = 2 * p.nq;                          // ring-B boxes per tile ((d chunk, j half) of the gradient MMA)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
@@ -180,12 +191,10 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // Issue-side design notes.  (1) Every issuing warp runs warp-uniform loops; all lanes wait on the
-  // barriers and one elected lane issues (inside an `if (lane == 0)` region ptxas wraps each
-  // UTCHMMA/UTMALDG in a waterfall loop).  (2) A ring stage carries K = 128 (two TMA boxes) so that one
-  // barrier round trip feeds 8 MMAs.  (3) The logits MMAs and the gradient MMAs are issued by two
-  // different warps from two different rings: with 128x64x16 instructions (32 tensor-clocks each) a
-  // single issuing thread, not the tensor pipe, was the limiter.
+  // Issue-side design.  (1) Every issuing warp runs warp-uniform loops; all lanes wait on the barriers
+  // and one elected lane issues (inside an `if (lane == 0)` region ptxas wraps each UTCHMMA/UTMALDG in a
+  // waterfall loop).  (2) A ring stage can carry two boxes (K = 128) so one barrier round trip feeds 8
+  // MMAs.  (3) Logits MMAs and gradient MMAs are issued by two different warps from two different rings.
   const uint32_t desc_hi = static_cast<uint32_t>(ptx::smem_desc_k_sw128(0) >> 32);   // SBO, version, swizzle mode
   auto desc = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
   auto desc_lo = [&](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
@@ -209,31 +218,34 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < p.n_jt; ++t) {
-      for (int ks = 0; ks < nks; ++ks) {
+      for (int g0 = 0; g0 < nga; g0 += p.boxes) {
         ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);   // free in EVERY CTA of the cluster
         if (ptx::elect_one()) {
-          const int nsub = min(2, p.nkc - 2 * ks);
+          const int nsub = min(p.boxes, nga - g0);
           ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), nsub * BOX_BYTES);
           for (int sub = 0; sub < nsub; ++sub)
-            load_box(ring_a + stage * STAGE_BYTES + sub * BOX_BYTES, &tmap_y, bar(B_FULL_A + stage),
-                     (2 * ks + sub) * BLOCK_K, t * BLOCK_J);
+            load_box(ring_a + stage * stage_bytes + sub * BOX_BYTES, &tmap_y, bar(B_FULL_A + stage),
+                     (g0 + sub) * BLOCK_K, t * BLOCK_J);
         }
         __syncwarp();
         if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 2 && MODE == 1) {
-    // ======================================================================= producer B: Y^T tiles [128 d][128 j]
+    // ======================================================================= producer B: Y^T boxes [128 d][64 j]
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < p.n_jt; ++t) {
-      for (int q = 0; q < p.nq; ++q) {
+      for (int g0 = 0; g0 < ngb; g0 += p.boxes) {
         ptx::mbar_wait(bar(B_EMPTY_B + stage), phase ^ 1u);
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), STAGE_BYTES);
-          for (int kk = 0; kk < 2; ++kk)
-            load_box(ring_b + stage * STAGE_BYTES + kk * BOX_BYTES, &tmap_yt, bar(B_FULL_B + stage),
-                     t * BLOCK_J + kk * BLOCK_K, q * 128);
+          const int nsub = min(p.boxes, ngb - g0);
+          ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), nsub * BOX_BYTES);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int g = g0 + sub;   // (d chunk g >> 1, j half g & 1)
+            load_box(ring_b + stage * stage_bytes + sub * BOX_BYTES, &tmap_yt, bar(B_FULL_B + stage),
+                     t * BLOCK_J + (g & 1) * BLOCK_K, (g >> 1) * 128);
+          }
         }
         __syncwarp();
         if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
@@ -247,28 +259,28 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     uint32_t phase = 0;
     ptx::mbar_wait(bar(B_XFULL), 0);
     for (int t = 0; t < p.n_jt; ++t) {
-      const int b = t & 1;
-      ptx::mbar_wait(bar(B_SEMPTY + b), ((t >> 1) & 1) ^ 1u);   // epilogue drained this S buffer (tile t-2)
+      const int sb = t % NSBUF;
+      ptx::mbar_wait(bar(B_SEMPTY + sb), ((t / NSBUF) & 1) ^ 1u);   // epilogue drained this S buffer
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + S_COL0 + b * BLOCK_I;
-      for (int ks = 0; ks < nks; ++ks) {
+      const uint32_t d_tmem = tmem_base + S_COL0 + sb * BLOCK_I;
+      for (int g0 = 0; g0 < nga; g0 += p.boxes) {
         ptx::mbar_wait(bar(B_FULL_A + stage), phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);
-          const uint32_t b_lo = x_lo0 + ks * (2 * X_CHUNK >> 4);
-          const int nsub = min(2, p.nkc - 2 * ks);
+          const uint32_t a_lo = a_lo0 + stage * (stage_bytes >> 4);
+          const uint32_t b_lo = x_lo0 + g0 * (X_CHUNK >> 4);
+          const int nsub = min(p.boxes, nga - g0);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             if (sub < nsub) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
                 ptx::mma_f16(d_tmem, desc(a_lo + sub * (BOX_BYTES >> 4) + 2 * k),
-                             desc(b_lo + sub * (X_CHUNK >> 4) + 2 * k), idesc_s, (ks | sub | k) != 0);
+                             desc(b_lo + sub * (X_CHUNK >> 4) + 2 * k), idesc_s, (g0 | sub | k) != 0);
             }
           }
           commit_empty(bar(B_EMPTY_A + stage));
-          if (ks == nks - 1) ptx::mma_commit(bar(B_SFULL + b));
+          if (g0 + p.boxes >= nga) ptx::mma_commit(bar(B_SFULL + sb));
         }
         __syncwarp();
         if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
@@ -276,29 +288,34 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 3 && MODE == 1) {
     // ======================================================================= gradient MMA issuer
-    constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, 64);
+    constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
     const uint32_t a_lo0 = desc_lo(ring_b), g_lo0 = desc_lo(g_smem);
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < p.n_jt; ++t) {
-      const int b = t & 1;
-      ptx::mbar_wait(bar(B_GFULL + b), (t >> 1) & 1);            // epilogue wrote the bf16 gradient tile t
+      const int gb = t & 1;
+      ptx::mbar_wait(bar(B_GFULL + gb), (t >> 1) & 1);            // epilogue wrote the bf16 gradient tile t
       ptx::tc_fence_after();
-      for (int q = 0; q < p.nq; ++q) {
+      for (int g0 = 0; g0 < ngb; g0 += p.boxes) {
         ptx::mbar_wait(bar(B_FULL_B + stage), phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);     // Y^T boxes  [128 d][64 j] x 2
-          const uint32_t b_lo = g_lo0 + b * (G_BYTES >> 4);             // G chunks   [ 64 i][64 j] x 2
+          const uint32_t a_lo = a_lo0 + stage * (stage_bytes >> 4);     // Y^T boxes [128 d][64 j]
+          const uint32_t b_lo = g_lo0 + gb * (G_BYTES >> 4);            // G chunks  [BLOCK_I i][64 j] x 2
+          const int nsub = min(p.boxes, ngb - g0);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub < nsub) {
+              const int g = g0 + sub, q = g >> 1, kk = g & 1;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              ptx::mma_f16(tmem_base + q * 64, desc(a_lo + kk * (BOX_BYTES >> 4) + 2 * k),
-                           desc(b_lo + kk * (G_BYTES >> 5) + 2 * k), idesc_g, (t | kk | k) != 0);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                ptx::mma_f16(tmem_base + q * BLOCK_I, desc(a_lo + sub * (BOX_BYTES >> 4) + 2 * k),
+                             desc(b_lo + kk * (G_BYTES >> 5) + 2 * k), idesc_g, (t | kk | k) != 0);
+            }
+          }
           commit_empty(bar(B_EMPTY_B + stage));
-          if (q == p.nq - 1) {
-            ptx::mma_commit(bar(B_GEMPTY + b));
+          if (g0 + p.boxes >= ngb) {
+            ptx::mma_commit(bar(B_GEMPTY + gb));
             if (t == p.n_jt - 1) ptx::mma_commit(bar(B_ACCFULL));
           }
         }
@@ -326,6 +343,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     epi_bar_sync();
 
     if (MODE == 0) {
+      constexpr int NCH = HALF / 32;                // 32-column TMEM loads per tile per warp
       float racc[HALF];
 #pragma unroll
       for (int i = 0; i < HALF; ++i) racc[i] = 0.f;
@@ -399,32 +417,20 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
     } else {
+      // This thread owns column j of the logits tile and HALF consecutive rows i (TMEM columns), handled in
+      // groups of 16.  The element loops are straight-line code (the rare diagonal / ragged tiles take a
+      // separate masked loop): independent chains the scheduler interleaves, one ex2 per logit.
+      constexpr int NG = HALF / 16;
       float ds = 0.f;
-      // Per-row constants of this thread's 32 TMEM columns live in registers for the whole sweep, and the
-      // element loop is straight-line code (the rare diagonal / ragged tiles take a separate masked loop):
-      // 32 independent chains the scheduler can interleave, no shared-memory loads, one ex2 per logit.
-      float rxk[32], u_r[32];
-#pragma unroll
-      for (int x = 0; x < 32; ++x) {
-        rxk[x] = rx_s[h * 32 + x];
-        u_r[x] = u_s[h * 32 + x];
-      }
       const int jj = j_local & 63;
       uint32_t row_off[8];   // byte offset of (row i, column jj) inside an 8-row swizzle group, i & 7 = k
 #pragma unroll
       for (int k = 0; k < 8; ++k) row_off[k] = k * 128 + (((jj >> 3) ^ k) << 4) + (jj & 7) * 2;
-      uint8_t* const g_gen = smem + (g_smem - base) + (j_local >> 6) * (G_BYTES / 2) + h * 4096;
+      uint8_t* const g_gen = smem + (g_smem - base) + (j_local >> 6) * (G_BYTES / 2) + (h * HALF / 8) * 1024;
+      const float* const rx_h = rx_s + h * HALF;
+      const float* const u_h = u_s + h * HALF;
       for (int t = 0; t < p.n_jt; ++t) {
-        const int b = t & 1;
-        ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
-        ptx::tc_fence_after();
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + b * 64 + h * 32, r);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(B_SEMPTY + b));
-
+        const int sb = t % NSBUF, gb = t & 1;
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
         const float vj = (jvalid && p.col_w != nullptr) ? p.col_w[jg] * ex2((p.scale - p.col_m_in[jg]) * LOG2E) : 0.f;
@@ -432,48 +438,84 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const float cj = ryj * p.k2;
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
         const bool plain = (i_valid == BLOCK_I) && !diag_tile && (long long)(t + 1) * BLOCK_J <= p.n_cols;  // warp-uniform
-        float g[32];
-        if (plain) {
+
+        ptx::mbar_wait(bar(B_SFULL + sb), (t / NSBUF) & 1);
+        ptx::tc_fence_after();
+        uint32_t r[NG][16];
 #pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const float y = __uint_as_float(r[x]) * rxk[x] * cj;      // S_ij * log2(e)
-            g[x] = ex2(y - p.k2) * (u_r[x] + vj);
-            ds = fmaf(g[x], y, ds);
+        for (int gq = 0; gq < NG; ++gq) ptx::tmem_ld_32x32b_x16(t_lane + S_COL0 + sb * BLOCK_I + h * HALF + gq * 16, r[gq]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(B_SEMPTY + sb));   // S buffer is in registers: the next logits tile may land
+
+        uint32_t gpk[NG][8];   // bf16 pairs are NOT adjacent in memory (K-major [i][j]); pack only to save registers
+#pragma unroll
+        for (int gq = 0; gq < NG; ++gq) {
+          float g[16];
+          if (plain) {
+#pragma unroll
+            for (int x4 = 0; x4 < 4; ++x4) {
+              const float4 rx4 = *reinterpret_cast<const float4*>(rx_h + gq * 16 + x4 * 4);
+              const float4 u4 = *reinterpret_cast<const float4*>(u_h + gq * 16 + x4 * 4);
+              const float rxv[4] = {rx4.x, rx4.y, rx4.z, rx4.w};
+              const float uv[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+              for (int xx = 0; xx < 4; ++xx) {
+                const int x = x4 * 4 + xx;
+                const float y = __uint_as_float(r[gq][x]) * rxv[xx] * cj;      // S_ij * log2(e)
+                g[x] = ex2(y - p.k2) * (uv[xx] + vj);
+                ds = fmaf(g[x], y, ds);
+              }
+            }
+          } else {
+            const long long id = jg - dcol0 - h * HALF - gq * 16;
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+              const float y = __uint_as_float(r[gq][x]) * rx_h[gq * 16 + x] * cj;
+              float gv = ex2(y - p.k2) * (u_h[gq * 16 + x] + vj);
+              if (id == x) gv -= p.diag_w;
+              if (!(jvalid && h * HALF + gq * 16 + x < i_valid)) gv = 0.f;
+              g[x] = gv;
+              ds = fmaf(gv, y, ds);
+            }
           }
-        } else {
-          const long long id = jg - dcol0 - h * 32;
 #pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const float y = __uint_as_float(r[x]) * rxk[x] * cj;
-            float gv = ex2(y - p.k2) * (u_r[x] + vj);
-            if (id == x) gv -= p.diag_w;
-            if (!(jvalid && h * 32 + x < i_valid)) gv = 0.f;
-            g[x] = gv;
-            ds = fmaf(gv, y, ds);
+          for (int x = 0; x < 8; ++x) {   // contracted against the RAW y_j -> fold rinv_y[j] into G
+            const __nv_bfloat162 pr = __floats2bfloat162_rn(g[2 * x] * ryj, g[2 * x + 1] * ryj);
+            gpk[gq][x] = *reinterpret_cast<const uint32_t*>(&pr);
           }
         }
-        ptx::mbar_wait(bar(B_GEMPTY + b), ((t >> 1) & 1) ^ 1u);   // gradient MMA of tile t-2 has read this buffer
-        uint8_t* const gb_base = g_gen + b * G_BYTES;
+        ptx::mbar_wait(bar(B_GEMPTY + gb), ((t >> 1) & 1) ^ 1u);   // gradient MMA of tile t-2 has read this buffer
+        uint8_t* const gb_base = g_gen + gb * G_BYTES;
 #pragma unroll
-        for (int x = 0; x < 32; ++x)   // contracted against the RAW y_j -> fold rinv_y[j] into G
-          *reinterpret_cast<__nv_bfloat16*>(gb_base + (x >> 3) * 1024 + row_off[x & 7]) = __float2bfloat16_rn(g[x] * ryj);
+        for (int gq = 0; gq < NG; ++gq)
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const int il = gq * 16 + x;   // row within this warp's half
+            const uint16_t v = static_cast<uint16_t>((x & 1) ? (gpk[gq][x >> 1] >> 16) : (gpk[gq][x >> 1] & 0xFFFFu));
+            *reinterpret_cast<uint16_t*>(gb_base + (il >> 3) * 1024 + row_off[il & 7]) = v;
+          }
         ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(B_GFULL + b));
+        if (lane == 0) ptx::mbar_arrive(bar(B_GFULL + gb));
       }
       // accumulators complete: dXhat^T[d = qc*128 + lane_global, i]  ->  dx[i][d]
       ptx::mbar_wait(bar(B_ACCFULL), 0);
       ptx::tc_fence_after();
       for (int qc = 0; qc < p.nq; ++qc) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_lane + qc * 64 + h * 32, r);
-        ptx::tmem_ld_wait();
         const int dd = qc * 128 + j_local;
-        if (dd < p.d) {
 #pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const int i = h * 32 + x;
-            if (i < i_valid) p.dx[(long long)(i0 + i) * p.d + dd] = __uint_as_float(r[x]) * p.out_scale;
+        for (int gq = 0; gq < NG; ++gq) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(t_lane + qc * BLOCK_I + h * HALF + gq * 16, r);
+          ptx::tmem_ld_wait();
+          if (dd < p.d) {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+              const int i = h * HALF + gq * 16 + x;
+              if (i < i_valid) p.dx[(long long)(i0 + i) * p.d + dd] = __uint_as_float(r[x]) * p.out_scale;
+            }
           }
         }
       }
