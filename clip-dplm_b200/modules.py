@@ -1,0 +1,350 @@
+"""Drop-in counterparts of the reference's CLIP modules and loss functions.
+
+Same class / function names, constructor arguments, forward signatures and output keys as the
+reference, so that training scripts written against it keep working; only the tail of each forward
+(normalise -> scaled similarity -> cross-entropy, and its backward) runs through the fused CUDA path.
+The encoders / projection heads above that tail are ordinary torch modules -- they are not part of
+the hot path and are kept structurally compatible (same parameter names, so reference state_dicts load).
+
+    reference                                         here
+    old/clip.py:38-73    RNAProteinCLIPModule          RNAProteinCLIPModule
+    old/clip.py:75-110   DiffMapProteinCLIPModule      DiffMapProteinCLIPModule
+    old/clip_opt.py:46   OptimizedCLIPModule           OptimizedCLIPModule   (+ optimized_clip_loss, :130-151)
+    rna_clip_codes.ipynb:1925-1954  RNARBPCLIPModel    RNARBPCLIPModel
+    tf_clip_codes (1).ipynb:13146-13165 (loss lines)   trimodal_contrastive_losses
+    tong/utils/losses.py:4-19  contrastive_loss        contrastive_loss
+    tong/utils/data.py:154-184 MemoryQueue             MemoryQueue
+
+Differences a caller can observe, all deliberate:
+  * output dicts gain "loss"; "logits_per_*" is a LazyLogits that only materialises the N x N matrix
+    when touched (``.materialize()``, ``.argmax``, ``torch.*`` functions) -- large batches never allocate N^2;
+  * with ``gather_distributed=True`` gradients flow through the gather (the reference's
+    ``dist.all_gather`` + ``torch.cat`` silently cuts them, old/clip_opt.py:102-112).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .engine import default_engine
+from .functional import fused_clip_loss
+
+LOGIT_SCALE_INIT = math.log(1.0 / 0.07)   # 2.6592 (run1/configuration_hybrid_clip.py:100)
+
+
+# ------------------------------------------------------------------------------------------------
+# differentiable L2 normalise through the C-ABI (returned "*_embeds" stay part of the autograd graph)
+# ------------------------------------------------------------------------------------------------
+class _Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        eng = default_engine()
+        xc = x.detach().contiguous()
+        rinv, xh = eng.normalize(xc, want_hat=xc.dtype)
+        ctx.save_for_backward(xc, rinv)
+        return xh
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, rinv = ctx.saved_tensors
+        return default_engine().normalize_backward(xc, rinv, g.float().contiguous(), xc.dtype)
+
+
+def fused_normalize(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(x, dim=-1) for a [N,d] CUDA tensor (bf16 / fp32)."""
+    return _Normalize.apply(x)
+
+
+class LazyLogits:
+    """Stands in for ``matmul(a, b.t()) * logit_scale`` (old/clip.py:67).  Nothing is computed until used."""
+
+    def __init__(self, a_hat, b_hat, scale):
+        self.a_hat, self.b_hat, self.scale = a_hat, b_hat, scale
+        self._m = None
+
+    @property
+    def shape(self):
+        return torch.Size((self.a_hat.shape[0], self.b_hat.shape[0]))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def materialize(self) -> torch.Tensor:
+        if self._m is None:
+            self._m = torch.matmul(self.a_hat.float(), self.b_hat.float().t()) * self.scale
+        return self._m
+
+    def argmax(self, dim=1):
+        return self.materialize().argmax(dim=dim)
+
+    def t(self):
+        return LazyLogits(self.b_hat, self.a_hat, self.scale)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        conv = lambda o: o.materialize() if isinstance(o, LazyLogits) else o
+        return func(*[conv(a) for a in args], **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+
+# ------------------------------------------------------------------------------------------------
+# encoders / heads above the hot path (plain torch; parameter names match the reference)
+# ------------------------------------------------------------------------------------------------
+class CLIPEncoder(nn.Module):
+    """``num_hidden_layers`` x (Linear + ReLU), then LayerNorm  (old/clip.py:8-17)."""
+
+    def __init__(self, config):
+        super().__init__()
+        h = config.hidden_size
+        self.layers = nn.ModuleList(nn.Linear(h, h) for _ in range(config.num_hidden_layers))
+        self.layernorm = nn.LayerNorm(h, eps=config.layer_norm_eps)
+
+    def forward(self, x):
+        for lin in self.layers:
+            x = torch.relu(lin(x))
+        return self.layernorm(x)
+
+
+def _mlp_head(dims, dropout):
+    mods = []
+    for k in range(len(dims) - 1):
+        mods += [nn.Linear(dims[k], dims[k + 1]), nn.LayerNorm(dims[k + 1])]
+        if k < len(dims) - 2:
+            mods += [nn.GELU(), nn.Dropout(dropout)]
+    return nn.Sequential(*mods)
+
+
+class ProjectionHead(nn.Module):
+    """Linear-LN-GELU-Dropout-Linear-LN  (old/clip.py:20-36)."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim=None, dropout=0.1):
+        super().__init__()
+        self.projection = _mlp_head([input_dim, hidden_dim or input_dim, output_dim], dropout)
+
+    def forward(self, x):
+        return self.projection(x)
+
+
+class OptimizedProjectionHead(nn.Module):
+    """skip(x) + layer_scale * three-layer MLP, Xavier init  (old/clip_opt.py:9-44, notebook :1901-1909)."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim=None, dropout=0.1):
+        super().__init__()
+        hidden = hidden_dim or 2 * input_dim
+        self.skip = nn.Linear(input_dim, output_dim)
+        self.layer_scale = nn.Parameter(torch.full((1,), 1e-4))
+        self.projection = _mlp_head([input_dim, hidden, hidden, output_dim], dropout)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        return self.skip(x) + self.layer_scale * self.projection(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP modules
+# ------------------------------------------------------------------------------------------------
+class _PairCLIP(nn.Module):
+    """Shared body of the two-tower modules: encoders -> heads -> fused contrastive tail."""
+
+    names = ("a", "b")      # output-key stems, set by subclasses
+    symmetric = True
+    clamp_max: Optional[float] = None
+
+    def _tail(self, emb_a, emb_b, extra_cols=None, group=None):
+        loss = fused_clip_loss(emb_a, emb_b, self.logit_scale, symmetric=self.symmetric, clamp_max=self.clamp_max,
+                               extra_cols=extra_cols, group=group)
+        a_hat, b_hat = fused_normalize(emb_a), fused_normalize(emb_b)
+        s = self.logit_scale.detach().exp()
+        if self.clamp_max is not None:
+            s = s.clamp(max=self.clamp_max)
+        na, nb = self.names
+        return {f"logits_per_{na}_{nb}": LazyLogits(a_hat.detach(), b_hat.detach(), s), f"{na}_embeds": a_hat,
+                f"{nb}_embeds": b_hat, "loss": loss}
+
+
+class RNAProteinCLIPModule(_PairCLIP):
+    names = ("rna", "protein")
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.rna_model = CLIPEncoder(config.rna_config)
+        self.protein_model = CLIPEncoder(config.protein_config)
+        p = config.projection_dim
+        self.rna_projection = ProjectionHead(config.rna_config.hidden_size, p, hidden_dim=2 * p)
+        self.protein_projection = ProjectionHead(config.protein_config.hidden_size, p, hidden_dim=2 * p)
+        self.logit_scale = nn.Parameter(torch.ones([]) * config.logit_scale_init_value)
+
+    def forward(self, rna_values, protein_values):
+        return self._tail(self.rna_projection(self.rna_model(rna_values)),
+                          self.protein_projection(self.protein_model(protein_values)))
+
+
+class DiffMapProteinCLIPModule(_PairCLIP):
+    names = ("diffmap", "protein")
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.diffmap_model = CLIPEncoder(config.diffmap_config)
+        self.protein_model = CLIPEncoder(config.protein_config)
+        p = config.projection_dim
+        self.diffmap_projection = ProjectionHead(config.diffmap_config.hidden_size, p, hidden_dim=2 * p)
+        self.protein_projection = ProjectionHead(config.protein_config.hidden_size, p, hidden_dim=2 * p)
+        self.logit_scale = nn.Parameter(torch.ones([]) * config.logit_scale_init_value)
+
+    def forward(self, diffmap_values, protein_values):
+        return self._tail(self.diffmap_projection(self.diffmap_model(diffmap_values)),
+                          self.protein_projection(self.protein_model(protein_values)))
+
+
+class OptimizedCLIPModule(_PairCLIP):
+    """old/clip_opt.py:46-128: wider skip heads, FIFO cache of normalised protein embeddings used as extra
+    negative columns (:52-56, :76-81, :118-121), ``exp().clamp(max=100)`` (:100), global negatives (:102-112)."""
+
+    names = ("diffmap", "protein")
+    clamp_max = 100.0
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        p = config.projection_dim
+        self.register_buffer("protein_embedding_cache", torch.zeros(config.cache_size, p), persistent=False)
+        self.cache_ptr = 0
+        self.diffmap_model = CLIPEncoder(config.diffmap_config)
+        self.protein_model = CLIPEncoder(config.protein_config)
+        self.diffmap_projection = OptimizedProjectionHead(config.diffmap_config.hidden_size, p, hidden_dim=4 * p)
+        self.protein_projection = OptimizedProjectionHead(config.protein_config.hidden_size, p, hidden_dim=4 * p)
+        self.logit_scale = nn.Parameter(torch.ones([]) * LOGIT_SCALE_INIT)
+
+    @torch.no_grad()
+    def update_cache(self, protein_embeds):
+        """FIFO write that restarts at 0 when the batch does not fit (old/clip_opt.py:76-81)."""
+        n = protein_embeds.size(0)
+        if self.cache_ptr + n > self.config.cache_size:
+            self.cache_ptr = 0
+        self.protein_embedding_cache[self.cache_ptr:self.cache_ptr + n] = protein_embeds.detach().to(
+            self.protein_embedding_cache.dtype)
+        self.cache_ptr = (self.cache_ptr + n) % self.config.cache_size
+
+    def forward(self, diffmap_values, protein_values, gather_distributed=True):
+        ea = self.diffmap_projection(self.diffmap_model(diffmap_values))
+        eb = self.protein_projection(self.protein_model(protein_values))
+        self.update_cache(fused_normalize(eb.detach()))       # the reference updates before the similarity (:97)
+        cache = self.protein_embedding_cache[:self.cache_ptr]
+        group = dist.group.WORLD if (gather_distributed and dist.is_available() and dist.is_initialized()) else None
+        out = self._tail(ea, eb, extra_cols=cache if cache.shape[0] else None, group=group)
+        a_hat = out["diffmap_embeds"]
+        s = self.logit_scale.detach().exp().clamp(max=100.0)
+        out["logits_per_diffmap_cache"] = LazyLogits(a_hat.detach(), cache, s)
+        return out
+
+
+def optimized_clip_loss(outputs, temperature=0.07):
+    """old/clip_opt.py:130-151 -- (CE([S | S_cache]) + CE(S^T)) / 2 (its label-smoothing tensors are dead code and
+    ``temperature`` is unused there too).  The fused modules already computed it."""
+    if "loss" in outputs:
+        return outputs["loss"]
+    raise RuntimeError("optimized_clip_loss expects the outputs of a clip_dplm_b200 module (they carry 'loss'); "
+                       "materialised logits are never re-read on the product path")
+
+
+# ------------------------------------------------------------------------------------------------
+# RNA <-> RBP model of current/rna_clip_codes.ipynb (cells 24 + 28)
+# ------------------------------------------------------------------------------------------------
+def create_padding_mask(emb):
+    """True where a position holds data; padding rows are NaN-filled (rna_clip_codes.ipynb:1841-1845)."""
+    return ~torch.isnan(emb).any(dim=-1)
+
+
+class RNARBPCLIPEncoder(nn.Module):
+    def __init__(self, embed_dim, num_layers=3):
+        super().__init__()
+        self.layers = nn.ModuleList(nn.TransformerEncoderLayer(d_model=embed_dim, nhead=8, dim_feedforward=4 * embed_dim,
+                                                               dropout=0.1) for _ in range(num_layers))
+        self.layernorm = nn.LayerNorm(embed_dim)
+
+    def forward(self, x, src_key_padding_mask=None):
+        for layer in self.layers:
+            x = layer(x, src_key_padding_mask=src_key_padding_mask)
+        return self.layernorm(x)
+
+
+class RNARBPCLIPProjectionHead(OptimizedProjectionHead):
+    def __init__(self, input_dim, output_dim):
+        nn.Module.__init__(self)
+        self.skip = nn.Linear(input_dim, output_dim)
+        self.layer_scale = nn.Parameter(torch.ones(1) * 1e-4)
+        self.projection = _mlp_head([input_dim, 2 * input_dim, 2 * input_dim, output_dim], 0.1)
+
+
+class RNARBPCLIPModel(nn.Module):
+    """forward(rna_emb, rbp_emb) -> (rna_embed, rbp_embed, loss)   (rna_clip_codes.ipynb:1935-1954)."""
+
+    def __init__(self, rna_dim=120, rbp_dim=1280, projection_dim=512):
+        super().__init__()
+        self.rna_encoder = RNARBPCLIPEncoder(rna_dim)
+        self.rbp_encoder = RNARBPCLIPEncoder(rbp_dim)
+        self.rna_projection = RNARBPCLIPProjectionHead(rna_dim, projection_dim)
+        self.rbp_projection = RNARBPCLIPProjectionHead(rbp_dim, projection_dim)
+        self.logit_scale = nn.Parameter(torch.ones([]) * LOGIT_SCALE_INIT)
+
+    def forward(self, rna_emb, rbp_emb):
+        rna_mask = create_padding_mask(rna_emb).transpose(0, 1)
+        rbp_mask = create_padding_mask(rbp_emb).transpose(0, 1)
+        rna_emb = torch.nan_to_num(rna_emb, 0.0)
+        rbp_emb = torch.nan_to_num(rbp_emb, 0.0)
+        rna_enc = self.rna_encoder(rna_emb, src_key_padding_mask=~rna_mask)
+        rbp_enc = self.rbp_encoder(rbp_emb, src_key_padding_mask=~rbp_mask)
+        pa, pb = self.rna_projection(rna_enc[:, 0]), self.rbp_projection(rbp_enc[:, 0])
+        loss = fused_clip_loss(pa, pb, self.logit_scale)          # replaces notebook lines 1948-1953
+        return fused_normalize(pa), fused_normalize(pb), loss
+
+
+# ------------------------------------------------------------------------------------------------
+# tri-modal losses and the tong queue variant
+# ------------------------------------------------------------------------------------------------
+def trimodal_contrastive_losses(cell_embed, pert_embed, protein_embed, logit_scale):
+    """Three pairwise symmetric InfoNCE losses sharing one logit_scale, summed
+    (tf_clip_codes (1).ipynb:13146-13165).  Inputs are the three projection outputs (un-normalised)."""
+    cp = fused_clip_loss(cell_embed, pert_embed, logit_scale)
+    cq = fused_clip_loss(cell_embed, protein_embed, logit_scale)
+    pq = fused_clip_loss(pert_embed, protein_embed, logit_scale)
+    return {"cell_embed": fused_normalize(cell_embed), "pert_embed": fused_normalize(pert_embed),
+            "protein_embed": fused_normalize(protein_embed), "loss": cp + cq + pq, "cell_pert_loss": cp,
+            "cell_protein_loss": cq, "pert_protein_loss": pq}
+
+
+def contrastive_loss(x, y, temperature=0.1, queue=None):
+    """tong/utils/losses.py:4-19 -- one-directional InfoNCE, logits divided by a fixed temperature, optional memory
+    queue appended to the columns as stored (no gradient)."""
+    return fused_clip_loss(x, y, 1.0 / temperature, symmetric=False, scale_is_log=False, extra_cols=queue,
+                           extra_normalized=False if queue is not None else True)
+
+
+class MemoryQueue:
+    """FIFO of detached embeddings with split write on wrap-around (tong/utils/data.py:154-184)."""
+
+    def __init__(self, size, dim, device=None, dtype=torch.float32):
+        self.size, self.dim, self.ptr = size, dim, 0
+        self.queue = torch.zeros(size, dim, device=device, dtype=dtype)
+
+    @torch.no_grad()
+    def enqueue_dequeue(self, embeddings):
+        e = embeddings.detach().to(self.queue.dtype)
+        n = e.shape[0]
+        if self.ptr + n > self.size:
+            first = self.size - self.ptr
+            self.queue[self.ptr:] = e[:first]
+            self.queue[:n - first] = e[first:]
+            self.ptr = n - first
+        else:
+            self.queue[self.ptr:self.ptr + n] = e
+            self.ptr = (self.ptr + n) % self.size
+        return self.queue

@@ -181,3 +181,26 @@ def test_row_sharded_global_batch_gloo(symmetric):
         assert rel(da, ref["d_a"][rank * nl:(rank + 1) * nl]) < 1e-9
         assert rel(db, ref["d_b"][rank * nl:(rank + 1) * nl]) < 1e-9
         assert abs(dt - float(ref["d_logit_scale"])) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ drop-in surface
+@pytest.mark.skipif(not os.path.exists("/root/reference/old/clip.py"), reason="reference checkout only exists in the build container")
+def test_module_parameter_names_match_reference():
+    """state_dicts of the reference modules must load into the drop-in modules (same names and shapes)."""
+    import importlib.util
+    import sys
+    import types
+    stub = types.ModuleType("configuration_hybrid_clip")
+    stub.HybridCLIPConfig = object
+    sys.modules.setdefault("configuration_hybrid_clip", stub)
+    spec = importlib.util.spec_from_file_location("ref_old_clip_t", "/root/reference/old/clip.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from clip_dplm_b200 import modules as M
+    sub = lambda h: types.SimpleNamespace(hidden_size=h, num_hidden_layers=2, layer_norm_eps=1e-5)
+    cfg = types.SimpleNamespace(rna_config=sub(24), protein_config=sub(32), diffmap_config=sub(24), projection_dim=16,
+                                logit_scale_init_value=2.6592, cache_size=8)
+    for name in ("RNAProteinCLIPModule", "DiffMapProteinCLIPModule"):
+        a = {k: tuple(v.shape) for k, v in getattr(ref, name)(cfg).state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in getattr(M, name)(cfg).state_dict().items()}
+        assert a == b, name
