@@ -83,7 +83,12 @@ def test_notebook_model_and_tong_loss():
     ra, rb, loss = model(rna, rbp)
     assert ra.shape == (12, 32) and rb.shape == (12, 32)
     assert abs(float(ra.norm(dim=1).mean()) - 1) < 1e-4
-    assert abs(float(loss) - math.log(12)) < 1.0          # untrained model: loss ~ ln(batch) (notebook: 3.50 vs ln 32)
+    with torch.no_grad():
+        re_ = model.rna_encoder(rna, src_key_padding_mask=~M.create_padding_mask(rna).transpose(0, 1))
+        be_ = model.rbp_encoder(rbp, src_key_padding_mask=~M.create_padding_mask(rbp).transpose(0, 1))
+        pa, pb = model.rna_projection(re_[:, 0]), model.rbp_projection(be_[:, 0])
+    ref_l = O.ref_loss(pa.cpu().double(), pb.cpu().double(), model.logit_scale.detach().cpu().double())
+    assert abs(float(loss) - float(ref_l)) <= 1e-5 * abs(float(ref_l))
     x, y, q = torch.randn(33, 40, device="cuda"), torch.randn(33, 40, device="cuda"), torch.randn(17, 40, device="cuda")
     l = M.contrastive_loss(x, y, temperature=0.1, queue=q)
     ref = O.ref_loss(x.cpu().double(), y.cpu().double(), torch.tensor(10.0, dtype=torch.float64), symmetric=False,
