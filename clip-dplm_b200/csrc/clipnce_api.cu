@@ -97,33 +97,22 @@ int check_device_sm100() {
   return 0;
 }
 
-// CTAs per cluster that share the streamed tiles via TMA multicast.  CLIPNCE_CLUSTER overrides (1/2/4/8).
-int cluster_size(int64_t n_blocks) {
-  const char* e = getenv("CLIPNCE_CLUSTER");
-  const int v = e ? atoi(e) : 0;
-  int c = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 1;   // measured: the kernels are not L2-bound, multicast does not pay
-  while (c > 1 && n_blocks < 2 * c) c >>= 1;   // tiny problems: do not pad the grid with idle CTAs
-  return c;
-}
-
 template <int MODE, int BLOCK_I>
 int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tyt, tc::Params p,
               int grid, cudaStream_t st) {
   auto kern = tc::clip_tc_kernel<MODE, BLOCK_I>;
   const int fixed = tc::smem_bytes(MODE, BLOCK_I, p.nkc, 0);
-  const int total_boxes = (tc::SMEM_LIMIT - fixed) / tc::BOX_BYTES;   // 16 KiB TMA boxes the ring(s) can hold
+  const int total_boxes = (tc::SMEM_LIMIT - fixed) / tc::BOX_BYTES;   // 16 KiB ring stages that fit
   if (total_boxes < (MODE == 1 ? 2 : 1)) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for a TMA ring", p.d);
-  p.boxes = total_boxes >= 8 ? 2 : 1;          // K = 128 per stage when the rings stay >= 4 stages deep in total
-  int stages = total_boxes / p.boxes;
   auto cap = [](int v) { return v > tc::MAX_STAGES ? tc::MAX_STAGES : v; };
   if (MODE == 1) {
-    p.stages_b = cap(stages / 2);
-    p.stages_a = cap(stages - stages / 2);
+    p.stages_b = cap(total_boxes / 2);
+    p.stages_a = cap(total_boxes - total_boxes / 2);
   } else {
-    p.stages_a = cap(stages);
+    p.stages_a = cap(total_boxes);
     p.stages_b = 0;
   }
-  const int smem = tc::smem_bytes(MODE, BLOCK_I, p.nkc, (p.stages_a + p.stages_b) * p.boxes);
+  const int smem = tc::smem_bytes(MODE, BLOCK_I, p.nkc, p.stages_a + p.stages_b);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_attr_done[attr_slot]) {
@@ -131,20 +120,8 @@ int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const
       g_attr_done[attr_slot] = true;
     }
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3((unsigned)(ceil_div(grid, p.cluster) * p.cluster));   // padded: extra CTAs only feed the multicast
-  cfg.blockDim = dim3(tc::NUM_THREADS);
-  cfg.dynamicSmemBytes = (size_t)smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)p.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tx, ty, tyt, p));
+  kern<<<grid, tc::num_threads(MODE, BLOCK_I), smem, st>>>(tx, ty, tyt, p);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -268,15 +245,13 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
     const int bi = fwd_block_i(n_rows, d);
     const int64_t n_ib = ceil_div(n_rows, bi);
     const int64_t col_ld = round_up(n_cols, 32);
-    const size_t need = sizeof(float) * 2 * (size_t)n_ib * (size_t)col_ld;
+    const size_t need = sizeof(float) * (size_t)(bi / 32) * (size_t)n_ib * (size_t)col_ld;
     if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
-    const int cl = cluster_size(n_ib);
     CUtensorMap tx, ty;
     if ((rc = make_tmap(&tx, x, d, n_rows, d, bi))) return rc;
-    if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J / cl))) return rc;
+    if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J))) return rc;
     tc::Params p;
     memset(&p, 0, sizeof p);
-    p.cluster = cl;
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
@@ -285,7 +260,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
     if (bi == 128) rc = launch_tc<0, 128>(0, tx, ty, ty, p, (int)n_ib, st);
     else           rc = launch_tc<0, 64>(1, tx, ty, ty, p, (int)n_ib, st);
     if (rc) return rc;
-    aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, (int)(2 * n_ib), col_ld,
+    aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, (int)((bi / 32) * n_ib), col_ld,
                                                                                 n_cols, scale, col_m, col_l);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -340,14 +315,12 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     const int64_t n_ib = ceil_div(n_rows, bi);
     const size_t need = sizeof(float) * (size_t)n_ib;
     if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
-    const int cl = cluster_size(n_ib);
     CUtensorMap tx, ty, tyt;
     if ((rc = make_tmap(&tx, x, d, n_rows, d, bi))) return rc;
-    if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J / cl))) return rc;
-    if ((rc = make_tmap(&tyt, y_t, n_cols, d, ld_t, 128 / cl))) return rc;
+    if ((rc = make_tmap(&ty, y, d, n_cols, d, tc::BLOCK_J))) return rc;
+    if ((rc = make_tmap(&tyt, y_t, n_cols, d, ld_t, 128))) return rc;
     tc::Params p;
     memset(&p, 0, sizeof p);
-    p.cluster = cl;
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;

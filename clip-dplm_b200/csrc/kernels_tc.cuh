@@ -44,9 +44,11 @@ constexpr int BLOCK_J = 128;                         // streamed rows per tile =
 constexpr int BLOCK_K = 64;                          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int BOX_BYTES = BLOCK_J * BLOCK_K * 2;     // one TMA box [128 rows][64 elems] = 16 KiB
-constexpr int MAX_STAGES = 5;                        // per ring
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 32 * (4 + NUM_EPI_WARPS);
+constexpr int MAX_STAGES = 5;                        // per ring (one 16 KiB box per stage)
+// epilogue warps: MODE 0 gives every warp 32 TMEM columns (BLOCK_I / 32 warps per lane quarter: ex2-bound, it wants
+// many warps and few registers each); MODE 1 splits the tile's columns between two warps per lane quarter
+__host__ __device__ constexpr int num_epi_warps(int mode, int block_i) { return mode == 0 ? 4 * (block_i / 32) : 8; }
+__host__ __device__ constexpr int num_threads(int mode, int block_i) { return 32 * (4 + num_epi_warps(mode, block_i)); }
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 232448;                   // 227 KiB opt-in maximum per CTA
 constexpr float LOG2E = 1.4426950408889634f;
@@ -60,10 +62,8 @@ struct Params {
   int nkc;         // ceil(d / 64)   K boxes per logits tile
   int nq;          // ceil(d / 128)  accumulator chunks of the gradient MMA
   int n_jt;        // ceil(n_cols / 128)
-  int boxes;       // TMA boxes per ring stage (1 or 2): K = 64 or 128 per barrier round trip
-  int stages_a;    // ring A: streamed Y boxes for the logits MMA
+  int stages_a;    // ring A (16 KiB stages): streamed Y boxes for the logits MMA
   int stages_b;    // ring B: streamed Y^T boxes for the gradient MMA (MODE 1)
-  int cluster;     // CTAs per cluster sharing the streamed tiles through TMA multicast (1, 2, 4 or 8)
   long long diag_offset;
   float scale;     // s
   float k2;        // s * log2(e)
@@ -95,7 +95,29 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
+// exp2 on the FMA/ALU pipes.  MUFU.EX2 issues one warp instruction per 32 clk per SM sub-partition on B200 (ncu: the XU
+// pipe sat at 113 % of its sustained peak with the forward at 4 exp/clk/SM), which made the exponential -- not the tensor
+// pipe -- the limiter of the forward.  Range reduction by the 1.5*2^23 rounding trick, degree-5 minimax polynomial for
+// 2^f on [-0.5, 0.5] (max relative error 2.4e-7, the same class as MUFU.EX2), exponent spliced in with an integer add.
+// Valid for x in [-125, 1]; the tensor-core path guarantees x >= -2 s log2(e) >= -124.1.
+__device__ __forceinline__ float ex2_poly(float x) {
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float q = 0.001327646430581808f;
+  q = fmaf(q, f, 0.009675540961325169f);
+  q = fmaf(q, f, 0.05550713464617729f);
+  q = fmaf(q, f, 0.24022120237350464f);
+  q = fmaf(q, f, 0.6931469440460205f);
+  q = fmaf(q, f, 1.0000001192092896f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+// One logit in MUFU_EVERY goes to the MUFU, the others to the polynomial: both pipes stay busy.
+constexpr int MUFU_EVERY = 4;
+template <int X>
+__device__ __forceinline__ float ex2_mix(float x) { return (X % MUFU_EVERY == 0) ? ex2(x) : ex2_poly(x); }
+
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 // Transposing butterfly: every lane holds N partial sums v[0..N); afterwards lane L holds, in
 // v[0..N/32), the totals over the warp of entries (N/32)*L + {0..N/32-1}.
@@ -116,7 +138,7 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[N], int lane) {
 }
 
 template <int MODE, int BLOCK_I>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(MODE, BLOCK_I), 1)
 clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
                const __grid_constant__ CUtensorMap tmap_yt, const Params p) {
   static_assert(BLOCK_I == 64 || BLOCK_I == 96 || BLOCK_I == 128, "BLOCK_I");
@@ -127,16 +149,16 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   constexpr int NSBUF = num_s_buffers(MODE, BLOCK_I);
   constexpr int S_COL0 = (MODE == 0) ? 0 : TMEM_COLS - NSBUF * BLOCK_I;
   constexpr int G_BYTES = g_bytes(BLOCK_I);
+  constexpr int NUM_EPI_WARPS = num_epi_warps(MODE, BLOCK_I);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ptx::smem_u32(smem);
   if ((base & 1023u) != 0) __trap();   // SWIZZLE_128B operands need 1 KiB alignment (dynamic smem starts at 1 KiB)
 
-  const int stage_bytes = p.boxes * BOX_BYTES;
   const uint32_t x_smem = base;
   const uint32_t ring_a = x_smem + p.nkc * X_CHUNK;
-  const uint32_t ring_b = ring_a + p.stages_a * stage_bytes;
-  const uint32_t g_smem = ring_b + (MODE == 1 ? p.stages_b : 0) * stage_bytes;
+  const uint32_t ring_b = ring_a + p.stages_a * BOX_BYTES;
+  const uint32_t g_smem = ring_b + (MODE == 1 ? p.stages_b : 0) * BOX_BYTES;
   const uint32_t small_off = (g_smem - base) + (MODE == 1 ? 2 * G_BYTES : 0);
   const uint32_t bars = base + small_off;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
@@ -152,11 +174,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   const int warp = threadIdx.x >> 5;   // warp-uniform
   const int lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * BLOCK_I;   // may lie beyond n_rows for the CTAs that pad the last cluster
-  const int csize = p.cluster;
-  const uint32_t crank = (csize > 1) ? ptx::cluster_ctarank() : 0u;
-  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
-  const int slice_rows = BLOCK_J / csize;            // rows of every streamed box this CTA fetches (for all)
+  const int i0 = blockIdx.x * BLOCK_I;
   const int nga = p.nkc;                             // ring-A boxes per tile (K chunks of the logits MMA)
   const int ngb = 2 * p.nq;                          // ring-B boxes per tile ((d chunk, j half) of the gradient MMA)
 
@@ -168,9 +186,9 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(bar(B_FULL_A + s), 1);
-      ptx::mbar_init(bar(B_EMPTY_A + s), csize);   // every CTA of the cluster releases every stage everywhere
+      ptx::mbar_init(bar(B_EMPTY_A + s), 1);
       ptx::mbar_init(bar(B_FULL_B + s), 1);
-      ptx::mbar_init(bar(B_EMPTY_B + s), csize);
+      ptx::mbar_init(bar(B_EMPTY_B + s), 1);
     }
     ptx::mbar_init(bar(B_XFULL), 1);
     for (int b = 0; b < 2; ++b) {
@@ -187,142 +205,121 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  if (csize > 1) ptx::cluster_sync(); else __syncthreads();   // peers' barriers must exist before any remote arrive
+  __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // Issue-side design.  (1) Every issuing warp runs warp-uniform loops; all lanes wait on the barriers
-  // and one elected lane issues (inside an `if (lane == 0)` region ptxas wraps each UTCHMMA/UTMALDG in a
-  // waterfall loop).  (2) A ring stage can carry two boxes (K = 128) so one barrier round trip feeds 8
-  // MMAs.  (3) Logits MMAs and gradient MMAs are issued by two different warps from two different rings.
+  // Issue-side design (each step measured, see DESIGN.md section 5.1 and tools/umma_bench.cu).
+  //  * One ELECTED lane runs each issuing role's whole loop, waits included.  Issuing from inside an
+  //    `if (lane == 0)` region makes ptxas wrap every UTCHMMA/UTMALDG in a waterfall loop; electing per
+  //    iteration costs a reconvergence (~100 clk) per four MMAs.
+  //  * mbarrier.try_wait takes ~170 clk even on a completed phase -- longer than issuing the four MMAs of a box --
+  //    so the wait for stage s+1 is started before stage s is issued (ptx::mma_box_prefetch / tma_box_prefetch).
+  //  * Logits MMAs and gradient MMAs are issued by two different warps from two different rings.
   const uint32_t desc_hi = static_cast<uint32_t>(ptx::smem_desc_k_sw128(0) >> 32);   // SBO, version, swizzle mode
   auto desc = [&](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
   auto desc_lo = [&](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
-  // one multicast-aware box load into `dst` (this CTA fetches its row slice for every CTA of the cluster)
-  auto load_box = [&](uint32_t dst, const CUtensorMap* m, uint32_t full_bar, int c0, int c1) {
-    if (csize == 1) ptx::tma_load_2d(dst, m, full_bar, c0, c1);
-    else ptx::tma_load_2d_mc(dst + crank * slice_rows * 128, m, full_bar, c0, c1 + crank * slice_rows, cmask);
-  };
-  auto commit_empty = [&](uint32_t b) {
-    if (csize == 1) ptx::mma_commit(b); else ptx::mma_commit_mc(b, cmask);
-  };
 
   if (warp == 0) {
-    // ======================================================================= producer A: X panel, then Y tiles
+    // ======================================================================= producer A: X panel, then Y boxes
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar(B_XFULL), p.nkc * X_CHUNK);
       for (int kc = 0; kc < p.nkc; ++kc)
         ptx::tma_load_2d(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * BLOCK_K, i0);
+      int stage = 0;
+      uint32_t phase = 0, ready = 1;   // every stage starts free
+      for (int t = 0; t < p.n_jt; ++t) {
+        for (int g = 0; g < nga; ++g) {
+          if (!ready) ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == p.stages_a) { ns = 0; np ^= 1u; }
+          ready = ptx::tma_box_prefetch(ring_a + stage * BOX_BYTES, &tmap_y, bar(B_FULL_A + stage), BOX_BYTES,
+                                        g * BLOCK_K, t * BLOCK_J, bar(B_EMPTY_A + ns), np ^ 1u);
+          stage = ns;
+          phase = np;
+        }
+      }
     }
     __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = 0; t < p.n_jt; ++t) {
-      for (int g0 = 0; g0 < nga; g0 += p.boxes) {
-        ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);   // free in EVERY CTA of the cluster
-        if (ptx::elect_one()) {
-          const int nsub = min(p.boxes, nga - g0);
-          ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), nsub * BOX_BYTES);
-          for (int sub = 0; sub < nsub; ++sub)
-            load_box(ring_a + stage * stage_bytes + sub * BOX_BYTES, &tmap_y, bar(B_FULL_A + stage),
-                     (g0 + sub) * BLOCK_K, t * BLOCK_J);
-        }
-        __syncwarp();
-        if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
-      }
-    }
   } else if (warp == 2 && MODE == 1) {
     // ======================================================================= producer B: Y^T boxes [128 d][64 j]
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = 0; t < p.n_jt; ++t) {
-      for (int g0 = 0; g0 < ngb; g0 += p.boxes) {
-        ptx::mbar_wait(bar(B_EMPTY_B + stage), phase ^ 1u);
-        if (ptx::elect_one()) {
-          const int nsub = min(p.boxes, ngb - g0);
-          ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), nsub * BOX_BYTES);
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int g = g0 + sub;   // (d chunk g >> 1, j half g & 1)
-            load_box(ring_b + stage * stage_bytes + sub * BOX_BYTES, &tmap_yt, bar(B_FULL_B + stage),
-                     t * BLOCK_J + (g & 1) * BLOCK_K, (g >> 1) * 128);
-          }
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, ready = 1;
+      for (int t = 0; t < p.n_jt; ++t) {
+        for (int g = 0; g < ngb; ++g) {   // (d chunk g >> 1, j half g & 1)
+          if (!ready) ptx::mbar_wait(bar(B_EMPTY_B + stage), phase ^ 1u);
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == p.stages_b) { ns = 0; np ^= 1u; }
+          ready = ptx::tma_box_prefetch(ring_b + stage * BOX_BYTES, &tmap_yt, bar(B_FULL_B + stage), BOX_BYTES,
+                                        t * BLOCK_J + (g & 1) * BLOCK_K, (g >> 1) * 128, bar(B_EMPTY_B + ns), np ^ 1u);
+          stage = ns;
+          phase = np;
         }
-        __syncwarp();
-        if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ======================================================================= logits MMA issuer
-    constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
-    const uint32_t a_lo0 = desc_lo(ring_a), x_lo0 = desc_lo(x_smem);
-    int stage = 0;
-    uint32_t phase = 0;
-    ptx::mbar_wait(bar(B_XFULL), 0);
-    for (int t = 0; t < p.n_jt; ++t) {
-      const int sb = t % NSBUF;
-      ptx::mbar_wait(bar(B_SEMPTY + sb), ((t / NSBUF) & 1) ^ 1u);   // epilogue drained this S buffer
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + S_COL0 + sb * BLOCK_I;
-      for (int g0 = 0; g0 < nga; g0 += p.boxes) {
-        ptx::mbar_wait(bar(B_FULL_A + stage), phase);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t a_lo = a_lo0 + stage * (stage_bytes >> 4);
-          const uint32_t b_lo = x_lo0 + g0 * (X_CHUNK >> 4);
-          const int nsub = min(p.boxes, nga - g0);
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            if (sub < nsub) {
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
-                ptx::mma_f16(d_tmem, desc(a_lo + sub * (BOX_BYTES >> 4) + 2 * k),
-                             desc(b_lo + sub * (X_CHUNK >> 4) + 2 * k), idesc_s, (g0 | sub | k) != 0);
-            }
-          }
-          commit_empty(bar(B_EMPTY_A + stage));
-          if (g0 + p.boxes >= nga) ptx::mma_commit(bar(B_SFULL + sb));
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
+      const uint32_t a_lo0 = desc_lo(ring_a), x_lo0 = desc_lo(x_smem);
+      int stage = 0;
+      uint32_t phase = 0, ready = 0;
+      ptx::mbar_wait(bar(B_XFULL), 0);
+      for (int t = 0; t < p.n_jt; ++t) {
+        const int sb = t % NSBUF;
+        ptx::mbar_wait(bar(B_SEMPTY + sb), ((t / NSBUF) & 1) ^ 1u);   // epilogue drained this S buffer
+        const uint32_t d_tmem = tmem_base + S_COL0 + sb * BLOCK_I;
+        for (int g = 0; g < nga; ++g) {
+          if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
+          ptx::tc_fence_after();
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == p.stages_a) { ns = 0; np ^= 1u; }
+          ready = ptx::mma_box_prefetch(d_tmem, desc(a_lo0 + stage * (BOX_BYTES >> 4)), desc(x_lo0 + g * (X_CHUNK >> 4)),
+                                        idesc_s, g != 0, bar(B_FULL_A + ns), np);
+          ptx::mma_commit(bar(B_EMPTY_A + stage));
+          if (g == nga - 1) ptx::mma_commit(bar(B_SFULL + sb));
+          stage = ns;
+          phase = np;
         }
-        __syncwarp();
-        if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
       }
     }
+    __syncwarp();
   } else if (warp == 3 && MODE == 1) {
     // ======================================================================= gradient MMA issuer
-    constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
-    const uint32_t a_lo0 = desc_lo(ring_b), g_lo0 = desc_lo(g_smem);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = 0; t < p.n_jt; ++t) {
-      const int gb = t & 1;
-      ptx::mbar_wait(bar(B_GFULL + gb), (t >> 1) & 1);            // epilogue wrote the bf16 gradient tile t
-      ptx::tc_fence_after();
-      for (int g0 = 0; g0 < ngb; g0 += p.boxes) {
-        ptx::mbar_wait(bar(B_FULL_B + stage), phase);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t a_lo = a_lo0 + stage * (stage_bytes >> 4);     // Y^T boxes [128 d][64 j]
-          const uint32_t b_lo = g_lo0 + gb * (G_BYTES >> 4);            // G chunks  [BLOCK_I i][64 j] x 2
-          const int nsub = min(p.boxes, ngb - g0);
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            if (sub < nsub) {
-              const int g = g0 + sub, q = g >> 1, kk = g & 1;
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                ptx::mma_f16(tmem_base + q * BLOCK_I, desc(a_lo + sub * (BOX_BYTES >> 4) + 2 * k),
-                             desc(b_lo + kk * (G_BYTES >> 5) + 2 * k), idesc_g, (t | kk | k) != 0);
-            }
-          }
-          commit_empty(bar(B_EMPTY_B + stage));
-          if (g0 + p.boxes >= ngb) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_g = ptx::idesc_bf16_f32(BLOCK_J, BLOCK_I);
+      const uint32_t a_lo0 = desc_lo(ring_b), g_lo0 = desc_lo(g_smem);
+      int stage = 0;
+      uint32_t phase = 0, ready = 0;
+      for (int t = 0; t < p.n_jt; ++t) {
+        const int gb = t & 1;
+        ptx::mbar_wait(bar(B_GFULL + gb), (t >> 1) & 1);            // epilogue wrote the bf16 gradient tile t
+        const uint32_t b_lo = g_lo0 + gb * (G_BYTES >> 4);            // G chunks [BLOCK_I i][64 j] x 2
+        for (int g = 0; g < ngb; ++g) {
+          if (!ready) ptx::mbar_wait(bar(B_FULL_B + stage), phase);
+          ptx::tc_fence_after();
+          int ns = stage + 1;
+          uint32_t np = phase;
+          if (ns == p.stages_b) { ns = 0; np ^= 1u; }
+          const int q = g >> 1, kk = g & 1;
+          ready = ptx::mma_box_prefetch(tmem_base + q * BLOCK_I, desc(a_lo0 + stage * (BOX_BYTES >> 4)),
+                                        desc(b_lo + kk * (G_BYTES >> 5)), idesc_g, (t | kk) != 0, bar(B_FULL_B + ns), np);
+          ptx::mma_commit(bar(B_EMPTY_B + stage));
+          if (g == ngb - 1) {
             ptx::mma_commit(bar(B_GEMPTY + gb));
             if (t == p.n_jt - 1) ptx::mma_commit(bar(B_ACCFULL));
           }
+          stage = ns;
+          phase = np;
         }
-        __syncwarp();
-        if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ======================================================================= epilogue
     const int e = warp - 4;        // 0..7
@@ -340,77 +337,74 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       // (row_m_i == s when the statistics come from the MODE 0 kernel, so u_i = row_w_i exactly)
       if (MODE == 1) u_s[te] = (te < i_valid) ? p.row_w[i0 + te] * ex2((p.scale - p.row_m_in[i0 + te]) * LOG2E) : 0.f;
     }
-    epi_bar_sync();
+    epi_bar_sync<NUM_EPI_WARPS * 32>();
 
     if (MODE == 0) {
-      constexpr int NCH = HALF / 32;                // 32-column TMEM loads per tile per warp
-      float racc[HALF];
+      // warp (quarter q, column group cg): lanes j = q*32.., TMEM columns i = cg*32.. -- 32 logits per thread per tile
+      const int cg = e >> 2;
+      const int ibase = cg * 32;
+      float racc[32];
 #pragma unroll
-      for (int i = 0; i < HALF; ++i) racc[i] = 0.f;
+      for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+      float ry_n = (j_local < p.n_cols) ? p.rinv_y[j_local] : 0.f;   // fetched one tile ahead
       for (int t = 0; t < p.n_jt; ++t) {
         const int b = t & 1;
-        ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
-        ptx::tc_fence_after();
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
-        const float ryj = jvalid ? p.rinv_y[jg] : 0.f;
+        const float ryj = ry_n;
+        ry_n = (t + 1 < p.n_jt && jg + BLOCK_J < p.n_cols) ? p.rinv_y[jg + BLOCK_J] : 0.f;
         const float cj = ryj * p.k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
-        float csum = 0.f;
+        ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + b * BLOCK_I + ibase, r);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();   // S buffer drained by this warp -> let the MMA warp overwrite it
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(B_SEMPTY + b));
+        if (jvalid) {
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};   // four partial column sums: no 32-long dependent FADD chain
+          if (i_valid == BLOCK_I) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + b * BLOCK_I + h * HALF + c * 32, r);
-          ptx::tmem_ld_wait();
-          if (c == NCH - 1) {   // S buffer drained by this warp -> let the MMA warp overwrite it
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar(B_SEMPTY + b));
-          }
-          if (jvalid) {
-            const int ibase = h * HALF + c * 32;
-            if (i_valid == BLOCK_I) {
+            for (int x4 = 0; x4 < 8; ++x4) {
+              const float4 rx4 = *reinterpret_cast<const float4*>(rx_s + ibase + x4 * 4);
+              const float rxv[4] = {rx4.x, rx4.y, rx4.z, rx4.w};
 #pragma unroll
-              for (int x4 = 0; x4 < 8; ++x4) {
-                const float4 rx4 = *reinterpret_cast<const float4*>(rx_s + ibase + x4 * 4);
-                const float rxv[4] = {rx4.x, rx4.y, rx4.z, rx4.w};
-#pragma unroll
-                for (int xx = 0; xx < 4; ++xx) {
-                  const int x = x4 * 4 + xx;
-                  const float ev = ex2(fmaf(__uint_as_float(r[x]) * rxv[xx], cj, -p.k2));
-                  racc[c * 32 + x] += ev;
-                  csum += ev;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int x = 0; x < 32; ++x) {
-                const float ev =
-                    (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]) * rx_s[ibase + x], cj, -p.k2)) : 0.f;
-                racc[c * 32 + x] += ev;
-                csum += ev;
+              for (int xx = 0; xx < 4; ++xx) {
+                const int x = x4 * 4 + xx;
+                const float xv = fmaf(__uint_as_float(r[x]) * rxv[xx], cj, -p.k2);
+                const float ev = (xx == 0) ? ex2(xv) : ex2_poly(xv);     // 1 in 4 on the MUFU
+                racc[x] += ev;
+                cs[xx] += ev;
               }
             }
-            if (diag_tile) {
-              const long long id = jg - dcol0 - ibase;   // TMEM column (within this load) holding S_{i,i+off}
+          } else {
 #pragma unroll
-              for (int x = 0; x < 32; ++x)
-                if (id == x && ibase + x < i_valid)
-                  p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * rx_s[ibase + x] * ryj * p.scale;
+            for (int x = 0; x < 32; ++x) {
+              const float ev = (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]) * rx_s[ibase + x], cj, -p.k2)) : 0.f;
+              racc[x] += ev;
+              cs[x & 3] += ev;
             }
           }
+          if (diag_tile) {
+            const long long id = jg - dcol0 - ibase;   // TMEM column (within this load) holding S_{i,i+off}
+#pragma unroll
+            for (int x = 0; x < 32; ++x)
+              if (id == x && ibase + x < i_valid)
+                p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * rx_s[ibase + x] * ryj * p.scale;
+          }
+          p.col_part[(long long)(blockIdx.x * (BLOCK_I / 32) + cg) * p.col_ld + jg] = (cs[0] + cs[1]) + (cs[2] + cs[3]);
         }
-        if (jvalid) p.col_part[(long long)(blockIdx.x * 2 + h) * p.col_ld + jg] = csum;
       }
-      // row sums: reduce the per-lane partials over the 128 lanes (4 warps) that share half h
-      warp_transpose_reduce<HALF>(racc, lane);
-#pragma unroll
-      for (int x = 0; x < HALF / 32; ++x) red[e * 64 + (HALF / 32) * lane + x] = racc[x];
-      epi_bar_sync();
+      // row sums: reduce the per-lane partials over the 128 lanes (4 warps) that share column group cg
+      warp_transpose_reduce<32>(racc, lane);
+      red[e * 32 + lane] = racc[0];
+      epi_bar_sync<NUM_EPI_WARPS * 32>();
       if (te < BLOCK_I) {
-        const int hh = te / HALF, ii = te % HALF;
-        const float tot = red[(hh * 4 + 0) * 64 + ii] + red[(hh * 4 + 1) * 64 + ii] + red[(hh * 4 + 2) * 64 + ii] +
-                          red[(hh * 4 + 3) * 64 + ii];
+        const int cgi = te >> 5, ii = te & 31;
+        const float tot = (red[(cgi * 4 + 0) * 32 + ii] + red[(cgi * 4 + 1) * 32 + ii]) +
+                          (red[(cgi * 4 + 2) * 32 + ii] + red[(cgi * 4 + 3) * 32 + ii]);
         if (te < i_valid) {
           p.row_m[i0 + te] = p.scale;
           p.row_l[i0 + te] = tot;
@@ -429,13 +423,24 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       uint8_t* const g_gen = smem + (g_smem - base) + (j_local >> 6) * (G_BYTES / 2) + (h * HALF / 8) * 1024;
       const float* const rx_h = rx_s + h * HALF;
       const float* const u_h = u_s + h * HALF;
+      // per-column scalars are fetched one tile ahead so their L2 latency never sits on the S -> G critical path
+      auto load_col = [&](int t, float& cw, float& cm, float& ry) {
+        const long long jn = (long long)t * BLOCK_J + j_local;
+        const bool ok = t < p.n_jt && jn < p.n_cols;
+        cw = (ok && p.col_w != nullptr) ? p.col_w[jn] : 0.f;
+        cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : p.scale;
+        ry = ok ? p.rinv_y[jn] : 0.f;
+      };
+      float cw_n, cm_n, ry_n;
+      load_col(0, cw_n, cm_n, ry_n);
       for (int t = 0; t < p.n_jt; ++t) {
         const int sb = t % NSBUF, gb = t & 1;
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
-        const float vj = (jvalid && p.col_w != nullptr) ? p.col_w[jg] * ex2((p.scale - p.col_m_in[jg]) * LOG2E) : 0.f;
-        const float ryj = jvalid ? p.rinv_y[jg] : 0.f;
+        const float vj = cw_n * ex2((p.scale - cm_n) * LOG2E);
+        const float ryj = ry_n;
         const float cj = ryj * p.k2;
+        load_col(t + 1, cw_n, cm_n, ry_n);
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
         const bool plain = (i_valid == BLOCK_I) && !diag_tile && (long long)(t + 1) * BLOCK_J <= p.n_cols;  // warp-uniform
 
@@ -464,7 +469,8 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               for (int xx = 0; xx < 4; ++xx) {
                 const int x = x4 * 4 + xx;
                 const float y = __uint_as_float(r[gq][x]) * rxv[xx] * cj;      // S_ij * log2(e)
-                g[x] = ex2(y - p.k2) * (uv[xx] + vj);
+                const float ev = (xx == 0) ? ex2(y - p.k2) : ex2_poly(y - p.k2);   // 1 in 4 on the MUFU
+                g[x] = ev * (uv[xx] + vj);
                 ds = fmaf(g[x], y, ds);
               }
             }
@@ -523,7 +529,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
         if (lane == 0) red[e] = ds;
-        epi_bar_sync();
+        epi_bar_sync<NUM_EPI_WARPS * 32>();
         if (te == 0) {
           float tot = 0.f;
 #pragma unroll
@@ -535,7 +541,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 
   ptx::tc_fence_before();
-  if (csize > 1) ptx::cluster_sync(); else __syncthreads();   // no CTA may exit while peers still multicast into it
+  __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 

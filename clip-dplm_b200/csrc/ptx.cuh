@@ -126,6 +126,60 @@ __device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask) : "memory");
 }
 
+// Software-pipelined issue blocks.  An mbarrier.try_wait costs ~170 clk even when the phase has already
+// completed (measured, tools/umma_bench.cu) -- more than the four 128xNx16 MMAs of one K=64 box take to issue.  These
+// blocks start the try_wait for the NEXT stage first, issue the current stage's work, and only then read the
+// predicate, so the wait latency hides behind the issue.  Returns 1 if the next stage is already complete.
+
+// Four MMAs over one K=64 box (descriptor start addresses advance by 32 B = 2 units per K=16 step).
+__device__ __forceinline__ uint32_t mma_box_prefetch(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                     uint32_t accumulate_first, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P, PA, PT;\n\t"
+      ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%6], %7;\n\t"
+      "setp.ne.b32 PA, %5, 0;\n\t"
+      "setp.eq.u32 PT, %1, %1;\n\t"
+      "add.u64 a1, %2, 2;\n\t"
+      "add.u64 b1, %3, 2;\n\t"
+      "add.u64 a2, %2, 4;\n\t"
+      "add.u64 b2, %3, 4;\n\t"
+      "add.u64 a3, %2, 6;\n\t"
+      "add.u64 b3, %3, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %4, PA;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %4, PT;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %4, PT;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %4, PT;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_parity)
+      : "memory");
+  return ready;
+}
+
+// Arm `full_bar` for `bytes` and issue one TMA box load; try_wait on the next stage's EMPTY barrier overlaps.
+__device__ __forceinline__ uint32_t tma_box_prefetch(uint32_t dst_smem, const CUtensorMap* m, uint32_t full_bar,
+                                                     uint32_t bytes, int c0, int c1, uint32_t next_bar,
+                                                     uint32_t next_parity) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%7], %8;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n\t"
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%5, %6}], [%3];\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(full_bar), "r"(bytes), "r"(c0), "r"(c1), "r"(next_bar),
+        "r"(next_parity)
+      : "memory");
+  return ready;
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (lane l gets its own row).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
