@@ -29,6 +29,7 @@ SIGNATURES = {
     "clipnce_version": [],
     "clipnce_last_error": [],
     "clipnce_uses_tensor_cores": [_int, _i64, _f32, _int],
+    "clipnce_needs_transposed": [_int, _i64, _f32, _int],
     "clipnce_workspace_bytes": [_i64, _i64, _i64, _int, _int, ctypes.POINTER(_sz)],
     "clipnce_normalize": [_vp, _int, _i64, _i64, _vp, _vp, _int, _vp],
     "clipnce_stage_operand": [_vp, _int, _i64, _i64, _vp, _vp, _i64, _int, _vp],

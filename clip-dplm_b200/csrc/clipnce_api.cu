@@ -14,6 +14,7 @@
 
 #include "../../include/clipnce.h"
 #include "kernels_aux.cuh"
+#include "kernels_pair.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 
@@ -48,13 +49,19 @@ bool tc_eligible(int dtype, int64_t d, float scale, int flags) {
          scale > 0.f && 2.f * scale <= 86.f;
 }
 
+// CTA-pair kernels (kernels_pair.cuh): the main tensor-core path.  CLIPNCE_NO_PAIR=1 forces the single-CTA kernels.
+bool pair_eligible(int64_t d) {
+  static const bool off = [] { const char* e = getenv("CLIPNCE_NO_PAIR"); return e && atoi(e) != 0; }();
+  return !off && d % 128 == 0 && d >= 128 && d <= 768;
+}
+
 // ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda) ----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
-bool g_attr_done[4] = {false, false, false, false};
+bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
 
 int get_encode(EncodeTiledFn* out) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -125,6 +132,56 @@ int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const
   return 0;
 }
 
+template <int ROWS>
+int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams p, cudaStream_t st) {
+  auto kern = pair::fwd_kernel<ROWS>;
+  int stages = (pair::SMEM_LIMIT - pair::fwd_smem_bytes(ROWS, p.nkc, 0)) / pair::STAGE_BYTES;
+  if (stages > pair::MAX_STAGES) stages = pair::MAX_STAGES;
+  if (stages < 2) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for a TMA ring", p.d);
+  p.stages = stages;
+  CUtensorMap tx, ty;
+  int rc;
+  if ((rc = make_tmap(&tx, x, p.d, p.n_rows, p.d, ROWS))) return rc;
+  if ((rc = make_tmap(&ty, y, p.d, p.n_cols, p.d, 128))) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_attr_done[attr_slot]) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
+      g_attr_done[attr_slot] = true;
+    }
+  }
+  const int grid = 2 * (int)ceil_div(p.n_rows, 2 * ROWS);
+  kern<<<grid, pair::FWD_THREADS, pair::fwd_smem_bytes(ROWS, p.nkc, stages), st>>>(tx, ty, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_t st) {
+  auto kern = pair::bwd_kernel;
+  const int total = (pair::SMEM_LIMIT - pair::bwd_smem_bytes(p.nkc, 0)) / pair::STAGE_BYTES;
+  if (total < 4) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for the TMA rings", p.d);
+  auto cap = [](int v) { return v > pair::MAX_STAGES ? pair::MAX_STAGES : v; };
+  p.stages_b = cap(total / 2);
+  p.stages_a = cap(total - total / 2);
+  p.nsbuf = p.nq2 <= 2 ? 2 : 1;   // 128 nq2 accumulator columns + 128 per logits buffer <= 512
+  CUtensorMap tx, ty, tyg;
+  int rc;
+  if ((rc = make_tmap(&tx, x, p.d, p.n_rows, p.d, pair::BWD_ROWS))) return rc;
+  if ((rc = make_tmap(&ty, y, p.d, p.n_cols, p.d, 128))) return rc;
+  if ((rc = make_tmap(&tyg, y, p.d, p.n_cols, p.d, 64))) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_attr_done[6]) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
+      g_attr_done[6] = true;
+    }
+  }
+  const int grid = 2 * (int)ceil_div(p.n_rows, 2 * pair::BWD_ROWS);
+  kern<<<grid, pair::BWD_THREADS, pair::bwd_smem_bytes(p.nkc, p.stages_a + p.stages_b), st>>>(tx, ty, tyg, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int fwd_block_i(int64_t n_rows, int64_t d) { return (d <= 512 && n_rows >= 128 * 148) ? 128 : 64; }
 // 64 rows (two logits buffers, deeper rings) measured faster than 96 rows (one buffer, 16 KiB stages) on B200
 // (9.6 vs 11.4 ms per side at N = 65536, d = 512); CLIPNCE_BWD_ROWS=96 selects the wider variant.
@@ -163,13 +220,19 @@ int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags) {
   return tc_eligible(dtype, d, scale, flags) ? 1 : 0;
 }
 
+int clipnce_needs_transposed(int dtype, int64_t d, float scale, int flags) {
+  return (tc_eligible(dtype, d, scale, flags) && !pair_eligible(d)) ? 1 : 0;
+}
+
 int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, int flags, size_t* out) {
   if (!out || n_rows < 1 || n_cols < 1 || d < 1) return fail(CLIPNCE_EINVAL, "workspace_bytes: bad shape");
   if (dtype != CLIPNCE_BF16 && dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "workspace_bytes: bad dtype %d", dtype);
   (void)flags;
   // tensor-core path (worst case over BLOCK_I choices) and exact path, forward and backward
   size_t tc_fwd = sizeof(float) * 2 * (size_t)ceil_div(n_rows, 64) * (size_t)round_up(n_cols, 32);
-  size_t tc_bwd = sizeof(float) * (size_t)ceil_div(n_rows, 64);
+  size_t tc_bwd = sizeof(float) * (size_t)ceil_div(n_rows, 8);
+  size_t pair_fwd = sizeof(float) * 2 * (size_t)ceil_div(n_rows, 128) * (size_t)round_up(n_cols, 256);
+  if (pair_fwd > tc_fwd) tc_fwd = pair_fwd;
   SimtFwdWs w = simt_fwd_ws(nullptr, n_rows, n_cols);
   size_t simt_bwd = sizeof(float) * (size_t)ceil_div(n_rows, simt::TILE);
   size_t m = tc_fwd;
@@ -242,6 +305,26 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
 
   if (tc_eligible(dtype, d, scale, flags)) {
     if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
+    if (pair_eligible(d)) {
+      const int rows = d <= 512 ? 128 : 64;
+      pair::FwdParams p;
+      memset(&p, 0, sizeof p);
+      p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
+      p.nkc = (int)ceil_div(d, 64); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
+      p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E;
+      p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_l = row_l; p.diag = diag;
+      p.col_part = reinterpret_cast<float*>(workspace);
+      p.col_ld = (long long)p.n_steps * pair::STEP_J;
+      const int n_part = 2 * (int)ceil_div(n_rows, 2 * rows);
+      const size_t need = sizeof(float) * (size_t)n_part * (size_t)p.col_ld;
+      if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
+      rc = rows == 128 ? launch_pair_fwd<128>(4, x, y, p, st) : launch_pair_fwd<64>(5, x, y, p, st);
+      if (rc) return rc;
+      aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, n_part, p.col_ld, n_cols, scale,
+                                                                                  col_m, col_l);
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
     const int bi = fwd_block_i(n_rows, d);
     const int64_t n_ib = ceil_div(n_rows, bi);
     const int64_t col_ld = round_up(n_cols, 32);
@@ -303,6 +386,30 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
   cudaStream_t st = as_stream(stream);
   int rc = check_device_sm100();
   if (rc) return rc;
+
+  if (tc_eligible(dtype, d, scale, flags) && pair_eligible(d)) {
+    if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "backward: operands must be 16-byte aligned");
+    const int64_t n_blk = ceil_div(n_rows, 8);
+    const size_t need = sizeof(float) * (size_t)n_blk;
+    if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
+    pair::BwdParams p;
+    memset(&p, 0, sizeof p);
+    p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
+    p.nkc = (int)ceil_div(d, 64); p.nq2 = (int)ceil_div(d, 256); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
+    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E; p.diag_w = diag_w; p.out_scale = grad_out * scale;
+    p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m_in = row_m; p.row_w = row_w; p.col_m_in = col_m; p.col_w = col_w;
+    p.dx = dx_hat;
+    if ((rc = launch_pair_bwd(x, y, p, st))) return rc;
+    if (d_scale_sum) {
+      // sum_ij G_ij S_ij = sum_i <xhat_i, dxhat_i> / grad_out: read it off the finished gradient instead of
+      // carrying an extra FMA per logit through the epilogue
+      float* part = reinterpret_cast<float*>(workspace);
+      aux::rowdot_partials<<<(unsigned)n_blk, 256, 0, st>>>((const __nv_bfloat16*)x, rinv_x, dx_hat, n_rows, (int)d, part);
+      aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(part, (int)n_blk, 1.f, d_scale_sum);
+      CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+  }
 
   if (tc_eligible(dtype, d, scale, flags)) {
     if (!y_t) return fail(CLIPNCE_EINVAL, "backward: the tensor-core path needs y_t");

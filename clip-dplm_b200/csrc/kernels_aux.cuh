@@ -163,4 +163,37 @@ __global__ void reduce_scalar_partials(const float* __restrict__ part, int n_par
   }
 }
 
+// part[block] = sum over the block's 8 rows of rinv_i <x_i, g_i>   (= <xhat_i, dxhat_i>; one warp per row)
+template <typename TI>
+__global__ void rowdot_partials(const TI* __restrict__ x, const float* __restrict__ rinv, const float* __restrict__ g,
+                                int64_t n, int d, float* __restrict__ part) {
+  __shared__ float sh[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 8 + w;
+  float dot = 0.f;
+  if (row < n) {
+    const TI* xr = x + row * d;
+    const float* gr = g + row * d;
+    for (int k = lane; k < d; k += 32) dot = fmaf(ld_f(xr + k), gr[k], dot);
+    dot = warp_sum(dot) * rinv[row];
+  }
+  if (lane == 0) sh[w] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) part[blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
+}
+
+// *dst += coef * sum_p part[p]: 256 threads, strided fp64 partial sums + a fixed-order tree (deterministic).
+__global__ void reduce_scalar_partials_par(const float* __restrict__ part, int n_part, float coef, float* __restrict__ dst) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int p = threadIdx.x; p < n_part; p += 256) acc += (double)part[p];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dst[0] += (float)(sh[0] * (double)coef);
+}
+
 }  // namespace aux

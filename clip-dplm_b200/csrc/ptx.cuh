@@ -204,6 +204,95 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ CTA pairs (cta_group::2)
+// A pair = cluster of two CTAs on the two SMs of one TPC.  One tcgen05.mma issued by the leader (cluster rank 0)
+// reads A (its M/2 rows) and B (its N/2 rows) from the shared memory of BOTH CTAs at the same offsets and writes the
+// accumulator rows of each CTA into that CTA's own TMEM.  All four primitives below were validated on a B200 with
+// tools/umma_probe.cu (numerics against a CPU GEMM for K-/MN-major operands, 4x1 and 2x2 accumulator layouts).
+
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive (count 1) on an mbarrier of ANY CTA of the cluster; release at cluster scope so the waiter sees our writes
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait on a LOCAL barrier whose arrivals may come from the peer CTA (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {   // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA box load into THIS CTA's shared memory whose completion bytes are counted on the LEADER's mbarrier at the same
+// offset (bit 24 of a shared-window address selects the CTA within a pair)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+// Four pair-MMAs over one K = 64 slab; descriptor start addresses advance by a_step / b_step (16-byte units) per K = 16
+// (2 for a K-major operand, 128 for an MN-major one whose 8-row groups are 1 KiB apart).  The try_wait on the NEXT
+// stage's barrier overlaps the issue (see mma_box_prefetch); returns 1 if that stage is already complete.
+__device__ __forceinline__ uint32_t mma_box_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t a_step,
+                                                 uint32_t b_step, uint32_t idesc, uint32_t accumulate_first,
+                                                 uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P, PA, PT;\n\t"
+      ".reg .b64 sa, sb, a1, b1, a2, b2, a3, b3;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%8], %9;\n\t"
+      "setp.ne.b32 PA, %7, 0;\n\t"
+      "setp.eq.u32 PT, %1, %1;\n\t"
+      "cvt.u64.u32 sa, %4;\n\t"
+      "cvt.u64.u32 sb, %5;\n\t"
+      "add.u64 a1, %2, sa;\n\t"
+      "add.u64 b1, %3, sb;\n\t"
+      "add.u64 a2, a1, sa;\n\t"
+      "add.u64 b2, b1, sb;\n\t"
+      "add.u64 a3, a2, sa;\n\t"
+      "add.u64 b3, b2, sb;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %6, PA;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %6, PT;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %6, PT;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %6, PT;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate_first),
+        "r"(next_bar), "r"(next_parity)
+      : "memory");
+  return ready;
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor for a K-major bf16 operand tile stored as rows of 128 B
 // (64 bf16) with the 128-byte swizzle, 8-row groups 1024 B apart -- exactly what a TMA box
@@ -218,6 +307,25 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+
+// The same physical tile read as an MN-major operand: a TMA box {64 elements, R rows} of a row-major [k][mn] matrix
+// holds 64 consecutive MN elements per 128-byte row and consecutive K per row; the canonical SWIZZLE_128B MN-major
+// layout is ((64 mn, groups) , (8 k, groups)) with LBO = byte distance between 64-element MN groups (the next box)
+// and SBO = 1 KiB between 8-row K groups.  One K = 16 instruction step advances the start address by 2 KiB.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_major(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // Instruction descriptor, kind::f16: bf16 A and B (both K-major), f32 accumulate, shape M x N.

@@ -49,6 +49,9 @@ class CudaEngine:
     def uses_tensor_cores(self, dtype, d, scale, flags=0):
         return bool(self.lib.clipnce_uses_tensor_cores(_DT[dtype], d, float(scale), flags))
 
+    def needs_transposed(self, dtype, d, scale, flags=0):
+        return bool(self.lib.clipnce_needs_transposed(_DT[dtype], d, float(scale), flags))
+
     def workspace(self, n_rows, n_cols, d, dtype, flags, device):
         key = (n_rows, n_cols, d, dtype, flags, device, torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws.get(key)

@@ -88,7 +88,7 @@ def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra=Non
     diag_offset = rank * n_local
 
     tc = engine.uses_tensor_cores(compute_dtype, a.shape[1], scale, flags)
-    want_t = need_grad and tc
+    want_t = need_grad and tc and engine.needs_transposed(compute_dtype, a.shape[1], scale, flags)
     rinv_a, _ = engine.normalize(a)
     rinv_b, _ = engine.normalize(b)
     a_c, a_c_t = engine.stage(a, compute_dtype, want_t=want_t)

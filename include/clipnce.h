@@ -52,6 +52,11 @@ const char* clipnce_last_error(void);
  * CUDA-core kernels (dtype F32, d % 8 != 0, d > 768, or 2*scale > 86 where exp(S - s) leaves fp32). */
 int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags);
 
+/* 1 if clipnce_backward needs the transposed copy y_t for these arguments.  The CTA-pair kernels (d % 128 == 0,
+ * d <= 768) read the streamed rows directly as an MN-major MMA operand and take y_t = NULL; only the single-CTA
+ * tensor-core kernels (other d % 8 == 0 up to 768) stream a transposed copy. */
+int clipnce_needs_transposed(int dtype, int64_t d, float scale, int flags);
+
 /* Bytes of scratch clipnce_forward / clipnce_backward need for these shapes (max of the two). */
 int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, int flags, size_t* out);
 
@@ -121,7 +126,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
  * Columns without positives (hard-negative cache, old/clip_opt.py:118-121) carry col_w_j = 0.
  * Call it once as (A, B, B^T, rinv_a, rinv_b, row, col, +offset) for dAhat and once as
  * (B, A, A^T, rinv_b, rinv_a, col, row, -offset) for dBhat.
- * y_t [d,ld_t] (clipnce_stage_operand) is only read by the tensor-core path (NULL for the exact path).
+ * y_t [d,ld_t] (clipnce_stage_operand) is only read when clipnce_needs_transposed() says so (NULL otherwise).
  * col_m/col_w (together) and d_scale_sum may be NULL.
  */
 int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t,

@@ -21,6 +21,9 @@ class TorchCpuEngine:
     def uses_tensor_cores(self, dtype, d, scale, flags=0):
         return True   # so that step.py exercises the transposed-operand plumbing too
 
+    def needs_transposed(self, dtype, d, scale, flags=0):
+        return True
+
     def normalize(self, x, want_hat=None):
         xf = x.to(self.dt)
         denom = xf.norm(dim=1).clamp_min(EPS)
