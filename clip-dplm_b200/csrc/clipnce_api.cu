@@ -132,6 +132,15 @@ int launch_tc(int attr_slot, const CUtensorMap& tx, const CUtensorMap& ty, const
   return 0;
 }
 
+int pair_slots() {   // CTA pairs that can be resident at once: one per two SMs
+  static const int slots = [] {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms / 2 > 0 ? sms / 2 : 1;
+  }();
+  return slots;
+}
+
 template <int ROWS>
 int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams p, cudaStream_t st) {
   auto kern = pair::fwd_kernel<ROWS>;
@@ -150,7 +159,7 @@ int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams
       g_attr_done[attr_slot] = true;
     }
   }
-  const int grid = 2 * (int)ceil_div(p.n_rows, 2 * ROWS);
+  const int grid = 2 * p.n_pairs * (int)ceil_div(p.n_steps, p.split_steps);
   kern<<<grid, pair::FWD_THREADS, pair::fwd_smem_bytes(ROWS, p.nkc, stages), st>>>(tx, ty, p);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -231,7 +240,8 @@ int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype
   // tensor-core path (worst case over BLOCK_I choices) and exact path, forward and backward
   size_t tc_fwd = sizeof(float) * 2 * (size_t)ceil_div(n_rows, 64) * (size_t)round_up(n_cols, 32);
   size_t tc_bwd = sizeof(float) * (size_t)ceil_div(n_rows, 8);
-  size_t pair_fwd = sizeof(float) * 2 * (size_t)ceil_div(n_rows, 128) * (size_t)round_up(n_cols, 256);
+  size_t pair_fwd = sizeof(float) * (2 * (size_t)ceil_div(n_rows, 128) * (size_t)round_up(n_cols, 256) +
+                                     (size_t)pair::MAX_SPLIT * (size_t)n_rows);
   if (pair_fwd > tc_fwd) tc_fwd = pair_fwd;
   SimtFwdWs w = simt_fwd_ws(nullptr, n_rows, n_cols);
   size_t simt_bwd = sizeof(float) * (size_t)ceil_div(n_rows, simt::TILE);
@@ -312,16 +322,36 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
       p.nkc = (int)ceil_div(d, 64); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
       p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E;
-      p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_l = row_l; p.diag = diag;
-      p.col_part = reinterpret_cast<float*>(workspace);
+      p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.diag = diag;
+      p.n_pairs = (int)ceil_div(n_rows, 2 * rows);
+      // cut the column sweep so that the work items fill whole waves of CTA pairs (one pair per two SMs)
+      int n_split = 1;
+      {
+        const int slots = pair_slots();
+        double best = 0.0;
+        for (int ns = 1; ns <= pair::MAX_SPLIT; ++ns) {
+          if (ns > 1 && p.n_steps / ns < 4) break;
+          const int sps = (int)ceil_div(p.n_steps, ns);
+          const int items = p.n_pairs * (int)ceil_div(p.n_steps, sps);
+          const double eff = (double)items / ((double)slots * (double)ceil_div(items, slots)) - 0.005 * ns;
+          if (eff > best) { best = eff; n_split = ns; }
+        }
+      }
+      p.split_steps = (int)ceil_div(p.n_steps, n_split);
+      n_split = (int)ceil_div(p.n_steps, p.split_steps);
       p.col_ld = (long long)p.n_steps * pair::STEP_J;
-      const int n_part = 2 * (int)ceil_div(n_rows, 2 * rows);
-      const size_t need = sizeof(float) * (size_t)n_part * (size_t)p.col_ld;
+      const int n_part = 2 * p.n_pairs;
+      const size_t col_bytes = sizeof(float) * (size_t)n_part * (size_t)p.col_ld;
+      const size_t need = col_bytes + sizeof(float) * (size_t)n_split * (size_t)n_rows;
       if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
+      p.col_part = reinterpret_cast<float*>(workspace);
+      p.row_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + col_bytes);
       rc = rows == 128 ? launch_pair_fwd<128>(4, x, y, p, st) : launch_pair_fwd<64>(5, x, y, p, st);
       if (rc) return rc;
       aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, n_part, p.col_ld, n_cols, scale,
                                                                                   col_m, col_l);
+      aux::reduce_col_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(p.row_part, n_split, n_rows, n_rows, scale,
+                                                                                  row_m, row_l);
       CUDA_TRY(cudaGetLastError());
       return 0;
     }

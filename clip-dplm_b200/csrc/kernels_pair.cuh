@@ -39,6 +39,7 @@ namespace pair {
 constexpr int STEP_J = 256;            // streamed columns per step (128 TMA rows per CTA)
 constexpr int STAGE_BYTES = 16384;     // one ring stage: [128 rows][64 k] or 2 x [64 j][64 d]
 constexpr int MAX_STAGES = 6;
+constexpr int MAX_SPLIT = 8;          // forward: work items per row block
 constexpr int SMEM_LIMIT = 232448;
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -200,7 +201,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       ptx::mbar_wait(bar(B_XFULL), 0);
       for (int t = 0; t < p.n_steps; ++t) {
         const int sb = t % p.nsbuf;
-        ptx::mbar_wait_cluster(bar(B_SEMPTY + sb), ((t / p.nsbuf) & 1) ^ 1u);
+        ptx::mbar_wait(bar(B_SEMPTY + sb), ((t / p.nsbuf) & 1) ^ 1u);
         const uint32_t d_tmem = tmem_base + S_COL0 + sb * 128;
         for (int g = 0; g < p.nkc; ++g) {
           if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
@@ -227,7 +228,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       uint32_t phase = 0, ready = 0;
       for (int t = 0; t < p.n_steps; ++t) {
         for (int kc = 0; kc < 4; ++kc) {
-          ptx::mbar_wait_cluster(bar(B_GFULL + kc), t & 1);   // both CTAs wrote gradient box kc of step t
+          ptx::mbar_wait(bar(B_GFULL + kc), t & 1);   // both CTAs wrote gradient box kc of step t
           for (int q = 0; q < p.nq2; ++q) {
             const int wq = min(256, p.d - 256 * q);
             const uint32_t idesc_g = ptx::idesc_bf16_f32_major(2 * BWD_ROWS, wq, 0, 1);
@@ -384,12 +385,14 @@ constexpr int FWD_SMALL = 16384;   // barriers (512) | tmem ptr | +1024: column 
 struct FwdParams {
   int n_rows, n_cols, d;
   int nkc, n_steps, stages;
+  int n_pairs;        // row blocks (pairs of CTAs)
+  int split_steps;    // steps per work item: the column sweep is cut into ceil(n_steps / split_steps) work items per
+                      // row block so that the grid fills whole waves of CTA pairs
   long long diag_offset;
   float scale, k2;
   const float* rinv_x;
   const float* rinv_y;
-  float* row_m;       // [n_rows] = s (the fixed shift)
-  float* row_l;       // [n_rows] sum_j exp(S_ij - s)
+  float* row_part;    // [n_split][n_rows] partial sum_j exp(S_ij - s) over the item's columns
   float* col_part;    // [gridDim.x][col_ld] partial sum_i exp(S_ij - s) over this CTA's rows
   long long col_ld;   // n_steps * 256
   float* diag;        // [n_rows]
@@ -419,7 +422,12 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int i0 = (blockIdx.x >> 1) * (2 * ROWS) + (int)rank * ROWS;
+  const int item = blockIdx.x >> 1;
+  const int split = item / p.n_pairs;
+  const int i0 = (item % p.n_pairs) * (2 * ROWS) + (int)rank * ROWS;
+  const int t_begin = split * p.split_steps;
+  const int t_end = min(p.n_steps, t_begin + p.split_steps);
+  const int col_row = 2 * (item % p.n_pairs) + (int)rank;   // this CTA's row of the column-partial matrix
 
   const uint32_t x_smem = base;
   const uint32_t ring_a = x_smem + p.nkc * X_CHUNK;
@@ -462,7 +470,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         ptx::tma_load_2d_pair(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < p.n_steps; ++t) {
+      for (int t = t_begin; t < t_end; ++t) {
         for (int g = 0; g < p.nkc; ++g) {
           ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
           if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
@@ -484,9 +492,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
       int stage = 0;
       uint32_t phase = 0, ready = 0;
       ptx::mbar_wait(bar(B_XFULL), 0);
-      for (int t = 0; t < p.n_steps; ++t) {
+      for (int t = 0; t < t_end - t_begin; ++t) {
         const int sb = t & 1;
-        ptx::mbar_wait_cluster(bar(B_SEMPTY + sb), ((t >> 1) & 1) ^ 1u);
+        ptx::mbar_wait(bar(B_SEMPTY + sb), ((t >> 1) & 1) ^ 1u);
         const uint32_t d_tmem = tmem_base + sb * SBUF_COLS;
         for (int g = 0; g < p.nkc; ++g) {
           if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
@@ -525,28 +533,32 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
 
     auto flush_cols = [&](int t) {   // column partials of step t: sum the lane quarters in fixed order
       if (te < STEP_J) {
-        const float* cr = colred + (t & 1) * 1024 + te;
+        const float* cr = colred + ((t - t_begin) & 1) * 1024 + te;
         float s = cr[0] + cr[256];
         if (NSLOT == 4) s = (s + cr[512]) + cr[768];
-        p.col_part[(long long)blockIdx.x * p.col_ld + (long long)t * STEP_J + te] = s;
+        p.col_part[(long long)col_row * p.col_ld + (long long)t * STEP_J + te] = s;
       }
     };
 
     float ry_n = 0.f;
-    if (te < STEP_J) ry_n = (te < p.n_cols) ? p.rinv_y[te] : -1.f;   // -1 marks a column past the end
-    for (int t = 0; t < p.n_steps; ++t) {
-      const int sb = t & 1;
-      float* const cv = colv + (t & 1) * 512;
+    if (te < STEP_J) {   // -1 marks a column past the end
+      const long long j = (long long)t_begin * STEP_J + te;
+      ry_n = (j < p.n_cols) ? p.rinv_y[j] : -1.f;
+    }
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tl = t - t_begin;
+      const int sb = tl & 1;
+      float* const cv = colv + (tl & 1) * 512;
       if (te < STEP_J) {
         cv[te] = ry_n < 0.f ? 0.f : ry_n * p.k2;
         cv[256 + te] = ry_n < 0.f ? -10000.f : -p.k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
         const long long jn = (long long)(t + 1) * STEP_J + te;
-        ry_n = (t + 1 < p.n_steps && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
+        ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
       }
       named_bar_sync(1, EPI_THREADS);
-      if (t > 0) flush_cols(t - 1);
+      if (t > t_begin) flush_cols(t - 1);
 
-      ptx::mbar_wait(bar(B_SFULL + sb), (t >> 1) & 1);
+      ptx::mbar_wait(bar(B_SFULL + sb), (tl >> 1) & 1);
       ptx::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -585,11 +597,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         for (int x = 0; x < 32; ++x) r4[x & 3] += ev[x];
         rsum += (r4[0] + r4[1]) + (r4[2] + r4[3]);
         tc::warp_transpose_reduce<32>(ev, lane);   // lane L: sum over this warp's 32 rows of column L
-        colred[(t & 1) * 1024 + slot * 256 + jl0 + 32 * c + lane] = ev[0];
+        colred[(tl & 1) * 1024 + slot * 256 + jl0 + 32 * c + lane] = ev[0];
       }
     }
     named_bar_sync(1, EPI_THREADS);
-    flush_cols(p.n_steps - 1);
+    if (t_end > t_begin) flush_cols(t_end - 1);
 
     // row sums: combine the warps that share a row (column groups, and for the 2x2 layout both column halves)
     rowred[e * 32 + lane] = rsum;
@@ -602,10 +614,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         const bool mine = ROWS == 128 ? ((w & 3) == rq) : ((w & 1) == rq);
         if (mine) tot += rowred[w * 32 + rl];
       }
-      if ((long long)i0 + te < p.n_rows) {
-        p.row_m[i0 + te] = p.scale;
-        p.row_l[i0 + te] = tot;
-      }
+      if ((long long)i0 + te < p.n_rows) p.row_part[(long long)split * p.n_rows + i0 + te] = tot;
     }
   }
 
