@@ -141,6 +141,26 @@ int pair_slots() {   // CTA pairs that can be resident at once: one per two SMs
   return slots;
 }
 
+// Cut a row block's column sweep into work items so that the grid fills whole waves of CTA pairs; every item pays a
+// fixed prologue / drain (~0.75 step), so fewer, longer items win ties.  Returns steps per item.
+int pick_split_steps(int n_pairs, int n_steps, int max_split) {
+  if (const char* e = getenv("CLIPNCE_SPLIT_STEPS")) {   // test hook: force the number of steps per work item
+    const int v = atoi(e);
+    if (v >= 1) return (int)ceil_div(n_steps, v) <= max_split ? v : (int)ceil_div(n_steps, max_split);
+  }
+  const int slots = pair_slots();
+  double best = -1.0;
+  int best_sps = n_steps;
+  for (int ns = 1; ns <= max_split; ++ns) {
+    const int sps = (int)ceil_div(n_steps, ns);
+    if (ns > 1 && sps < 8) break;
+    const int items = n_pairs * (int)ceil_div(n_steps, sps);
+    const double eff = (double)items / ((double)slots * (double)ceil_div(items, slots)) * (double)sps / ((double)sps + 0.75);
+    if (eff > best + 1e-9) { best = eff; best_sps = sps; }
+  }
+  return best_sps;
+}
+
 template <int ROWS>
 int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams p, cudaStream_t st) {
   auto kern = pair::fwd_kernel<ROWS>;
@@ -185,7 +205,7 @@ int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_
       g_attr_done[6] = true;
     }
   }
-  const int grid = 2 * (int)ceil_div(p.n_rows, 2 * pair::BWD_ROWS);
+  const int grid = 2 * p.n_pairs * (int)ceil_div(p.n_steps, p.split_steps);
   kern<<<grid, pair::BWD_THREADS, pair::bwd_smem_bytes(p.nkc, p.stages_a + p.stages_b), st>>>(tx, ty, tyg, p);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -239,7 +259,16 @@ int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype
   (void)flags;
   // tensor-core path (worst case over BLOCK_I choices) and exact path, forward and backward
   size_t tc_fwd = sizeof(float) * 2 * (size_t)ceil_div(n_rows, 64) * (size_t)round_up(n_cols, 32);
-  size_t tc_bwd = sizeof(float) * (size_t)ceil_div(n_rows, 8);
+  size_t tc_bwd = round_up(sizeof(float) * (size_t)ceil_div(n_rows, 8), 256);
+  {   // pair backward: per-split partial gradients when the row blocks alone cannot fill the GPU (capped at 256 MiB)
+    const size_t slab = sizeof(float) * (size_t)n_rows * (size_t)d;
+    const int n_pairs = (int)ceil_div(n_rows, 128);
+    if (pair_eligible(d) && n_pairs < 4 * pair_slots()) {
+      size_t ns = pair::MAX_SPLIT;
+      while (ns > 1 && ns * slab > ((size_t)256 << 20)) --ns;
+      if (ns > 1) tc_bwd += ns * slab;
+    }
+  }
   size_t pair_fwd = sizeof(float) * (2 * (size_t)ceil_div(n_rows, 128) * (size_t)round_up(n_cols, 256) +
                                      (size_t)pair::MAX_SPLIT * (size_t)n_rows);
   if (pair_fwd > tc_fwd) tc_fwd = pair_fwd;
@@ -324,21 +353,8 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E;
       p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.diag = diag;
       p.n_pairs = (int)ceil_div(n_rows, 2 * rows);
-      // cut the column sweep so that the work items fill whole waves of CTA pairs (one pair per two SMs)
-      int n_split = 1;
-      {
-        const int slots = pair_slots();
-        double best = 0.0;
-        for (int ns = 1; ns <= pair::MAX_SPLIT; ++ns) {
-          if (ns > 1 && p.n_steps / ns < 4) break;
-          const int sps = (int)ceil_div(p.n_steps, ns);
-          const int items = p.n_pairs * (int)ceil_div(p.n_steps, sps);
-          const double eff = (double)items / ((double)slots * (double)ceil_div(items, slots)) - 0.005 * ns;
-          if (eff > best) { best = eff; n_split = ns; }
-        }
-      }
-      p.split_steps = (int)ceil_div(p.n_steps, n_split);
-      n_split = (int)ceil_div(p.n_steps, p.split_steps);
+      p.split_steps = pick_split_steps(p.n_pairs, p.n_steps, pair::MAX_SPLIT);
+      const int n_split = (int)ceil_div(p.n_steps, p.split_steps);
       p.col_ld = (long long)p.n_steps * pair::STEP_J;
       const int n_part = 2 * p.n_pairs;
       const size_t col_bytes = sizeof(float) * (size_t)n_part * (size_t)p.col_ld;
@@ -420,16 +436,30 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
   if (tc_eligible(dtype, d, scale, flags) && pair_eligible(d)) {
     if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "backward: operands must be 16-byte aligned");
     const int64_t n_blk = ceil_div(n_rows, 8);
-    const size_t need = sizeof(float) * (size_t)n_blk;
-    if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, need);
+    const size_t part_bytes = round_up(sizeof(float) * (size_t)n_blk, 256);
     pair::BwdParams p;
     memset(&p, 0, sizeof p);
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq2 = (int)ceil_div(d, 256); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
     p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E; p.diag_w = diag_w; p.out_scale = grad_out * scale;
     p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m_in = row_m; p.row_w = row_w; p.col_m_in = col_m; p.col_w = col_w;
-    p.dx = dx_hat;
+    p.n_pairs = (int)ceil_div(n_rows, 2 * pair::BWD_ROWS);
+    // split the column sweep only where the row blocks alone leave SMs idle (few local rows: the row-sharded step),
+    // and only as far as the scratch for the per-split partial gradients reaches
+    int max_split = (int)((workspace_bytes > part_bytes ? workspace_bytes - part_bytes : 0) / (sizeof(float) * (size_t)n_rows * (size_t)d));
+    if (max_split > pair::MAX_SPLIT) max_split = pair::MAX_SPLIT;
+    p.split_steps = max_split >= 2 ? pick_split_steps(p.n_pairs, p.n_steps, max_split) : p.n_steps;
+    const int n_split = (int)ceil_div(p.n_steps, p.split_steps);
+    if (workspace_bytes < part_bytes) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, part_bytes);
+    float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part_bytes);
+    p.dx = n_split > 1 ? dx_part : dx_hat;
     if ((rc = launch_pair_bwd(x, y, p, st))) return rc;
+    if (n_split > 1) {
+      const int64_t n4 = n_rows * d / 4;
+      aux::sum_splits<<<(unsigned)ceil_div(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(dx_part), n_split, n4,
+                                                                     reinterpret_cast<float4*>(dx_hat));
+      CUDA_TRY(cudaGetLastError());
+    }
     if (d_scale_sum) {
       // sum_ij G_ij S_ij = sum_i <xhat_i, dxhat_i> / grad_out: read it off the finished gradient instead of
       // carrying an extra FMA per logit through the epilogue

@@ -163,6 +163,18 @@ __global__ void reduce_scalar_partials(const float* __restrict__ part, int n_par
   }
 }
 
+// out = sum_s part[s] over n_split slabs of `n4` float4 each (fixed order).
+__global__ void sum_splits(const float4* __restrict__ part, int n_split, int64_t n4, float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = part[i];
+  for (int s = 1; s < n_split; ++s) {
+    const float4 v = part[(int64_t)s * n4 + i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  out[i] = acc;
+}
+
 // part[block] = sum over the block's 8 rows of rinv_i <x_i, g_i>   (= <xhat_i, dxhat_i>; one warp per row)
 template <typename TI>
 __global__ void rowdot_partials(const TI* __restrict__ x, const float* __restrict__ rinv, const float* __restrict__ g,

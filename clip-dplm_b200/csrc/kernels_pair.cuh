@@ -39,7 +39,7 @@ namespace pair {
 constexpr int STEP_J = 256;            // streamed columns per step (128 TMA rows per CTA)
 constexpr int STAGE_BYTES = 16384;     // one ring stage: [128 rows][64 k] or 2 x [64 j][64 d]
 constexpr int MAX_STAGES = 6;
-constexpr int MAX_SPLIT = 8;          // forward: work items per row block
+constexpr int MAX_SPLIT = 16;         // work items per row block (column-sweep split)
 constexpr int SMEM_LIMIT = 232448;
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -73,6 +73,8 @@ struct BwdParams {
   int nq2;        // ceil(d / 256): accumulator chunks (TMEM slots of 128 columns)
   int n_steps;    // ceil(n_cols / 256)
   int stages_a, stages_b, nsbuf;
+  int n_pairs;      // row blocks
+  int split_steps;  // steps per work item (column-sweep split, see FwdParams); item s accumulates into dx + s n_rows d
   long long diag_offset;
   float scale, k2, diag_w, out_scale;
   const float* rinv_x;
@@ -81,7 +83,7 @@ struct BwdParams {
   const float* row_w;
   const float* col_m_in;   // or nullptr (with col_w)
   const float* col_w;
-  float* dx;               // [n_rows, d] f32
+  float* dx;               // [n_split][n_rows, d] f32 (summed over the splits by aux::sum_splits when n_split > 1)
 };
 
 __host__ __device__ constexpr int bwd_smem_bytes(int nkc, int stages) {
@@ -100,7 +102,11 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int i0 = (blockIdx.x >> 1) * (2 * BWD_ROWS) + (int)rank * BWD_ROWS;   // first resident row of this CTA
+  const int item = blockIdx.x >> 1;
+  const int split = item / p.n_pairs;
+  const int i0 = (item % p.n_pairs) * (2 * BWD_ROWS) + (int)rank * BWD_ROWS;   // first resident row of this CTA
+  const int t_begin = split * p.split_steps;
+  const int n_t = min(p.n_steps, t_begin + p.split_steps) - t_begin;          // steps of this work item
 
   const uint32_t x_smem = base;
   const uint32_t g_smem = x_smem + p.nkc * BWD_X_CHUNK;
@@ -158,12 +164,12 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
         ptx::tma_load_2d_pair(x_smem + kc * BWD_X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < p.n_steps; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         for (int g = 0; g < p.nkc; ++g) {
           ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
           if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
           ptx::tma_load_2d_pair(ring_a + stage * STAGE_BYTES, &tmap_y, bar(B_FULL_A + stage), g * 64,
-                                t * STEP_J + (int)rank * 128);
+                                (t_begin + t) * STEP_J + (int)rank * 128);
           if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
         }
       }
@@ -174,7 +180,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < p.n_steps; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         for (int kc = 0; kc < 4; ++kc) {
           for (int q = 0; q < p.nq2; ++q) {
             const int wq = min(256, p.d - 256 * q);   // 128 or 256 (d % 128 == 0)
@@ -184,7 +190,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
             if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), 2 * ngr * 8192);
             for (int gi = 0; gi < ngr; ++gi)
               ptx::tma_load_2d_pair(ring_b + stage * STAGE_BYTES + gi * 8192, &tmap_yg, bar(B_FULL_B + stage),
-                                    256 * q + half * (int)rank + 64 * gi, t * STEP_J + 64 * kc);
+                                    256 * q + half * (int)rank + 64 * gi, (t_begin + t) * STEP_J + 64 * kc);
             if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
           }
         }
@@ -199,7 +205,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       int stage = 0;
       uint32_t phase = 0, ready = 0;
       ptx::mbar_wait(bar(B_XFULL), 0);
-      for (int t = 0; t < p.n_steps; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         const int sb = t % p.nsbuf;
         ptx::mbar_wait(bar(B_SEMPTY + sb), ((t / p.nsbuf) & 1) ^ 1u);
         const uint32_t d_tmem = tmem_base + S_COL0 + sb * 128;
@@ -226,7 +232,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       const uint32_t g_lo0 = desc_lo(g_smem, 1), b_lo0 = desc_lo(ring_b, 8192 >> 4);
       int stage = 0;
       uint32_t phase = 0, ready = 0;
-      for (int t = 0; t < p.n_steps; ++t) {
+      for (int t = 0; t < n_t; ++t) {
         for (int kc = 0; kc < 4; ++kc) {
           ptx::mbar_wait(bar(B_GFULL + kc), t & 1);   // both CTAs wrote gradient box kc of step t
           for (int q = 0; q < p.nq2; ++q) {
@@ -272,9 +278,9 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     const uint32_t gfull_leader = ptx::mapa(bar(B_GFULL + kc), 0);
     const long long dcol0 = i_glob + p.diag_offset;   // column of this row's positive
 
-    auto load_col = [&](int t, float& cw, float& cm, float& ry) {
-      const long long jn = (long long)t * STEP_J + te;
-      const bool ok = t < p.n_steps && jn < p.n_cols;
+    auto load_col = [&](int t, float& cw, float& cm, float& ry) {   // t: step local to this work item
+      const long long jn = (long long)(t_begin + t) * STEP_J + te;
+      const bool ok = t < n_t && jn < p.n_cols;
       cw = (ok && p.col_w != nullptr) ? p.col_w[jn] : 0.f;
       cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : p.scale;
       ry = ok ? p.rinv_y[jn] : 0.f;
@@ -282,7 +288,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     float cw_n, cm_n, ry_n;
     load_col(0, cw_n, cm_n, ry_n);
 
-    for (int t = 0; t < p.n_steps; ++t) {
+    for (int t = 0; t < n_t; ++t) {
       const int sb = t % p.nsbuf;
       float* const cv = colv + (t & 1) * 768;
       {
@@ -293,7 +299,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       }
       load_col(t + 1, cw_n, cm_n, ry_n);
       named_bar_sync(1, BWD_EPI_WARPS * 32);
-      const long long dl = dcol0 - ((long long)t * STEP_J + jl0);   // step-local index of the positive, if in [0, 64)
+      const long long dl = dcol0 - ((long long)(t_begin + t) * STEP_J + jl0);   // step-local index of the positive, if in [0, 64)
       const bool has_diag = row_ok && dl >= 0 && dl < 64;
 
       ptx::mbar_wait(bar(B_SFULL + sb), (t / p.nsbuf) & 1);
@@ -358,7 +364,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
           ptx::tmem_ld_32x32b_x32(t_lane + 128 * q2 + 64 * h + 32 * c, r);
           ptx::tmem_ld_wait();
           if (row_ok) {
-            float* const dst = p.dx + i_glob * p.d + 256 * q2 + halfw * jh + 64 * h + 32 * c;
+            float* const dst = p.dx + ((long long)split * p.n_rows + i_glob) * p.d + 256 * q2 + halfw * jh + 64 * h + 32 * c;
 #pragma unroll
             for (int x4 = 0; x4 < 8; ++x4)
               *reinterpret_cast<float4*>(dst + 4 * x4) =

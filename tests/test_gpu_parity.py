@@ -223,3 +223,43 @@ def test_zero_row_is_clamped_like_F_normalize():
     assert abs(loss - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
     assert rel(db, ref["d_b"]) <= 5e-5
     assert torch.isfinite(da).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# CTA-pair kernels (d % 128 == 0): no transposed operand, column-sweep splits, ragged edges
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,d,split", [(3000, 3000, 512, 0), (3000, 3000, 512, 3), (1111, 2500, 256, 2),
+                                         (2100, 2100, 768, 4), (2049, 2304, 128, 1)])
+def test_pair_kernels_split_and_ragged(eng, monkeypatch, n, m, d, split):
+    """Forward statistics and both backward sides of the pair kernels against the float64 closed form with the
+    column sweep cut into work items (CLIPNCE_SPLIT_STEPS test hook), y_t = None, rows/columns that are not
+    multiples of the 128-row / 256-column tiles, and n_cols > n_rows (extra negative columns)."""
+    if split:
+        monkeypatch.setenv("CLIPNCE_SPLIT_STEPS", str(split))
+    else:
+        monkeypatch.delenv("CLIPNCE_SPLIT_STEPS", raising=False)
+    scale = 1 / 0.07
+    assert eng.uses_tensor_cores(torch.bfloat16, d, scale) and not eng.needs_transposed(torch.bfloat16, d, scale)
+    a, b = O.make_inputs(max(n, m), d, seed=21, mix=0.4)
+    a, b = a[:n], b[:m]
+    cf = O.closed_form(a.numpy(), b.numpy(), scale)
+    x, y = a.cuda().bfloat16(), b.cuda().bfloat16()
+    rx, _ = eng.normalize(x)
+    ry, _ = eng.normalize(y)
+    row_m, row_l, col_m, col_l, diag = eng.forward(x, y, rx, ry, 0, scale)
+    torch.cuda.synchronize()
+    row_lse = (row_m.double() + row_l.double().log()).cpu()
+    col_lse = (col_m.double() + col_l.double().log()).cpu()
+    assert torch.allclose(row_lse, torch.from_numpy(cf["row_lse"]), rtol=0, atol=1e-4)
+    assert torch.allclose(col_lse, torch.from_numpy(cf["col_lse"]), rtol=0, atol=1e-4)
+    assert torch.allclose(diag.double().cpu(), torch.from_numpy(cf["diag"]), rtol=0, atol=1e-4)
+    if n != m:
+        return   # rectangular: the closed form's gradients assume positives for every column
+    coef = 1.0 / (2 * n)
+    rw, cw = eng.softmax_weights(row_l, coef), eng.softmax_weights(col_l, coef)
+    da, ds = eng.backward(x, y, None, rx, ry, 0, scale, row_m, rw, col_m, cw, 1.0 / n, 1.0)
+    db, _ = eng.backward(y, x, None, ry, rx, 0, scale, col_m, cw, row_m, rw, 1.0 / n, 1.0, want_dscale=False)
+    torch.cuda.synchronize()
+    assert rel(da, cf["d_a_hat"]) <= GRAD_RTOL_BF16, rel(da, cf["d_a_hat"])
+    assert rel(db, cf["d_b_hat"]) <= GRAD_RTOL_BF16, rel(db, cf["d_b_hat"])
+    assert abs(float(ds) - cf["d_scale_sum"]) <= 2e-2 * abs(cf["d_scale_sum"]) + 1e-6
