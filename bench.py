@@ -196,6 +196,38 @@ def run_ours(args, rank, local_rank, world):
             return super().loss(*a, **k)
 
     eng = TimedEngine()
+    trace = {}
+    if args.trace:
+        # per-phase device timeline of one step: CUDA events around every engine call and every collective
+        from clip_dplm_b200 import step as _step_mod
+
+        def wrap(name, fn):
+            def inner(*a, **k):
+                if not eng.on:
+                    return fn(*a, **k)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **k)
+                if isinstance(out, tuple) and len(out) == 2 and hasattr(out[1], "wait"):   # async collective: time to completion
+                    work = out[1]
+
+                    class _W:
+                        def wait(self_inner):
+                            work.wait()
+                            e1.record()
+                    trace.setdefault(name, []).append((e0, e1))
+                    return out[0], _W()
+                e1.record()
+                trace.setdefault(name, []).append((e0, e1))
+                return out
+            return inner
+
+        for nm in ("normalize", "stage", "softmax_weights", "combine_lse", "normalize_backward", "loss"):
+            setattr(eng, nm, wrap(nm, getattr(eng, nm)))
+        _step_mod._all_gather_rows = wrap("all_gather", _step_mod._all_gather_rows)
+        _step_mod._reduce_scatter_rows = wrap("reduce_scatter(issue->done)", _step_mod._reduce_scatter_rows)
+        _orig_ar = dist.all_reduce
+        dist.all_reduce = wrap("all_reduce", _orig_ar)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     a = torch.randn(n_local, d, device=dev, generator=g)
     b = (0.5 * a + 0.5 * torch.randn(n_local, d, device=dev, generator=g)).to(torch.bfloat16)
@@ -241,6 +273,21 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.timeline:
+        # kernel-level timeline of three steps (CUPTI through torch.profiler), rank 0 writes it as text
+        from torch.profiler import profile, ProfilerActivity
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                step_resident()
+            barrier()
+        if rank == 0:
+            evs = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+            evs.sort(key=lambda e: e.time_range.start)
+            t0 = evs[0].time_range.start if evs else 0
+            with open(args.timeline, "w") as f:
+                for e in evs:
+                    f.write(f"{(e.time_range.start - t0) / 1e3:10.3f} ms  {e.time_range.elapsed_us():9.1f} us  {e.name[:110]}\n")
     sampler = ClockSampler(visible_gpu_index(local_rank))
     sampler.start()
     eng.on, eng.launches = True, 0
@@ -256,6 +303,12 @@ def run_ours(args, rank, local_rank, world):
 
     if rank != 0:
         return
+    if args.trace:
+        rows = [("forward (contraction + reductions)", eng.ev["fwd"]), ("backward side (avg of both)", eng.ev["bwd"])] + list(trace.items())
+        print(f"--- device time per step, rank 0, N={n_global} world={world} ---", file=sys.stderr)
+        for nm, evs in rows:
+            tot = sum(e0.elapsed_time(e1) for e0, e1 in evs) / args.steps
+            print(f"{nm:40s} {len(evs) / args.steps:5.1f} calls/step {tot:8.3f} ms/step", file=sys.stderr)
     ms_step = ms_total / args.steps
     value = n_global / (ms_step * 1e-3)
     e2e_value = n_global / (ms_e2e / args.steps * 1e-3)
@@ -283,7 +336,7 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_local * d * 2, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "tc::clip_tc_kernel<1,64> (backward side)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "pair::bwd_kernel (one backward side: logits recompute + gradient GEMM, cta_group::2)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "peak_kind": f"{peaks['src']} sustained bf16 cuBLAS", "frac_of_burst": achieved / peaks["burst"],
                      "ms_per_launch": t_bwd, "fwd_ms_per_launch": t_fwd,
@@ -297,6 +350,7 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -306,6 +360,8 @@ def main():
     ap.add_argument("--d", type=int, default=512)
     ap.add_argument("--ref-rows", type=int, default=1024, help="row block of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write a kernel timeline of three steps (torch.profiler) to this file")
+    ap.add_argument("--trace", action="store_true", help="print a per-phase device-time breakdown of the step to stderr")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

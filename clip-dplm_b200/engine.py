@@ -49,6 +49,11 @@ class CudaEngine:
     def uses_tensor_cores(self, dtype, d, scale, flags=0):
         return bool(self.lib.clipnce_uses_tensor_cores(_DT[dtype], d, float(scale), flags))
 
+    def fixed_shift(self, dtype, d, scale, flags=0):
+        """True when forward() returns col_m == row_m == scale (the tensor-core kernels' fixed shift): partial sums of
+        different ranks then add up directly, no max exchange needed."""
+        return self.uses_tensor_cores(dtype, d, scale, flags)
+
     def needs_transposed(self, dtype, d, scale, flags=0):
         return bool(self.lib.clipnce_needs_transposed(_DT[dtype], d, float(scale), flags))
 
@@ -103,7 +108,7 @@ class CudaEngine:
         row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
         col_m = torch.empty(n_cols, dtype=torch.float32, device=dev)
         col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
-        diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+        diag = torch.empty(n_rows, dtype=torch.float32, device=dev)   # every row's positive column exists: all written
         _lib.check(self.lib.clipnce_forward(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n_rows, n_cols, d, int(diag_offset),
                                             float(scale), _DT[x.dtype], flags, _p(row_m), _p(row_l), _p(col_m),
                                             _p(col_l), _p(diag), _p(ws), ws.numel(), _stream()), "forward")

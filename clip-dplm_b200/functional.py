@@ -29,17 +29,27 @@ def _scale_value(logit_scale, scale_is_log: bool, clamp_max: Optional[float]):
 
 class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, logit_scale, extra, symmetric, scale_is_log, clamp_max, group, compute_dtype, flags, engine):
-        t, s, clamped = _scale_value(logit_scale, scale_is_log, clamp_max)
+    def forward(ctx, a, b, logit_scale, extra, symmetric, scale_is_log, clamp_max, group, compute_dtype, flags, engine,
+                want_stats=True):
         need_grad = a.requires_grad or b.requires_grad or (torch.is_tensor(logit_scale) and logit_scale.requires_grad)
-        loss, st = _step.contrastive_forward(engine, a.detach().contiguous(), b.detach().contiguous(), s,
+        info = {}
+
+        def scale_now():   # called by the step after the scale-independent kernels and the all-gather are enqueued
+            info["v"] = _scale_value(logit_scale, scale_is_log, clamp_max)
+            return info["v"][1]
+
+        loss, st = _step.contrastive_forward(engine, a.detach().contiguous(), b.detach().contiguous(), scale_now,
                                              symmetric=symmetric, extra=extra, group=group,
                                              compute_dtype=compute_dtype, flags=flags, need_grad=need_grad)
+        t, s, clamped = info["v"]
         ctx.st, ctx.engine = st, engine
         ctx.scale_info = (s, clamped, scale_is_log)
         ctx.ls_meta = (logit_scale.dtype, logit_scale.device) if torch.is_tensor(logit_scale) else None
-        row_lse = engine.combine_lse(st.row_m, st.row_l)
-        col_lse = engine.combine_lse(st.col_m, st.col_l)
+        if want_stats:
+            row_lse = engine.combine_lse(st.row_m, st.row_l)
+            col_lse = engine.combine_lse(st.col_m, st.col_l)
+        else:   # two launches nobody reads
+            row_lse = col_lse = st.diag
         ctx.mark_non_differentiable(row_lse, col_lse, st.diag)
         return loss.reshape(()), row_lse, col_lse, st.diag
 
@@ -58,7 +68,7 @@ class _FusedClipLoss(torch.autograd.Function):
                 coef = 1.0 if scale_is_log else 1.0 / s
                 d_ls = (ds * g * coef).reshape(()).to(device=ctx.ls_meta[1], dtype=ctx.ls_meta[0])
         ctx.st = None
-        return da, db, d_ls, None, None, None, None, None, None, None, None
+        return da, db, d_ls, None, None, None, None, None, None, None, None, None
 
 
 def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: bool = True,
@@ -90,7 +100,7 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
     if extra_cols is not None and not extra_normalized:
         flags |= _step.FLAG_FORCE_EXACT
     loss, row_lse, col_lse, diag = _FusedClipLoss.apply(a, b, logit_scale, extra_cols, symmetric, scale_is_log,
-                                                        clamp_max, group, compute_dtype, flags, engine)
+                                                        clamp_max, group, compute_dtype, flags, engine, bool(return_stats))
     if return_stats:
         return loss, {"row_lse": row_lse, "col_lse": col_lse, "diag": diag}
     return loss

@@ -38,17 +38,20 @@ def _all_gather_rows(x, group):
     return out
 
 
-def _reduce_scatter_rows(x, group):
+def _reduce_scatter_rows(x, group, async_op=False):
+    """-> (out [n/world, ...], work or None).  With ``async_op`` the NCCL kernel runs on the communicator's own stream
+    behind everything already enqueued; the caller keeps launching compute and calls ``work.wait()`` (a stream wait,
+    not a host wait) before consuming ``out``."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = x.shape[0] // world
     if dist.get_backend(group) == "gloo":
         y = x.clone()
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
-        return y[rank * n:(rank + 1) * n].contiguous()
+        return y[rank * n:(rank + 1) * n].contiguous(), None
     out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
-    return out
+    work = dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return out, (work if async_op else None)
 
 
 @dataclass
@@ -76,9 +79,13 @@ class StepState:
     group: object
 
 
-def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra=None, group=None,
+def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, group=None,
                         compute_dtype=torch.bfloat16, flags=0, need_grad=True):
-    """Returns (loss [1] f32 -- the GLOBAL mean loss, identical on every rank --, StepState)."""
+    """Returns (loss [1] f32 -- the GLOBAL mean loss, identical on every rank --, StepState).
+
+    ``scale`` is s as a float, or a zero-argument callable returning it: the callable is invoked only after the
+    scale-independent work (row norms, the all-gather) has been enqueued, so that a host read of the logit_scale
+    parameter overlaps with it instead of leaving the GPU idle."""
     if a.dim() != 2 or b.dim() != 2 or a.shape != b.shape:
         raise ValueError(f"expected two [N,d] embedding matrices of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
     n_local = a.shape[0]
@@ -87,16 +94,24 @@ def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra=Non
     n_global = n_local * world
     diag_offset = rank * n_local
 
-    tc = engine.uses_tensor_cores(compute_dtype, a.shape[1], scale, flags)
-    want_t = need_grad and tc and engine.needs_transposed(compute_dtype, a.shape[1], scale, flags)
     rinv_a, _ = engine.normalize(a)
     rinv_b, _ = engine.normalize(b)
-    a_c, a_c_t = engine.stage(a, compute_dtype, want_t=want_t)
-    b_c, b_c_t = engine.stage(b, compute_dtype, want_t=want_t and world == 1 and extra is None)
-    y, y_t, rinv_y = b_c, b_c_t, rinv_b
+    a_c, _ = engine.stage(a, compute_dtype)
+    b_c, _ = engine.stage(b, compute_dtype)
+    y, rinv_y = b_c, rinv_b
     if world > 1:
         y = _all_gather_rows(b_c, group)
         rinv_y = _all_gather_rows(rinv_b, group)
+    if callable(scale):
+        scale = scale()
+    tc = engine.uses_tensor_cores(compute_dtype, a.shape[1], scale, flags)
+    want_t = need_grad and tc and engine.needs_transposed(compute_dtype, a.shape[1], scale, flags)
+    a_c_t = b_c_t = None
+    if want_t:
+        _, a_c_t = engine.stage(a_c, compute_dtype, want_t=True)
+        if world == 1 and extra is None:
+            _, b_c_t = engine.stage(b_c, compute_dtype, want_t=True)
+    y_t = b_c_t
     if extra is not None:   # used as stored (old/clip_opt.py:118-121, tong/utils/losses.py:10-11): rinv = 1
         y = torch.cat([y, extra.detach().to(compute_dtype)], dim=0).contiguous()
         rinv_y = torch.cat([rinv_y, torch.ones(extra.shape[0], dtype=rinv_y.dtype, device=rinv_y.device)])
@@ -105,11 +120,16 @@ def contrastive_forward(engine, a, b, scale: float, *, symmetric=True, extra=Non
 
     row_m, row_l, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags)
     if world > 1:
-        m_max = col_m.clone()
-        dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=group)
-        col_l = col_l * torch.exp(col_m - m_max)
-        dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=group)
-        col_m = m_max
+        fixed = getattr(engine, "fixed_shift", None)
+        if fixed is not None and fixed(compute_dtype, a.shape[1], scale, flags):
+            # tensor-core kernels: every partial sum already shares the fixed shift col_m == s on every rank
+            dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=group)
+        else:
+            m_max = col_m.clone()
+            dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=group)
+            col_l = col_l * torch.exp(col_m - m_max)
+            dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=group)
+            col_m = m_max
     if y.shape[0] > n_global:
         col_l[n_global:] = float("inf")   # extra negatives carry no positives: no column loss, no column soft-max
     loss = engine.loss(row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric)
@@ -134,18 +154,27 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
         col_m, col_w = st.col_m, torch.zeros_like(st.col_l)
     diag_w = 1.0 / n_glob
 
-    # side 1: local rows x all columns -> dA_hat (complete) and sum G.S over the local row block
-    da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, st.diag_offset, st.scale, st.row_m, row_w,
-                                 col_m, col_w, diag_w, 1.0, st.flags, want_dscale=True)
-    # side 2: the positive-carrying columns as rows x local rows as columns -> partial dB_hat [N,d]
+    # side B first: the positive-carrying columns as rows x local rows as columns -> partial dB_hat [N,d]; its
+    # reduce-scatter over NVLink then runs behind side A's contraction instead of after it
     db_part, _ = engine.backward(st.y[:n_glob], st.a_c, st.a_c_t, st.rinv_y[:n_glob].contiguous(), st.rinv_a,
                                  -st.diag_offset, st.scale, col_m[:n_glob].contiguous(), col_w[:n_glob].contiguous(),
                                  st.row_m, row_w, diag_w, 1.0, st.flags, want_dscale=False)
+    rs_work = None
     if world > 1:
-        db_hat = _reduce_scatter_rows(db_part, st.group)
-        dist.all_reduce(ds, op=dist.ReduceOp.SUM, group=st.group)
+        db_hat, rs_work = _reduce_scatter_rows(db_part, st.group, async_op=True)
     else:
         db_hat = db_part
+    # side A: local rows x all columns -> dA_hat (complete) and sum G.S over the local row block
+    da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, st.diag_offset, st.scale, st.row_m, row_w,
+                                 col_m, col_w, diag_w, 1.0, st.flags, want_dscale=True)
+    ds_work = None
+    if world > 1:   # the scalar's all-reduce (which also absorbs the ranks' skew) runs behind the normalise backward
+        nccl = dist.get_backend(st.group) != "gloo"
+        ds_work = dist.all_reduce(ds, op=dist.ReduceOp.SUM, group=st.group, async_op=nccl)
     da = engine.normalize_backward(st.a, st.rinv_a, da_hat, grad_dtype_a or st.a.dtype, grad_scale)
+    if rs_work is not None:
+        rs_work.wait()
     db = engine.normalize_backward(st.b, st.rinv_b, db_hat, grad_dtype_b or st.b.dtype, grad_scale)
+    if ds_work is not None and hasattr(ds_work, "wait"):
+        ds_work.wait()
     return da, db, ds
