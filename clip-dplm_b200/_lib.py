@@ -33,9 +33,9 @@ SIGNATURES = {
     "clipnce_workspace_bytes": [_i64, _i64, _i64, _int, _int, ctypes.POINTER(_sz)],
     "clipnce_normalize": [_vp, _int, _i64, _i64, _vp, _vp, _int, _vp],
     "clipnce_stage_operand": [_vp, _int, _i64, _i64, _vp, _vp, _i64, _int, _vp],
-    "clipnce_forward": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
-                        _vp],
-    "clipnce_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _f32, _f32,
+    "clipnce_forward": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+                        _sz, _vp],
+    "clipnce_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                          _int, _int, _vp, _vp, _vp, _sz, _vp],
     "clipnce_softmax_weights": [_vp, _i64, _f32, _vp, _vp],
     "clipnce_combine_lse": [_vp, _vp, _i64, _vp, _vp],
@@ -77,7 +77,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError here == header/library mismatch
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if lib.clipnce_version() != 100:
+        if lib.clipnce_version() != 101:
             raise RuntimeError("clip_dplm_b200: libclipnce.so version mismatch; rebuild")
         _lib = lib
         return lib

@@ -329,7 +329,8 @@ int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, voi
 }
 
 int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
-                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, int dtype, int flags, float* row_m,
+                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* scale_dev, int dtype,
+                    int flags, float* row_m,
                     float* row_l, float* col_m, float* col_l, float* diag, void* workspace, size_t workspace_bytes,
                     void* stream) {
   if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_l || !col_m || !col_l || !diag || !workspace)
@@ -350,7 +351,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       memset(&p, 0, sizeof p);
       p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
       p.nkc = (int)ceil_div(d, 64); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
-      p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E;
+      p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev;
       p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.diag = diag;
       p.n_pairs = (int)ceil_div(n_rows, 2 * rows);
       p.split_steps = pick_split_steps(p.n_pairs, p.n_steps, pair::MAX_SPLIT);
@@ -365,9 +366,9 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       rc = rows == 128 ? launch_pair_fwd<128>(4, x, y, p, st) : launch_pair_fwd<64>(5, x, y, p, st);
       if (rc) return rc;
       aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, n_part, p.col_ld, n_cols, scale,
-                                                                                  col_m, col_l);
+                                                                                  scale_dev, col_m, col_l);
       aux::reduce_col_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(p.row_part, n_split, n_rows, n_rows, scale,
-                                                                                  row_m, row_l);
+                                                                                  scale_dev, row_m, row_l);
       CUDA_TRY(cudaGetLastError());
       return 0;
     }
@@ -383,14 +384,14 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
     memset(&p, 0, sizeof p);
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
-    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
+    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E; p.scale_dev = scale_dev;
     p.rinv_x = rinv_x; p.rinv_y = rinv_y;
     p.row_m = row_m; p.row_l = row_l; p.col_part = reinterpret_cast<float*>(workspace); p.col_ld = col_ld; p.diag = diag;
     if (bi == 128) rc = launch_tc<0, 128>(0, tx, ty, ty, p, (int)n_ib, st);
     else           rc = launch_tc<0, 64>(1, tx, ty, ty, p, (int)n_ib, st);
     if (rc) return rc;
     aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, (int)((bi / 32) * n_ib), col_ld,
-                                                                                n_cols, scale, col_m, col_l);
+                                                                                n_cols, scale, scale_dev, col_m, col_l);
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
@@ -402,12 +403,12 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
   dim3 grid((unsigned)w.n_jt, (unsigned)w.n_it);
   if (dtype == CLIPNCE_BF16)
     simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y,
-                                                     n_rows, n_cols, (int)d, diag_offset, scale, w.row_pm, w.row_pl,
-                                                     w.col_pm, w.col_pl, diag);
+                                                     n_rows, n_cols, (int)d, diag_offset, scale, scale_dev, w.row_pm,
+                                                     w.row_pl, w.col_pm, w.col_pl, diag);
   else
     simt::fwd_stats<<<grid, simt::THREADS, 0, st>>>((const float*)x, (const float*)y, rinv_x, rinv_y, n_rows, n_cols,
-                                                     (int)d, diag_offset, scale, w.row_pm, w.row_pl, w.col_pm, w.col_pl,
-                                                     diag);
+                                                     (int)d, diag_offset, scale, scale_dev, w.row_pm, w.row_pl, w.col_pm,
+                                                     w.col_pl, diag);
   CUDA_TRY(cudaGetLastError());
   aux::reduce_ml_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(w.row_pm, w.row_pl, (int)w.n_jt, n_rows,
                                                                              n_rows, row_m, row_l);
@@ -419,7 +420,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
 
 int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
                      const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
-                     const float* row_m, const float* row_w, const float* col_m, const float* col_w, float diag_w,
+                     const float* scale_dev, const float* row_m, const float* row_w, const float* col_m, const float* col_w, float diag_w,
                      float grad_out, int dtype, int flags, float* dx_hat, float* d_scale_sum, void* workspace,
                      size_t workspace_bytes, void* stream) {
   if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !dx_hat || !workspace)
@@ -441,7 +442,7 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     memset(&p, 0, sizeof p);
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq2 = (int)ceil_div(d, 256); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
-    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * pair::LOG2E; p.diag_w = diag_w; p.out_scale = grad_out * scale;
+    p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev; p.diag_w = diag_w; p.grad_out = grad_out;
     p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m_in = row_m; p.row_w = row_w; p.col_m_in = col_m; p.col_w = col_w;
     p.n_pairs = (int)ceil_div(n_rows, 2 * pair::BWD_ROWS);
     // split the column sweep only where the row blocks alone leave SMs idle (few local rows: the row-sharded step),
@@ -490,7 +491,7 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     memset(&p, 0, sizeof p);
     p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
     p.nkc = (int)ceil_div(d, 64); p.nq = (int)ceil_div(d, 128); p.n_jt = (int)ceil_div(n_cols, tc::BLOCK_J);
-    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E;
+    p.diag_offset = diag_offset; p.scale = scale; p.k2 = scale * tc::LOG2E; p.scale_dev = scale_dev; p.grad_out = grad_out;
     p.rinv_x = rinv_x; p.rinv_y = rinv_y;
     p.row_m_in = row_m; p.row_w = row_w; p.col_m_in = col_m; p.col_w = col_w; p.diag_w = diag_w; p.out_scale = grad_out * scale;
     p.dx = dx_hat; p.ds_part = d_scale_sum ? reinterpret_cast<float*>(workspace) : nullptr;
@@ -512,11 +513,11 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
   dim3 grid((unsigned)ceil_div(d, simt::TILE), (unsigned)n_it);
   if (dtype == CLIPNCE_BF16)
     simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y,
-                                                    n_rows, n_cols, (int)d, diag_offset, scale, row_m, row_w, col_m, col_w,
-                                                    diag_w, grad_out * scale, dx_hat, ds_part);
+                                                    n_rows, n_cols, (int)d, diag_offset, scale, scale_dev, row_m, row_w, col_m,
+                                                    col_w, diag_w, grad_out * scale, dx_hat, ds_part);
   else
     simt::bwd_side<<<grid, simt::THREADS, 0, st>>>((const float*)x, (const float*)y, rinv_x, rinv_y, n_rows, n_cols,
-                                                    (int)d, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w,
+                                                    (int)d, diag_offset, scale, scale_dev, row_m, row_w, col_m, col_w, diag_w,
                                                     grad_out * scale, dx_hat, ds_part);
   CUDA_TRY(cudaGetLastError());
   if (d_scale_sum) {

@@ -129,9 +129,11 @@ __global__ void loss_reduce(const float* __restrict__ row_m, const float* __rest
 // col_l[j] = sum_p part[p][j] (fixed order), col_m[j] = shift.   Used by the tensor-core forward
 // whose partials all share the fixed shift s.
 __global__ void reduce_col_partials(const float* __restrict__ part, int n_part, int64_t ld, int64_t n_cols, float shift,
-                                    float* __restrict__ col_m, float* __restrict__ col_l) {
+                                    const float* __restrict__ shift_dev, float* __restrict__ col_m,
+                                    float* __restrict__ col_l) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_cols) return;
+  if (shift_dev != nullptr) shift = __ldg(shift_dev);
   float acc = 0.f;
   for (int p = 0; p < n_part; ++p) acc += part[(int64_t)p * ld + j];
   col_m[j] = shift;

@@ -76,7 +76,8 @@ struct BwdParams {
   int n_pairs;      // row blocks
   int split_steps;  // steps per work item (column-sweep split, see FwdParams); item s accumulates into dx + s n_rows d
   long long diag_offset;
-  float scale, k2, diag_w, out_scale;
+  float scale, diag_w, grad_out;
+  const float* scale_dev;  // optional DEVICE scalar s: read instead of `scale` (no host read of the logit scale per step)
   const float* rinv_x;
   const float* rinv_y;
   const float* row_m_in;
@@ -119,6 +120,9 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
   float* const colv = reinterpret_cast<float*>(smem + small_off + 1024);   // [2][3][256]
 
   const int S_COL0 = TMEM_COLS - 128 * p.nsbuf;
+  const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;   // s
+  const float k2 = sc * LOG2E;                                                // s log2(e)
+  const float out_scale = p.grad_out * sc;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
@@ -271,7 +275,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float rx = row_ok ? p.rinv_x[i_glob] : 0.f;
     // u_i = row_w_i exp(s - row_m_i): exp(S - s) u_i = exp(S - row_m_i) row_w_i from ONE ex2 per logit
-    const float u = row_ok ? p.row_w[i_glob] * ex2((p.scale - p.row_m_in[i_glob]) * LOG2E) : 0.f;
+    const float u = row_ok ? p.row_w[i_glob] * ex2((sc - p.row_m_in[i_glob]) * LOG2E) : 0.f;
     const uint32_t g_row = g_smem + kc * 8192 + (i_local >> 3) * 1024 + (i_local & 7) * 128;
     const uint32_t sw = i_local & 7;
     const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
@@ -282,7 +286,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       const long long jn = (long long)(t_begin + t) * STEP_J + te;
       const bool ok = t < n_t && jn < p.n_cols;
       cw = (ok && p.col_w != nullptr) ? p.col_w[jn] : 0.f;
-      cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : p.scale;
+      cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : sc;
       ry = ok ? p.rinv_y[jn] : 0.f;
     };
     float cw_n, cm_n, ry_n;
@@ -292,8 +296,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       const int sb = t % p.nsbuf;
       float* const cv = colv + (t & 1) * 768;
       {
-        const float vj = cw_n * ex2((p.scale - cm_n) * LOG2E);
-        cv[te] = ry_n * p.k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
+        const float vj = cw_n * ex2((sc - cm_n) * LOG2E);
+        cv[te] = ry_n * k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
         cv[256 + te] = vj * ry_n;      // G is contracted against the RAW y_j -> fold rinv_y[j] into it
         cv[512 + te] = ry_n;
       }
@@ -328,7 +332,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
 #pragma unroll
           for (int xx = 0; xx < 4; ++xx) {
             const float y = __uint_as_float(r[4 * x4 + xx]) * rx;
-            const float ev = ex2(fmaf(y, cjv[xx], -p.k2));              // exp(S_ij - s)
+            const float ev = ex2(fmaf(y, cjv[xx], -k2));              // exp(S_ij - s)
             g[xx] = ev * fmaf(u, ryv[xx], vrv[xx]);                     // (u_i + v_j) rinv_y[j]
           }
           if (has_diag) {
@@ -368,8 +372,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
 #pragma unroll
             for (int x4 = 0; x4 < 8; ++x4)
               *reinterpret_cast<float4*>(dst + 4 * x4) =
-                  make_float4(__uint_as_float(r[4 * x4]) * p.out_scale, __uint_as_float(r[4 * x4 + 1]) * p.out_scale,
-                              __uint_as_float(r[4 * x4 + 2]) * p.out_scale, __uint_as_float(r[4 * x4 + 3]) * p.out_scale);
+                  make_float4(__uint_as_float(r[4 * x4]) * out_scale, __uint_as_float(r[4 * x4 + 1]) * out_scale,
+                              __uint_as_float(r[4 * x4 + 2]) * out_scale, __uint_as_float(r[4 * x4 + 3]) * out_scale);
           }
         }
       }
@@ -395,7 +399,8 @@ struct FwdParams {
   int split_steps;    // steps per work item: the column sweep is cut into ceil(n_steps / split_steps) work items per
                       // row block so that the grid fills whole waves of CTA pairs
   long long diag_offset;
-  float scale, k2;
+  float scale;
+  const float* scale_dev;  // optional DEVICE scalar s (see BwdParams)
   const float* rinv_x;
   const float* rinv_y;
   float* row_part;    // [n_split][n_rows] partial sum_j exp(S_ij - s) over the item's columns
@@ -434,6 +439,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
   const int t_begin = split * p.split_steps;
   const int t_end = min(p.n_steps, t_begin + p.split_steps);
   const int col_row = 2 * (item % p.n_pairs) + (int)rank;   // this CTA's row of the column-partial matrix
+  const float k2 = (p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale) * LOG2E;
 
   const uint32_t x_smem = base;
   const uint32_t ring_a = x_smem + p.nkc * X_CHUNK;
@@ -556,8 +562,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
       const int sb = tl & 1;
       float* const cv = colv + (tl & 1) * 512;
       if (te < STEP_J) {
-        cv[te] = ry_n < 0.f ? 0.f : ry_n * p.k2;
-        cv[256 + te] = ry_n < 0.f ? -10000.f : -p.k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
+        cv[te] = ry_n < 0.f ? 0.f : ry_n * k2;
+        cv[256 + te] = ry_n < 0.f ? -10000.f : -k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
         const long long jn = (long long)(t + 1) * STEP_J + te;
         ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
       }

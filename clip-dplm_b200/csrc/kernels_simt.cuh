@@ -71,13 +71,14 @@ __device__ __forceinline__ void logits_tile(const T* __restrict__ x, const T* __
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
 fwd_stats(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ rinv_x,
-          const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, float* __restrict__ row_pm, float* __restrict__ row_pl,
+          const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, const float* __restrict__ scale_dev, float* __restrict__ row_pm, float* __restrict__ row_pl,
           float* __restrict__ col_pm, float* __restrict__ col_pl, float* __restrict__ diag) {
   __shared__ float Xs[KT][TILE + 1];
   __shared__ float Ys[KT][TILE + 1];
   __shared__ float St[TILE][TILE + 1];
   const int64_t j0 = (int64_t)blockIdx.x * TILE, i0 = (int64_t)blockIdx.y * TILE;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);   // device-resident s (no host read per step)
   float s[4][4];
   logits_tile<T>(x, y, rinv_x, rinv_y, n_rows, n_cols, d, i0, j0, scale, s, Xs, Ys);
 #pragma unroll
@@ -121,7 +122,7 @@ fwd_stats(const T* __restrict__ x, const T* __restrict__ y, const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
 bwd_side(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ rinv_x,
-         const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, const float* __restrict__ row_m, const float* __restrict__ row_w,
+         const float* __restrict__ rinv_y, int64_t n_rows, int64_t n_cols, int d, int64_t diag_offset, float scale, const float* __restrict__ scale_dev, const float* __restrict__ row_m, const float* __restrict__ row_w,
          const float* __restrict__ col_m, const float* __restrict__ col_w, float diag_w, float out_scale, float* __restrict__ dx, float* __restrict__ ds_part) {
   __shared__ float Xs[KT][TILE + 1];
   __shared__ float Ys[KT][TILE + 1];
@@ -131,6 +132,11 @@ bwd_side(const T* __restrict__ x, const T* __restrict__ y, const float* __restri
   const int64_t i0 = (int64_t)blockIdx.y * TILE;
   const int dd0 = blockIdx.x * TILE;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (scale_dev != nullptr) {   // out_scale was formed with the host's hint of s: swap in the device value
+    const float sd = __ldg(scale_dev);
+    out_scale = out_scale / scale * sd;
+    scale = sd;
+  }
   float rm[4], rw[4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {

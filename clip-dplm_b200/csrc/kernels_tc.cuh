@@ -66,7 +66,9 @@ struct Params {
   int stages_b;    // ring B: streamed Y^T boxes for the gradient MMA (MODE 1)
   long long diag_offset;
   float scale;     // s
-  float k2;        // s * log2(e)
+  float k2;        // s * log2(e)   (host copies; the kernel recomputes both when scale_dev is set)
+  const float* scale_dev;   // optional DEVICE scalar s
+  float grad_out;
   const float* rinv_x;   // [n_rows]  1 / |x_i|   (the normalise, applied to the fp32 accumulator)
   const float* rinv_y;   // [n_cols]
   // MODE 0 outputs
@@ -175,6 +177,9 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const int warp = threadIdx.x >> 5;   // warp-uniform
   const int lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * BLOCK_I;
+  const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;
+  const float k2 = sc * LOG2E;
+  const float out_scale = p.scale_dev != nullptr ? p.grad_out * sc : p.out_scale;
   const int nga = p.nkc;                             // ring-A boxes per tile (K chunks of the logits MMA)
   const int ngb = 2 * p.nq;                          // ring-B boxes per tile ((d chunk, j half) of the gradient MMA)
 
@@ -335,7 +340,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       rx_s[te] = (te < i_valid) ? p.rinv_x[i0 + te] : 0.f;
       // u_i = row_w_i exp(s - row_m_i): exp(S - s) u_i = exp(S - row_m_i) row_w_i from ONE ex2 per logit
       // (row_m_i == s when the statistics come from the MODE 0 kernel, so u_i = row_w_i exactly)
-      if (MODE == 1) u_s[te] = (te < i_valid) ? p.row_w[i0 + te] * ex2((p.scale - p.row_m_in[i0 + te]) * LOG2E) : 0.f;
+      if (MODE == 1) u_s[te] = (te < i_valid) ? p.row_w[i0 + te] * ex2((sc - p.row_m_in[i0 + te]) * LOG2E) : 0.f;
     }
     epi_bar_sync<NUM_EPI_WARPS * 32>();
 
@@ -354,7 +359,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
         const float ryj = ry_n;
         ry_n = (t + 1 < p.n_jt && jg + BLOCK_J < p.n_cols) ? p.rinv_y[jg + BLOCK_J] : 0.f;
-        const float cj = ryj * p.k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
+        const float cj = ryj * k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
         ptx::mbar_wait(bar(B_SFULL + b), (t >> 1) & 1);
         ptx::tc_fence_after();
         uint32_t r[32];
@@ -373,7 +378,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
               for (int xx = 0; xx < 4; ++xx) {
                 const int x = x4 * 4 + xx;
-                const float xv = fmaf(__uint_as_float(r[x]) * rxv[xx], cj, -p.k2);
+                const float xv = fmaf(__uint_as_float(r[x]) * rxv[xx], cj, -k2);
                 const float ev = (xx == 0) ? ex2(xv) : ex2_poly(xv);     // 1 in 4 on the MUFU
                 racc[x] += ev;
                 cs[xx] += ev;
@@ -382,7 +387,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           } else {
 #pragma unroll
             for (int x = 0; x < 32; ++x) {
-              const float ev = (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]) * rx_s[ibase + x], cj, -p.k2)) : 0.f;
+              const float ev = (ibase + x < i_valid) ? ex2(fmaf(__uint_as_float(r[x]) * rx_s[ibase + x], cj, -k2)) : 0.f;
               racc[x] += ev;
               cs[x & 3] += ev;
             }
@@ -392,7 +397,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
             for (int x = 0; x < 32; ++x)
               if (id == x && ibase + x < i_valid)
-                p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * rx_s[ibase + x] * ryj * p.scale;
+                p.diag[i0 + ibase + x] = __uint_as_float(r[x]) * rx_s[ibase + x] * ryj * sc;
           }
           p.col_part[(long long)(blockIdx.x * (BLOCK_I / 32) + cg) * p.col_ld + jg] = (cs[0] + cs[1]) + (cs[2] + cs[3]);
         }
@@ -406,7 +411,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const float tot = (red[(cgi * 4 + 0) * 32 + ii] + red[(cgi * 4 + 1) * 32 + ii]) +
                           (red[(cgi * 4 + 2) * 32 + ii] + red[(cgi * 4 + 3) * 32 + ii]);
         if (te < i_valid) {
-          p.row_m[i0 + te] = p.scale;
+          p.row_m[i0 + te] = sc;
           p.row_l[i0 + te] = tot;
         }
       }
@@ -428,7 +433,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const long long jn = (long long)t * BLOCK_J + j_local;
         const bool ok = t < p.n_jt && jn < p.n_cols;
         cw = (ok && p.col_w != nullptr) ? p.col_w[jn] : 0.f;
-        cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : p.scale;
+        cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : sc;
         ry = ok ? p.rinv_y[jn] : 0.f;
       };
       float cw_n, cm_n, ry_n;
@@ -437,9 +442,9 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int sb = t % NSBUF, gb = t & 1;
         const long long jg = (long long)t * BLOCK_J + j_local;
         const bool jvalid = jg < p.n_cols;
-        const float vj = cw_n * ex2((p.scale - cm_n) * LOG2E);
+        const float vj = cw_n * ex2((sc - cm_n) * LOG2E);
         const float ryj = ry_n;
-        const float cj = ryj * p.k2;
+        const float cj = ryj * k2;
         load_col(t + 1, cw_n, cm_n, ry_n);
         const bool diag_tile = dcol0 < (long long)(t + 1) * BLOCK_J && dcol0 + BLOCK_I > (long long)t * BLOCK_J;
         const bool plain = (i_valid == BLOCK_I) && !diag_tile && (long long)(t + 1) * BLOCK_J <= p.n_cols;  // warp-uniform
@@ -469,7 +474,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               for (int xx = 0; xx < 4; ++xx) {
                 const int x = x4 * 4 + xx;
                 const float y = __uint_as_float(r[gq][x]) * rxv[xx] * cj;      // S_ij * log2(e)
-                const float ev = (xx == 0) ? ex2(y - p.k2) : ex2_poly(y - p.k2);   // 1 in 4 on the MUFU
+                const float ev = (xx == 0) ? ex2(y - k2) : ex2_poly(y - k2);   // 1 in 4 on the MUFU
                 g[x] = ev * (uv[xx] + vj);
                 ds = fmaf(g[x], y, ds);
               }
@@ -479,7 +484,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
             for (int x = 0; x < 16; ++x) {
               const float y = __uint_as_float(r[gq][x]) * rx_h[gq * 16 + x] * cj;
-              float gv = ex2(y - p.k2) * (u_h[gq * 16 + x] + vj);
+              float gv = ex2(y - k2) * (u_h[gq * 16 + x] + vj);
               if (id == x) gv -= p.diag_w;
               if (!(jvalid && h * HALF + gq * 16 + x < i_valid)) gv = 0.f;
               g[x] = gv;
@@ -520,7 +525,7 @@ clip_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
             for (int x = 0; x < 16; ++x) {
               const int i = h * HALF + gq * 16 + x;
-              if (i < i_valid) p.dx[(long long)(i0 + i) * p.d + dd] = __uint_as_float(r[x]) * p.out_scale;
+              if (i < i_valid) p.dx[(long long)(i0 + i) * p.d + dd] = __uint_as_float(r[x]) * out_scale;
             }
           }
         }

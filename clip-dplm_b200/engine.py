@@ -96,8 +96,10 @@ class CudaEngine:
                                                       ld, _DT[c_dtype], _stream()), "stage_operand")
         return xc, xt
 
-    def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0):
-        """-> row_m, row_l [n_rows], col_m, col_l [n_cols], diag [n_rows]   (LSE = m + log l, kept as pairs)"""
+    def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0, scale_dev=None):
+        """-> row_m, row_l [n_rows], col_m, col_l [n_cols], diag [n_rows]   (LSE = m + log l, kept as pairs).
+        ``scale_dev``: optional 1-element f32 CUDA tensor holding s; the kernels then read s on the device and the float
+        ``scale`` only selects the kernel family."""
         self._chk(x, (torch.bfloat16, torch.float32), "x")
         self._chk(y, (x.dtype,), "y")
         n_rows, d = x.shape
@@ -110,12 +112,12 @@ class CudaEngine:
         col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
         diag = torch.empty(n_rows, dtype=torch.float32, device=dev)   # every row's positive column exists: all written
         _lib.check(self.lib.clipnce_forward(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n_rows, n_cols, d, int(diag_offset),
-                                            float(scale), _DT[x.dtype], flags, _p(row_m), _p(row_l), _p(col_m),
+                                            float(scale), _p(scale_dev), _DT[x.dtype], flags, _p(row_m), _p(row_l), _p(col_m),
                                             _p(col_l), _p(diag), _p(ws), ws.numel(), _stream()), "forward")
         return row_m, row_l, col_m, col_l, diag
 
     def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, grad_out,
-                 flags=0, want_dscale=True):
+                 flags=0, want_dscale=True, scale_dev=None):
         """-> dx_hat [n_rows,d] f32, d_scale_sum [1] f32 (or None)"""
         n_rows, d = x.shape
         n_cols = y.shape[0]
@@ -125,7 +127,7 @@ class CudaEngine:
         ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
         ld_t = y_t.shape[1] if y_t is not None else 0
         _lib.check(self.lib.clipnce_backward(_p(x), _p(y), _p(y_t), ld_t, _p(rinv_x), _p(rinv_y), n_rows, n_cols, d,
-                                             int(diag_offset), float(scale), _p(row_m), _p(row_w), _p(col_m), _p(col_w),
+                                             int(diag_offset), float(scale), _p(scale_dev), _p(row_m), _p(row_w), _p(col_m), _p(col_w),
                                              float(diag_w), float(grad_out), _DT[x.dtype], flags, _p(dx), _p(ds),
                                              _p(ws), ws.numel(), _stream()), "backward")
         return dx, ds

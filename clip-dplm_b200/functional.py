@@ -9,6 +9,7 @@ logits never exist in HBM.
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -18,13 +19,46 @@ from .engine import default_engine
 
 
 def _scale_value(logit_scale, scale_is_log: bool, clamp_max: Optional[float]):
-    """Host value of s and whether the clamp is active (d s / d logit_scale = 0 there)."""
-    t = float(logit_scale.detach()) if torch.is_tensor(logit_scale) else float(logit_scale)   # one host read of a 0-d parameter per step (the reference reads loss.item())
+    """Host value of s and whether the clamp is active (python-float logit scales, and the first read of a parameter)."""
+    t = float(logit_scale.detach()) if torch.is_tensor(logit_scale) else float(logit_scale)
     s = math.exp(t) if scale_is_log else t
     clamped = False
     if clamp_max is not None and s > clamp_max:
         s, clamped = float(clamp_max), True
     return t, s, clamped
+
+
+class _ScaleHint:
+    """Host-side, possibly stale copy of a device-resident s.  The kernels read s on the device (``scale_dev``); the host
+    only needs its magnitude to pick the kernel family (tensor-core path while 2 s <= 86).  One blocking read the first
+    time a parameter is seen; afterwards every step enqueues a non-blocking copy into pinned memory and picks up
+    whichever earlier copy has completed -- no host synchronisation in the step (the reference's loop reads
+    ``loss.item()`` every batch; this path does not even need that)."""
+
+    _by_id = {}
+
+    def __init__(self, tensor, s_dev):
+        self.ref = weakref.ref(tensor)
+        self.pinned = torch.empty(1, dtype=torch.float32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.value = float(s_dev)          # the one blocking read
+        self.pending = False
+
+    @classmethod
+    def get(cls, tensor, s_dev):
+        h = cls._by_id.get(id(tensor))
+        if h is None or h.ref() is not tensor:
+            if len(cls._by_id) > 64:
+                cls._by_id = {k: v for k, v in cls._by_id.items() if v.ref() is not None}
+            h = cls(tensor, s_dev)
+            cls._by_id[id(tensor)] = h
+        elif h.pending and h.event.query():
+            h.value, h.pending = float(h.pinned[0]), False
+        if not h.pending and not torch.cuda.is_current_stream_capturing():
+            h.pinned.copy_(s_dev, non_blocking=True)
+            h.event.record()
+            h.pending = True
+        return h.value
 
 
 class _FusedClipLoss(torch.autograd.Function):
@@ -33,17 +67,29 @@ class _FusedClipLoss(torch.autograd.Function):
                 want_stats=True):
         need_grad = a.requires_grad or b.requires_grad or (torch.is_tensor(logit_scale) and logit_scale.requires_grad)
         info = {}
+        s_dev = raw_dev = None
+        if torch.is_tensor(logit_scale) and logit_scale.is_cuda:
+            # s stays on the device: exp / clamp as two tiny kernels, read by the contraction kernels through scale_dev
+            t_dev = logit_scale.detach().to(torch.float32).reshape(1)
+            raw_dev = t_dev.exp() if scale_is_log else t_dev.clone()
+            s_dev = raw_dev.clamp(max=float(clamp_max)) if clamp_max is not None else raw_dev
+            hint = _ScaleHint.get(logit_scale, s_dev) * 1.05   # stale by a step or two at most: keep a margin
+            scale_arg = min(hint, float(clamp_max)) if clamp_max is not None else hint
+        else:
+            def scale_arg():   # called by the step after the scale-independent kernels and the all-gather are enqueued
+                info["v"] = _scale_value(logit_scale, scale_is_log, clamp_max)
+                return info["v"][1]
 
-        def scale_now():   # called by the step after the scale-independent kernels and the all-gather are enqueued
-            info["v"] = _scale_value(logit_scale, scale_is_log, clamp_max)
-            return info["v"][1]
-
-        loss, st = _step.contrastive_forward(engine, a.detach().contiguous(), b.detach().contiguous(), scale_now,
+        loss, st = _step.contrastive_forward(engine, a.detach().contiguous(), b.detach().contiguous(), scale_arg,
                                              symmetric=symmetric, extra=extra, group=group,
-                                             compute_dtype=compute_dtype, flags=flags, need_grad=need_grad)
-        t, s, clamped = info["v"]
+                                             compute_dtype=compute_dtype, flags=flags, need_grad=need_grad,
+                                             scale_dev=s_dev)
         ctx.st, ctx.engine = st, engine
-        ctx.scale_info = (s, clamped, scale_is_log)
+        if s_dev is None:
+            _, s, clamped = info["v"]
+            ctx.scale_info = (s, clamped, scale_is_log, None, None, None)
+        else:
+            ctx.scale_info = (None, None, scale_is_log, s_dev, raw_dev, clamp_max)
         ctx.ls_meta = (logit_scale.dtype, logit_scale.device) if torch.is_tensor(logit_scale) else None
         if want_stats:
             row_lse = engine.combine_lse(st.row_m, st.row_l)
@@ -56,15 +102,20 @@ class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g1, _g2, _g3):
         st, engine = ctx.st, ctx.engine
-        s, clamped, scale_is_log = ctx.scale_info
+        s, clamped, scale_is_log, s_dev, raw_dev, clamp_max = ctx.scale_info
         g = g_loss.reshape(1).to(torch.float32).contiguous()
         da, db, ds = _step.contrastive_backward(engine, st, grad_scale=g)
         d_ls = None
         if ctx.ls_meta is not None and ctx.needs_input_grad[2]:
-            if clamped:
+            # sum G.S = dL/dt for s = exp(t);  dL/ds = sum G.S / s for a raw scale;  0 where the clamp is active
+            if s_dev is not None:
+                d = ds * g if scale_is_log else ds * g / s_dev
+                if clamp_max is not None:
+                    d = torch.where(raw_dev > float(clamp_max), torch.zeros_like(d), d)
+                d_ls = d.reshape(()).to(dtype=ctx.ls_meta[0])
+            elif clamped:
                 d_ls = torch.zeros((), dtype=ctx.ls_meta[0], device=ctx.ls_meta[1])
             else:
-                # sum G.S = dL/dt for s = exp(t);  dL/ds = sum G.S / s for a raw scale
                 coef = 1.0 if scale_is_log else 1.0 / s
                 d_ls = (ds * g * coef).reshape(()).to(device=ctx.ls_meta[1], dtype=ctx.ls_meta[0])
         ctx.st = None

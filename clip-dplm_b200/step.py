@@ -71,6 +71,7 @@ class StepState:
     col_l: torch.Tensor
     diag: torch.Tensor
     scale: float
+    scale_dev: Optional[torch.Tensor]   # device scalar s (the kernels read it; `scale` is then only the host's hint)
     symmetric: bool
     n_local: int
     n_global: int
@@ -80,7 +81,7 @@ class StepState:
 
 
 def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, group=None,
-                        compute_dtype=torch.bfloat16, flags=0, need_grad=True):
+                        compute_dtype=torch.bfloat16, flags=0, need_grad=True, scale_dev=None):
     """Returns (loss [1] f32 -- the GLOBAL mean loss, identical on every rank --, StepState).
 
     ``scale`` is s as a float, or a zero-argument callable returning it: the callable is invoked only after the
@@ -118,7 +119,8 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
     if want_t and y_t is None:
         _, y_t = engine.stage(y, compute_dtype, want_t=True)
 
-    row_m, row_l, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags)
+    kw = {"scale_dev": scale_dev} if scale_dev is not None else {}
+    row_m, row_l, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags, **kw)
     if world > 1:
         fixed = getattr(engine, "fixed_shift", None)
         if fixed is not None and fixed(compute_dtype, a.shape[1], scale, flags):
@@ -136,7 +138,7 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
     if world > 1:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     st = StepState(a, b, a_c, a_c_t, y, y_t, rinv_a, rinv_b, rinv_y, row_m, row_l, col_m, col_l, diag, scale,
-                   symmetric, n_local, n_global, diag_offset, flags, group)
+                   scale_dev, symmetric, n_local, n_global, diag_offset, flags, group)
     return loss, st
 
 
@@ -153,12 +155,13 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     else:
         col_m, col_w = st.col_m, torch.zeros_like(st.col_l)
     diag_w = 1.0 / n_glob
+    kw = {"scale_dev": st.scale_dev} if st.scale_dev is not None else {}
 
     # side B first: the positive-carrying columns as rows x local rows as columns -> partial dB_hat [N,d]; its
     # reduce-scatter over NVLink then runs behind side A's contraction instead of after it
     db_part, _ = engine.backward(st.y[:n_glob], st.a_c, st.a_c_t, st.rinv_y[:n_glob].contiguous(), st.rinv_a,
                                  -st.diag_offset, st.scale, col_m[:n_glob].contiguous(), col_w[:n_glob].contiguous(),
-                                 st.row_m, row_w, diag_w, 1.0, st.flags, want_dscale=False)
+                                 st.row_m, row_w, diag_w, 1.0, st.flags, want_dscale=False, **kw)
     rs_work = None
     if world > 1:
         db_hat, rs_work = _reduce_scatter_rows(db_part, st.group, async_op=True)
@@ -166,7 +169,7 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
         db_hat = db_part
     # side A: local rows x all columns -> dA_hat (complete) and sum G.S over the local row block
     da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, st.diag_offset, st.scale, st.row_m, row_w,
-                                 col_m, col_w, diag_w, 1.0, st.flags, want_dscale=True)
+                                 col_m, col_w, diag_w, 1.0, st.flags, want_dscale=True, **kw)
     ds_work = None
     if world > 1:   # the scalar's all-reduce (which also absorbs the ranks' skew) runs behind the normalise backward
         nccl = dist.get_backend(st.group) != "gloo"

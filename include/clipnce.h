@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 100
+#define CLIPNCE_VERSION 101
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -97,6 +97,9 @@ int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, voi
  * diag_offset   column of row 0's positive: the positive of local row i is column i + diag_offset
  *               (0 on one GPU, rank * n_rows under the row-sharded global batch)
  * scale         s = exp(logit_scale), already clamped by the caller (old/clip_opt.py:100)
+ * scale_dev     optional DEVICE scalar (f32) holding s.  When non-NULL the kernels read s from it and `scale` is only
+ *               the host's (possibly one step old) hint used to pick the kernel family: the step then needs no host
+ *               read of the logit_scale parameter and can be captured in a CUDA graph.  NULL: `scale` is used.
  * Log-sum-exps are returned as (max-like shift m, sum l = sum exp(S - m)) PAIRS and never collapsed
  * to a single float inside the library: r_i = row_m_i + log(row_l_i).  Keeping the pair is what lets the
  * backward form soft-max probabilities as exp(S - m) / l with full fp32 relative accuracy (the way
@@ -109,7 +112,7 @@ int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, voi
  */
 int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
                     int64_t n_rows, int64_t n_cols, int64_t d,
-                    int64_t diag_offset, float scale, int dtype, int flags,
+                    int64_t diag_offset, float scale, const float* scale_dev, int dtype, int flags,
                     float* row_m, float* row_l, float* col_m, float* col_l, float* diag,
                     void* workspace, size_t workspace_bytes, void* stream);
 
@@ -132,6 +135,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
 int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t,
                      const float* rinv_x, const float* rinv_y,
                      int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                     const float* scale_dev,
                      const float* row_m, const float* row_w, const float* col_m, const float* col_w,
                      float diag_w, float grad_out,
                      int dtype, int flags, float* dx_hat, float* d_scale_sum,

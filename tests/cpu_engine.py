@@ -43,7 +43,9 @@ class TorchCpuEngine:
     def _logits(self, x, y, rinv_x, rinv_y, scale):
         return scale * ((x * rinv_x[:, None]) @ (y * rinv_y[:, None]).t())
 
-    def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0):
+    def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0, scale_dev=None):
+        if scale_dev is not None:
+            scale = float(scale_dev)
         S = self._logits(x, y, rinv_x, rinv_y, scale)
         n = x.shape[0]
         row_m = S.max(dim=1).values
@@ -55,7 +57,9 @@ class TorchCpuEngine:
         return row_m, row_l, col_m, col_l, diag
 
     def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, grad_out,
-                 flags=0, want_dscale=True):
+                 flags=0, want_dscale=True, scale_dev=None):
+        if scale_dev is not None:
+            scale = float(scale_dev)
         if y_t is not None:   # the transposed operand must be the same matrix
             assert torch.equal(y_t[:, :y.shape[0]].t(), y)
         S = self._logits(x, y, rinv_x, rinv_y, scale)
