@@ -2,6 +2,7 @@
 
 Public surface
     fused_clip_loss(a, b, logit_scale, ...)      the fused op (autograd-aware, optionally row-sharded)
+    graph.GraphedClipStep                        forward + backward of one fixed shape replayed as a single CUDA graph
     modules.*                                    drop-in modules / loss functions with the reference's signatures
     engine.CudaEngine                            stage-level access to the C-ABI (include/clipnce.h)
 

@@ -47,6 +47,12 @@ class _ScaleHint:
     @classmethod
     def get(cls, tensor, s_dev):
         h = cls._by_id.get(id(tensor))
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture no event query / host read is legal: use the hint of the warm-up steps
+            if h is None or h.ref() is not tensor:
+                raise RuntimeError("fused_clip_loss: run at least one eager step with this logit_scale tensor before "
+                                   "capturing a CUDA graph (the kernel family is chosen from its value)")
+            return h.value
         if h is None or h.ref() is not tensor:
             if len(cls._by_id) > 64:
                 cls._by_id = {k: v for k, v in cls._by_id.items() if v.ref() is not None}
@@ -54,7 +60,7 @@ class _ScaleHint:
             cls._by_id[id(tensor)] = h
         elif h.pending and h.event.query():
             h.value, h.pending = float(h.pinned[0]), False
-        if not h.pending and not torch.cuda.is_current_stream_capturing():
+        if not h.pending:
             h.pinned.copy_(s_dev, non_blocking=True)
             h.event.record()
             h.pending = True

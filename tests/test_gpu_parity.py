@@ -263,3 +263,27 @@ def test_pair_kernels_split_and_ragged(eng, monkeypatch, n, m, d, split):
     assert rel(da, cf["d_a_hat"]) <= GRAD_RTOL_BF16, rel(da, cf["d_a_hat"])
     assert rel(db, cf["d_b_hat"]) <= GRAD_RTOL_BF16, rel(db, cf["d_b_hat"])
     assert abs(float(ds) - cf["d_scale_sum"]) <= 2e-2 * abs(cf["d_scale_sum"]) + 1e-6
+
+
+def test_device_scale_and_graphed_step():
+    """The kernels read s from a device scalar (scale_dev); the host only passes a stale hint.  A CUDA-graph replay of
+    the whole step must follow the logit scale written into its static input, without re-capture."""
+    from clip_dplm_b200 import fused_clip_loss
+    from clip_dplm_b200.graph import GraphedClipStep
+    n, d = 1024, 256
+    a, b = O.make_inputs(n, d, seed=31, mix=0.4)
+    ac, bc = a.cuda().bfloat16(), b.cuda().bfloat16()
+    step = GraphedClipStep(n, d)
+    for ls in (math.log(1 / 0.07), 2.0, 3.2):
+        ref = O.ref_step(a.double(), b.double(), ls)
+        loss, da, db, dt = step(ac, bc, ls)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(ref["loss"])) <= LOSS_RTOL_BF16 * abs(float(ref["loss"]))
+        assert rel(da.float(), ref["d_a"]) <= GRAD_RTOL_BF16 and rel(db.float(), ref["d_b"]) <= GRAD_RTOL_BF16
+        assert abs(float(dt) - float(ref["d_logit_scale"])) <= 2e-2 * abs(float(ref["d_logit_scale"])) + 1e-6
+        # and the eager call agrees bit for bit with the replay (same kernels, same order)
+        t = torch.tensor(ls, device="cuda", requires_grad=True)
+        ar, br = ac.clone().requires_grad_(True), bc.clone().requires_grad_(True)
+        l2 = fused_clip_loss(ar, br, t)
+        l2.backward()
+        assert torch.equal(l2.detach(), loss) and torch.equal(ar.grad, da) and torch.equal(br.grad, db)
