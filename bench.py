@@ -328,10 +328,16 @@ def run_ours(args, rank, local_rank, world):
         ms_total = timed(step_resident, args.steps)
     clocks = sampler.finish()
 
+    feeder = None
+    if gstep is not None:
+        from clip_dplm_b200.graph import HostFedClipStep
+        feeder = HostFedClipStep(inner=gstep)      # shares the already captured graph
+
     def step_e2e_graph():
-        gstep.a.copy_(a_host, non_blocking=True)
-        gstep.b.copy_(b_host, non_blocking=True)
-        loss = gstep.replay()[0]
+        # every step: this batch's embeddings come from pinned host memory (the transfer of the NEXT batch is started
+        # right away so that it overlaps this step's graph), the loss goes back to pinned host memory
+        loss = feeder.step(a_host, b_host)[0]
+        feeder.prefetch(a_host, b_host)
         loss_host.copy_(loss, non_blocking=True)
 
     e2e_fn = step_e2e_graph if gstep is not None else step_e2e

@@ -82,3 +82,56 @@ class GraphedClipStep:
             self.recapture()
         self.graph.replay()
         return self.out
+
+
+class HostFedClipStep:
+    """A `GraphedClipStep` fed from pinned HOST buffers with the copies pipelined: while the graph of step k runs, the
+    embeddings of step k+1 cross PCIe on a copy stream into the other of two staging buffers.
+
+        feeder = HostFedClipStep(n_local, d, group=group)
+        for a_host, b_host in batches:                  # pinned [n_local, d] tensors
+            loss, d_a, d_b, d_t = feeder.step(a_host, b_host)   # results of THIS batch (device tensors)
+
+    `step` enqueues this batch's H2D (unless `prefetch` already did), waits for it on the compute stream, copies the
+    staging buffers into the graph's static inputs (device to device) and replays the graph; call
+    `prefetch(next_a_host, next_b_host)` right after `step` to overlap the next batch's transfer with this step.
+    """
+
+    def __init__(self, n_local: Optional[int] = None, d: Optional[int] = None, *, inner: Optional[GraphedClipStep] = None,
+                 **kw):
+        self.inner = inner if inner is not None else GraphedClipStep(n_local, d, **kw)
+        dev = self.inner.device
+        self.stage = [(torch.empty_like(self.inner.a), torch.empty_like(self.inner.b)) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into stage[i] done
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]      # stage[i] consumed by the compute stream
+        self.slot = 0
+        self.prefetched = False
+        for e in self.free:
+            e.record()
+
+    @property
+    def logit_scale(self):
+        return self.inner.logit_scale
+
+    def prefetch(self, a_host, b_host):
+        """Start the H2D of the NEXT batch (returns immediately)."""
+        i = self.slot
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[i])
+            self.stage[i][0].copy_(a_host, non_blocking=True)
+            self.stage[i][1].copy_(b_host, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.prefetched = True
+
+    def step(self, a_host=None, b_host=None):
+        if not self.prefetched:
+            self.prefetch(a_host, b_host)
+        i = self.slot
+        cur = torch.cuda.current_stream(self.inner.device)
+        cur.wait_event(self.ready[i])
+        self.inner.a.copy_(self.stage[i][0], non_blocking=True)
+        self.inner.b.copy_(self.stage[i][1], non_blocking=True)
+        self.free[i].record(cur)
+        self.slot, self.prefetched = 1 - i, False
+        return self.inner.replay()

@@ -287,3 +287,25 @@ def test_device_scale_and_graphed_step():
         l2 = fused_clip_loss(ar, br, t)
         l2.backward()
         assert torch.equal(l2.detach(), loss) and torch.equal(ar.grad, da) and torch.equal(br.grad, db)
+
+
+def test_host_fed_step_pipelines_batches():
+    """HostFedClipStep: batches from pinned host memory, H2D of batch k+1 overlapped with step k; every step must
+    return the results of ITS batch."""
+    from clip_dplm_b200.graph import GraphedClipStep, HostFedClipStep
+    n, d = 512, 128
+    batches = []
+    for seed in (41, 42, 43):
+        a, b = O.make_inputs(n, d, seed=seed, mix=0.4)
+        batches.append((a.bfloat16().pin_memory(), b.bfloat16().pin_memory()))
+    ref_step = GraphedClipStep(n, d)
+    feeder = HostFedClipStep(n, d)
+    feeder.prefetch(*batches[0])
+    for k, (ah, bh) in enumerate(batches):
+        loss, da, db, dt = feeder.step()
+        if k + 1 < len(batches):
+            feeder.prefetch(*batches[k + 1])
+        got = (loss.clone(), da.clone(), db.clone())
+        want = ref_step(ah.cuda(), bh.cuda(), feeder.logit_scale.detach())
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
