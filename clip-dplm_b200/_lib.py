@@ -40,6 +40,8 @@ SIGNATURES = {
     "clipnce_softmax_weights": [_vp, _i64, _f32, _vp, _vp],
     "clipnce_combine_lse": [_vp, _vp, _i64, _vp, _vp],
     "clipnce_normalize_backward": [_vp, _int, _vp, _vp, _vp, _i64, _i64, _vp, _int, _vp],
+    "clipnce_topk_workspace_bytes": [_i64, _i64, _i64, _int, _int, ctypes.POINTER(_sz)],
+    "clipnce_topk": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp],
     "clipnce_loss": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp],
 }
 _RESTYPES = {"clipnce_last_error": ctypes.c_char_p}

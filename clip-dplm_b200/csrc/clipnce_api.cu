@@ -61,7 +61,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
-bool g_attr_done[8] = {false, false, false, false, false, false, false, false};
+bool g_attr_done[12] = {};
 
 int get_encode(EncodeTiledFn* out) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -161,9 +161,9 @@ int pick_split_steps(int n_pairs, int n_steps, int max_split) {
   return best_sps;
 }
 
-template <int ROWS>
+template <int ROWS, int MODE = 0, int KT = 1>
 int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams p, cudaStream_t st) {
-  auto kern = pair::fwd_kernel<ROWS>;
+  auto kern = pair::fwd_kernel<ROWS, MODE, KT>;
   int stages = (pair::SMEM_LIMIT - pair::fwd_smem_bytes(ROWS, p.nkc, 0)) / pair::STAGE_BYTES;
   if (stages > pair::MAX_STAGES) stages = pair::MAX_STAGES;
   if (stages < 2) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for a TMA ring", p.d);
@@ -524,6 +524,65 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     aux::reduce_scalar_partials<<<1, 32, 0, st>>>(ds_part, (int)n_it, grad_out, d_scale_sum);
     CUDA_TRY(cudaGetLastError());
   }
+  return 0;
+}
+
+namespace {
+int topk_kt(int k) { return k <= 1 ? 1 : (k <= 10 ? 10 : 16); }
+struct TopkPlan {
+  int n_pairs, n_steps, split_steps, n_split, kt;
+  size_t cand_elems;
+};
+int topk_plan(int64_t n_q, int64_t n_lib, int64_t d, int k, int dtype, TopkPlan* pl) {
+  if (n_q < 1 || n_lib < 1 || n_lib >= (1ll << 31) || n_q >= (1ll << 31)) return fail(CLIPNCE_EINVAL, "topk: bad shape");
+  if (dtype != CLIPNCE_BF16 || d % 128 != 0 || d < 128 || d > 512 || k < 1 || k > 16)
+    return fail(CLIPNCE_EUNSUPPORTED, "topk: served for bf16, d in {128,256,384,512}, 1 <= k <= 16 (got dtype %d, d %lld, k %d)",
+                dtype, (long long)d, k);
+  pl->kt = topk_kt(k);
+  pl->n_pairs = (int)ceil_div(n_q, 256);
+  pl->n_steps = (int)ceil_div(n_lib, pair::STEP_J);
+  pl->split_steps = pick_split_steps(pl->n_pairs, pl->n_steps, pair::MAX_SPLIT);
+  pl->n_split = (int)ceil_div(pl->n_steps, pl->split_steps);
+  pl->cand_elems = (size_t)pl->n_split * 4 * (size_t)n_q * (size_t)pl->kt;
+  return 0;
+}
+}  // namespace
+
+int clipnce_topk_workspace_bytes(int64_t n_q, int64_t n_lib, int64_t d, int k, int dtype, size_t* out) {
+  if (!out) return fail(CLIPNCE_EINVAL, "topk_workspace_bytes: null pointer");
+  TopkPlan pl;
+  int rc = topk_plan(n_q, n_lib, d, k, dtype, &pl);
+  if (rc) return rc;
+  *out = pl.cand_elems * 8 + 256;
+  return 0;
+}
+
+int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const float* rinv_lib, int64_t n_q, int64_t n_lib,
+                 int64_t d, int64_t col_offset, int k, int dtype, float* out_score, int64_t* out_idx, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  if (!q || !lib || !rinv_q || !rinv_lib || !out_score || !out_idx || !workspace) return fail(CLIPNCE_EINVAL, "topk: null pointer");
+  if (!aligned16(q) || !aligned16(lib)) return fail(CLIPNCE_EINVAL, "topk: operands must be 16-byte aligned");
+  if (col_offset < 0 || col_offset + n_lib >= (1ll << 31)) return fail(CLIPNCE_EINVAL, "topk: library index range must fit int32");
+  TopkPlan pl;
+  int rc = topk_plan(n_q, n_lib, d, k, dtype, &pl);
+  if (rc) return rc;
+  if ((rc = check_device_sm100())) return rc;
+  if (workspace_bytes < pl.cand_elems * 8) return fail(CLIPNCE_EWORKSPACE, "topk: workspace %zu < %zu", workspace_bytes, pl.cand_elems * 8);
+  cudaStream_t st = as_stream(stream);
+  pair::FwdParams p;
+  memset(&p, 0, sizeof p);
+  p.n_rows = (int)n_q; p.n_cols = (int)n_lib; p.d = (int)d;
+  p.nkc = (int)ceil_div(d, 64); p.n_steps = pl.n_steps; p.n_pairs = pl.n_pairs; p.split_steps = pl.split_steps;
+  p.rinv_x = rinv_q; p.rinv_y = rinv_lib; p.col_offset = col_offset;
+  p.cand_score = reinterpret_cast<float*>(workspace);
+  p.cand_idx = reinterpret_cast<int*>(p.cand_score + pl.cand_elems);
+  if (pl.kt == 1) rc = launch_pair_fwd<128, 1, 1>(8, q, lib, p, st);
+  else if (pl.kt == 10) rc = launch_pair_fwd<128, 1, 10>(9, q, lib, p, st);
+  else rc = launch_pair_fwd<128, 1, 16>(10, q, lib, p, st);
+  if (rc) return rc;
+  aux::topk_merge<<<(unsigned)ceil_div(n_q, 8), 256, 0, st>>>(p.cand_score, p.cand_idx, pl.n_split * 4, n_q, pl.kt, k, out_score,
+                                                               out_idx);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

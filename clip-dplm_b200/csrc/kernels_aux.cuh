@@ -179,6 +179,41 @@ __global__ void sum_splits(const float4* __restrict__ part, int n_split, int64_t
   out[i] = acc;
 }
 
+// Retrieval: merge `n_slot` candidate lists of KT entries per row into the row's k best (one warp per row; ties -> lower
+// column index).  cand_* are [n_slot][n_rows][KT]; out_* are [n_rows][k].
+__global__ void topk_merge(const float* __restrict__ cand_score, const int* __restrict__ cand_idx, int n_slot, int64_t n_rows,
+                           int kt, int k, float* __restrict__ out_score, int64_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int n_cand = n_slot * kt;                 // <= 32 * 64
+  unsigned long long used = 0ull;                 // this lane's candidates c = lane + 32 u, u < 64
+  for (int r = 0; r < k; ++r) {
+    float best = -INFINITY;
+    int best_i = 0x7fffffff, best_u = -1;
+    for (int u = 0, c = lane; c < n_cand; ++u, c += 32) {
+      if ((used >> u) & 1ull) continue;
+      const int64_t o = ((int64_t)(c / kt) * n_rows + row) * kt + (c % kt);
+      const float v = cand_score[o];
+      const int ix = cand_idx[o];
+      if (ix >= 0 && (v > best || (v == best && ix < best_i))) { best = v; best_i = ix; best_u = u; }
+    }
+    float wv = best;
+    int wi = best_i;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+    }
+    if (best_u >= 0 && best == wv && best_i == wi) used |= 1ull << best_u;   // (score, index) pairs are unique per row
+    if (lane == 0) {
+      out_score[row * k + r] = wi == 0x7fffffff ? -INFINITY : wv;
+      out_idx[row * k + r] = wi == 0x7fffffff ? -1 : (int64_t)wi;
+    }
+  }
+}
+
 // part[block] = sum over the block's 8 rows of rinv_i <x_i, g_i>   (= <xhat_i, dxhat_i>; one warp per row)
 template <typename TI>
 __global__ void rowdot_partials(const TI* __restrict__ x, const float* __restrict__ rinv, const float* __restrict__ g,

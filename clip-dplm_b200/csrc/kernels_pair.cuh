@@ -407,6 +407,10 @@ struct FwdParams {
   float* col_part;    // [gridDim.x][col_ld] partial sum_i exp(S_ij - s) over this CTA's rows
   long long col_ld;   // n_steps * 256
   float* diag;        // [n_rows]
+  // retrieval (MODE 1): per work item and column group, every row's K best columns
+  float* cand_score;  // [n_split * 4][n_rows][KT]   rinv_x[i] rinv_y[j] <x_i, y_j>  (cosine similarity)
+  int* cand_idx;      // same shape: col_offset + j, or -1
+  long long col_offset;
 };
 
 __host__ __device__ constexpr int fwd_smem_bytes(int rows, int nkc, int stages) {
@@ -414,12 +418,15 @@ __host__ __device__ constexpr int fwd_smem_bytes(int rows, int nkc, int stages) 
 }
 
 // ROWS = resident rows per CTA: 128 (M = 256, lane = row) for d <= 512, else 64 (M = 128, 2x2 layout).
-template <int ROWS>
+// MODE 0: InfoNCE forward statistics.  MODE 1 (ROWS = 128 only): retrieval -- the same similarity sweep with a running
+// top-KT per row instead of the soft-max sums (run1/full.py:152 argmax, :157 cosine_similarity; BASELINE config 5).
+template <int ROWS, int MODE = 0, int KT = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS rows}
            const __grid_constant__ CUtensorMap tmap_y,   // Y box {64 k, 128 rows}
            const FwdParams p) {
   static_assert(ROWS == 64 || ROWS == 128, "ROWS");
+  static_assert(MODE == 0 || ROWS == 128, "retrieval uses the 128-row variant");
   constexpr int X_CHUNK = ROWS * 128;
   constexpr int SBUF_COLS = ROWS == 128 ? 256 : 128;       // TMEM columns of one logits buffer
   constexpr int NCH = ROWS == 128 ? 2 : 1;                 // 32-column chunks per warp per step
@@ -524,6 +531,86 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
       }
     }
     __syncwarp();
+  } else if (warp >= 4 && MODE == 1) {
+    // ================================================================= epilogue (retrieval): running top-KT per row
+    const int e = warp - 4;
+    const int q = warp & 3;
+    const int cgp = e >> 2;
+    const int i_local = 32 * q + lane;
+    const long long i_glob = (long long)i0 + i_local;
+    const bool row_ok = i_glob < p.n_rows;
+    const int col0 = 64 * cgp;
+    const int te = threadIdx.x - 128;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
+    float bv[KT];   // descending; ties keep the earlier (lower) column
+    int bi[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { bv[k] = -INFINITY; bi[k] = -1; }
+
+    float ry_n = 0.f;
+    if (te < STEP_J) {
+      const long long j = (long long)t_begin * STEP_J + te;
+      ry_n = (j < p.n_cols) ? p.rinv_y[j] : -1.f;
+    }
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tl = t - t_begin;
+      const int sb = tl & 1;
+      float* const cv = colv + (tl & 1) * 512;
+      if (te < STEP_J) {
+        cv[te] = ry_n < 0.f ? 0.f : ry_n;                  // score / rinv_x[i] = acc * rinv_y[j]
+        cv[256 + te] = ry_n < 0.f ? -INFINITY : 0.f;       // columns past the end never enter a list
+        const long long jn = (long long)(t + 1) * STEP_J + te;
+        ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
+      }
+      named_bar_sync(1, EPI_THREADS);
+      ptx::mbar_wait(bar(B_SFULL + sb), (tl >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_lane + sb * SBUF_COLS + col0 + 32 * c, r);
+        ptx::tmem_ld_wait();
+        if (c == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(sempty_leader + 8u * sb);
+        }
+        const float* const cjp = cv + col0 + 32 * c;
+        const int jbase = t * STEP_J + col0 + 32 * c;
+#pragma unroll
+        for (int x4 = 0; x4 < 8; ++x4) {
+          const float4 ry4 = *reinterpret_cast<const float4*>(cjp + 4 * x4);
+          const float4 c04 = *reinterpret_cast<const float4*>(cjp + 256 + 4 * x4);
+          const float ryv[4] = {ry4.x, ry4.y, ry4.z, ry4.w};
+          const float c0v[4] = {c04.x, c04.y, c04.z, c04.w};
+#pragma unroll
+          for (int xx = 0; xx < 4; ++xx) {
+            const float v = fmaf(__uint_as_float(r[4 * x4 + xx]), ryv[xx], c0v[xx]);
+            if (v > bv[KT - 1]) {   // rare after the first few steps: ~KT ln(columns / KT) insertions per row
+              const int j = jbase + 4 * x4 + xx;
+#pragma unroll
+              for (int k = KT - 1; k > 0; --k) {
+                const bool up = v > bv[k - 1];
+                const bool here = v > bv[k];
+                bi[k] = up ? bi[k - 1] : (here ? j : bi[k]);
+                bv[k] = up ? bv[k - 1] : (here ? v : bv[k]);
+              }
+              if (v > bv[0]) { bv[0] = v; bi[0] = j; }
+            }
+          }
+        }
+      }
+    }
+    if (row_ok) {
+      const float rx = p.rinv_x[i_glob];
+      const long long o = (((long long)split * 4 + cgp) * p.n_rows + i_glob) * KT;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        p.cand_score[o + k] = bv[k] * rx;
+        p.cand_idx[o + k] = bi[k] < 0 ? -1 : (int)(p.col_offset + bi[k]);
+      }
+    }
   } else if (warp >= 4) {
     // ================================================================= epilogue: row sums, column partials, diagonal
     const int e = warp - 4;            // 0..15

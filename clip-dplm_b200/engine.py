@@ -149,6 +149,23 @@ class CudaEngine:
                                                        _p(dx), _DT[out_dtype], _stream()), "normalize_backward")
         return dx
 
+    def topk(self, q, lib, rinv_q, rinv_lib, k, col_offset=0):
+        """-> scores [n_q,k] f32 (descending), indices [n_q,k] i64 of the k most similar library rows per query
+        (cosine similarity; run1/full.py:152,157).  bf16, d in {128,...,512}, k <= 16; raises otherwise."""
+        self._chk(q, (torch.bfloat16,), "queries")
+        self._chk(lib, (torch.bfloat16,), "library")
+        n_q, d = q.shape
+        n_lib = lib.shape[0]
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.clipnce_topk_workspace_bytes(n_q, n_lib, d, int(k), _DT[q.dtype], ctypes.byref(nbytes)),
+                   "topk_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=q.device)
+        scores = torch.empty((n_q, k), dtype=torch.float32, device=q.device)
+        idx = torch.empty((n_q, k), dtype=torch.int64, device=q.device)
+        _lib.check(self.lib.clipnce_topk(_p(q), _p(lib), _p(rinv_q), _p(rinv_lib), n_q, n_lib, d, int(col_offset), int(k),
+                                         _DT[q.dtype], _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "topk")
+        return scores, idx
+
     def loss(self, row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric):
         out = torch.empty(1, dtype=torch.float32, device=row_m.device)
         _lib.check(self.lib.clipnce_loss(_p(row_m), _p(row_l), _p(col_m), _p(col_l), _p(diag), row_m.numel(),

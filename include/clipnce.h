@@ -164,6 +164,24 @@ int clipnce_loss(const float* row_m, const float* row_l, const float* col_m, con
                  const float* diag, int64_t n_rows, int64_t diag_offset, int64_t n_global, int symmetric,
                  float* loss, void* stream);
 
+/*
+ * Retrieval: for every query row the k library rows of highest cosine similarity, without materialising the
+ * [n_q, n_lib] similarity matrix.  Replaces the evaluation tail of the reference
+ *   preds = logits.argmax(dim=1)                                        run1/full.py:152 (k = 1), :138-139, :265
+ *   F.cosine_similarity(a.unsqueeze(1), b.unsqueeze(0), dim=2)          run1/full.py:157 ([N,N,d] intermediate)
+ * and serves BASELINE.json config 5 (1M-entry protein library x 16k TF queries, top-10): the library is sharded by
+ * rows over the ranks, each rank calls this on its shard with col_offset = first global row of the shard and the
+ * [n_q, k] candidates of the ranks are merged by score.
+ * q [n_q,d], lib [n_lib,d] raw bf16 rows; rinv_* from clipnce_normalize; scores are rinv_q[i] rinv_lib[j] <q_i, lib_j>.
+ * out_score [n_q,k] f32 descending, out_idx [n_q,k] i64 = col_offset + j (ties: lower index first; -1 / -inf pad when
+ * n_lib < k).  Same tcgen05 CTA-pair sweep as clipnce_forward with a running top-k per row in the epilogue; served for
+ * CLIPNCE_BF16, d in {128, 256, 384, 512}, 1 <= k <= 16 -- anything else returns CLIPNCE_EUNSUPPORTED.
+ */
+int clipnce_topk_workspace_bytes(int64_t n_q, int64_t n_lib, int64_t d, int k, int dtype, size_t* out);
+int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const float* rinv_lib,
+                 int64_t n_q, int64_t n_lib, int64_t d, int64_t col_offset, int k, int dtype,
+                 float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,3 +165,13 @@ def retrieval_topk(queries, library, k=10):
     l = F.normalize(library, dim=-1)
     sim = torch.matmul(q, l.t())
     return torch.topk(sim, k, dim=1)
+
+
+def ref_topk(q, lib, k):
+    """Top-k retrieval the way the reference's evaluation forms it (run1/full.py:157 cosine similarity of every pair,
+    :152 argmax over it) -- as a dense normalised matmul (identical values; the reference's broadcast builds an
+    [n_q, n_lib, d] intermediate).  -> (scores [n_q,k], indices [n_q,k], sim [n_q,n_lib])."""
+    import torch.nn.functional as F
+    sim = F.normalize(q, dim=-1) @ F.normalize(lib, dim=-1).t()
+    scores, idx = torch.topk(sim, min(k, lib.shape[0]), dim=1)
+    return scores, idx, sim

@@ -40,6 +40,16 @@ class TorchCpuEngine:
             xt[:, :n] = xc.t()
         return xc, xt
 
+    def topk(self, q, lib, rinv_q, rinv_lib, k, col_offset=0):
+        sim = (q.to(self.dt) * rinv_q[:, None]) @ (lib.to(self.dt) * rinv_lib[:, None]).t()
+        kk = min(k, lib.shape[0])
+        s, i = torch.topk(sim, kk, dim=1)
+        if kk < k:
+            s = torch.cat([s, torch.full((s.shape[0], k - kk), float("-inf"), dtype=s.dtype)], dim=1)
+            i = torch.cat([i - col_offset, torch.full((i.shape[0], k - kk), -1 - col_offset, dtype=i.dtype)], dim=1)
+            return s.float(), i + col_offset
+        return s.float(), i + col_offset
+
     def _logits(self, x, y, rinv_x, rinv_y, scale):
         return scale * ((x * rinv_x[:, None]) @ (y * rinv_y[:, None]).t())
 

@@ -183,6 +183,59 @@ def test_row_sharded_global_batch_gloo(symmetric):
         assert abs(dt - float(ref["d_logit_scale"])) < 1e-9
 
 
+# ------------------------------------------------------------------------------------------------ retrieval (top-k)
+def test_ref_topk_is_the_reference_evaluation_tail():
+    """oracle.ref_topk == the reference's own forms: F.cosine_similarity(a.unsqueeze(1), b.unsqueeze(0), dim=2)
+    (run1/full.py:157) ranked by topk, and logits.argmax(dim=1) (run1/full.py:152) for k = 1."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    q, lib = torch.randn(37, 24, generator=g, dtype=torch.float64), torch.randn(91, 24, generator=g, dtype=torch.float64)
+    s, i, sim = O.ref_topk(q, lib, 5)
+    sim_ref = F.cosine_similarity(q.unsqueeze(1), lib.unsqueeze(0), dim=2)
+    assert torch.allclose(sim, sim_ref, atol=1e-12)
+    s2, i2 = torch.topk(sim_ref, 5, dim=1)
+    assert torch.equal(i, i2) and torch.allclose(s, s2, atol=1e-12)
+    logits = 14.3 * (F.normalize(q, dim=-1) @ F.normalize(lib, dim=-1).t())
+    assert torch.equal(O.ref_topk(q, lib, 1)[1][:, 0], logits.argmax(dim=1))
+
+
+def _gloo_topk_worker(rank, world, port, n_q, n_lib, d, k, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clip_dplm_b200.retrieval import topk_similarity
+        torch.set_num_threads(1)
+        g = torch.Generator().manual_seed(5)
+        qs, lib = torch.randn(n_q, d, generator=g, dtype=torch.float64), torch.randn(n_lib, d, generator=g, dtype=torch.float64)
+        nl = n_lib // world
+        s, i = topk_similarity(qs, lib[rank * nl:(rank + 1) * nl], k, group=dist.group.WORLD, engine=TorchCpuEngine())
+        q.put((rank, s.numpy(), i.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_retrieval_gloo():
+    """Library row-sharded over 2 ranks (BASELINE config 5 layout): per-shard top-k with global indices, candidates
+    all-gathered and merged -- must equal the single-process oracle on the whole library."""
+    world, n_q, n_lib, d, k = 2, 19, 64, 16, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_topk_worker, args=(r, world, port, n_q, n_lib, d, k, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    qs, lib = torch.randn(n_q, d, generator=g, dtype=torch.float64), torch.randn(n_lib, d, generator=g, dtype=torch.float64)
+    s_ref, i_ref, _ = O.ref_topk(qs, lib, k)
+    for rank, s, i in out:
+        assert np.array_equal(i, i_ref.numpy()) and np.allclose(s, s_ref.numpy(), atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------------ drop-in surface
 @pytest.mark.skipif(not os.path.exists("/root/reference/old/clip.py"), reason="reference checkout only exists in the build container")
 def test_module_parameter_names_match_reference():

@@ -309,3 +309,44 @@ def test_host_fed_step_pipelines_batches():
         want = ref_step(ah.cuda(), bh.cuda(), feeder.logit_scale.detach())
         torch.cuda.synchronize()
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# retrieval: top-k on the similarity sweep (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_q,n_lib,d,k,split", [(300, 5000, 512, 10, 0), (1000, 777, 128, 1, 0), (257, 20000, 256, 16, 9),
+                                                 (64, 9, 128, 10, 0), (513, 4096, 384, 5, 4)])
+def test_topk_matches_oracle(eng, monkeypatch, n_q, n_lib, d, k, split):
+    if split:
+        monkeypatch.setenv("CLIPNCE_SPLIT_STEPS", str(split))
+    else:
+        monkeypatch.delenv("CLIPNCE_SPLIT_STEPS", raising=False)
+    from clip_dplm_b200.retrieval import topk_similarity
+    g = torch.Generator().manual_seed(17)
+    q = torch.randn(n_q, d, generator=g).bfloat16()
+    lib = (torch.randn(n_lib, d, generator=g) * torch.rand(n_lib, 1, generator=g).add(0.5)).bfloat16()   # rows of varied norm
+    lib[: min(n_q, n_lib)] += 0.7 * q[: min(n_q, n_lib)]                                                 # planted neighbours
+    s_ref, i_ref, sim = O.ref_topk(q.double(), lib.double(), k)
+    s, i = topk_similarity(q.cuda(), lib.cuda(), k, library_offset=0)
+    torch.cuda.synchronize()
+    s, i = s.cpu().double(), i.cpu()
+    kk = min(k, n_lib)
+    assert (i[:, kk:] == -1).all() and torch.isinf(s[:, kk:]).all()
+    s, i = s[:, :kk], i[:, :kk]
+    assert torch.allclose(s, s_ref, atol=2e-5, rtol=0)
+    # same columns up to exact ties: the oracle's similarity AT the returned indices is the oracle's k-th best or better
+    assert torch.allclose(torch.gather(sim, 1, i), s_ref, atol=2e-5, rtol=0)
+    assert (i == i_ref).double().mean() > 0.999
+    assert all(len(set(r.tolist())) == kk for r in i)
+
+
+def test_top1_accuracy_matches_argmax(eng):
+    from clip_dplm_b200.retrieval import top1_accuracy
+    a, b = O.make_inputs(1500, 256, seed=23, mix=0.25)
+    _, i_ref, _ = O.ref_topk(a.double(), b.double(), 1)
+    want = (i_ref[:, 0] == torch.arange(1500)).double().mean()
+    got = top1_accuracy(a.cuda().bfloat16(), b.cuda().bfloat16())
+    assert abs(float(got) - float(want)) < 2e-3
+    with pytest.raises(RuntimeError):
+        eng.topk(torch.zeros(8, 64, device="cuda", dtype=torch.bfloat16), torch.zeros(8, 64, device="cuda", dtype=torch.bfloat16),
+                 torch.ones(8, device="cuda"), torch.ones(8, device="cuda"), 3)      # d = 64: not served -> loud
