@@ -584,19 +584,25 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
           const float4 c04 = *reinterpret_cast<const float4*>(cjp + 256 + 4 * x4);
           const float ryv[4] = {ry4.x, ry4.y, ry4.z, ry4.w};
           const float c0v[4] = {c04.x, c04.y, c04.z, c04.w};
+          float v4[4];
 #pragma unroll
-          for (int xx = 0; xx < 4; ++xx) {
-            const float v = fmaf(__uint_as_float(r[4 * x4 + xx]), ryv[xx], c0v[xx]);
-            if (v > bv[KT - 1]) {   // rare after the first few steps: ~KT ln(columns / KT) insertions per row
-              const int j = jbase + 4 * x4 + xx;
+          for (int xx = 0; xx < 4; ++xx) v4[xx] = fmaf(__uint_as_float(r[4 * x4 + xx]), ryv[xx], c0v[xx]);
+          // one test per four columns: insertions are rare after the first few steps (~KT ln(columns / KT) per row)
+          if (fmaxf(fmaxf(v4[0], v4[1]), fmaxf(v4[2], v4[3])) > bv[KT - 1]) {
 #pragma unroll
-              for (int k = KT - 1; k > 0; --k) {
-                const bool up = v > bv[k - 1];
-                const bool here = v > bv[k];
-                bi[k] = up ? bi[k - 1] : (here ? j : bi[k]);
-                bv[k] = up ? bv[k - 1] : (here ? v : bv[k]);
+            for (int xx = 0; xx < 4; ++xx) {
+              const float v = v4[xx];
+              if (v > bv[KT - 1]) {
+                const int j = jbase + 4 * x4 + xx;
+#pragma unroll
+                for (int k = KT - 1; k > 0; --k) {
+                  const bool up = v > bv[k - 1];
+                  const bool here = v > bv[k];
+                  bi[k] = up ? bi[k - 1] : (here ? j : bi[k]);
+                  bv[k] = up ? bv[k - 1] : (here ? v : bv[k]);
+                }
+                if (v > bv[0]) { bv[0] = v; bi[0] = j; }
               }
-              if (v > bv[0]) { bv[0] = v; bi[0] = j; }
             }
           }
         }
