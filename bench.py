@@ -345,6 +345,8 @@ def run_ours(args, rank, local_rank, world):
         e2e_fn()
     ms_e2e = timed(e2e_fn, args.steps)
 
+    if gstep is not None:
+        gstep.close()     # before the process group goes away
     if rank != 0:
         return
     if args.trace:

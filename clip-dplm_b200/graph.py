@@ -61,6 +61,14 @@ class GraphedClipStep:
             self.out = self._eager()
         return self
 
+    def close(self):
+        """Drop the captured graph.  Call before ``dist.destroy_process_group()``: a live graph that holds captured NCCL
+        kernels stalls the communicator's teardown."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph.reset()
+            self.graph = None
+
     def replay(self):
         """Replay on whatever the static inputs ``self.a``, ``self.b``, ``self.logit_scale`` hold (callers that write their
         embeddings straight into them -- e.g. an H2D copy -- skip the device-to-device copies of ``__call__``)."""
