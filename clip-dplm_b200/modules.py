@@ -79,6 +79,12 @@ class LazyLogits:
         return self._m
 
     def argmax(self, dim=1):
+        """``logits.argmax(dim=1)`` of run1/full.py:152 through the retrieval kernel (top-1 on the similarity sweep, no
+        N x N matrix) where it is served: CUDA, d in {128, 256, 384, 512}; the positive scale does not move an argmax."""
+        a, b = (self.a_hat, self.b_hat) if dim in (1, -1) else (self.b_hat, self.a_hat)
+        if self._m is None and a.is_cuda and a.shape[1] % 128 == 0 and a.shape[1] <= 512 and dim in (0, 1, -1, -2):
+            from .retrieval import topk_similarity
+            return topk_similarity(a, b, 1)[1][:, 0]
         return self.materialize().argmax(dim=dim)
 
     def t(self):
