@@ -73,6 +73,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def measured_traffic(n_global, d, world):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
+    dram__bytes_write.sum of pair::bwd_kernel), valid for the configuration it was captured on; None otherwise."""
+    if (n_global, d, world) != (65536, 512, 1):
+        return None
+    try:
+        import csv
+        rd = wr = None
+        for row in csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_pair_kernels_n65536.csv"))):
+            if row and row[0].startswith("dram__bytes_read.sum") and row[1] == "Mbyte":
+                rd = float(row[3])
+            if row and row[0].startswith("dram__bytes_write.sum") and row[1] == "Mbyte":
+                wr = float(row[3])
+        return (rd + wr) * 1e6 if rd is not None and wr is not None else None
+    except Exception:
+        return None
+
+
 def visible_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -383,7 +401,7 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "launch_mode": graph_note, "eager_ms_per_step": ms_eager / args.steps,
         "roofline": {"bound": "tensor", "kernel": "pair::bwd_kernel (one backward side: logits recompute + gradient GEMM, cta_group::2)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": measured_traffic(n_global, d, world),
                      "peak_kind": f"{peaks['src']} sustained bf16 cuBLAS", "frac_of_burst": achieved / peaks["burst"],
                      "ms_per_launch": t_bwd, "fwd_ms_per_launch": t_fwd,
                      "fwd_achieved": 2.0 * n_local * n_global * d / (t_fwd * 1e-3) / 1e12,

@@ -102,7 +102,10 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
     y, rinv_y = b_c, rinv_b
     if world > 1:
         y = _all_gather_rows(b_c, group)
-        rinv_y = _all_gather_rows(rinv_b, group)
+        if b.dtype == compute_dtype:
+            rinv_y, _ = engine.normalize(y)   # same kernel on the same rows as on their owner: identical values, one collective less
+        else:   # norms were taken on the caller's (wider) rows before staging: ship them
+            rinv_y = _all_gather_rows(rinv_b, group)
     if callable(scale):
         scale = scale()
     tc = engine.uses_tensor_cores(compute_dtype, a.shape[1], scale, flags)
