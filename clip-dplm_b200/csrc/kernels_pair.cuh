@@ -24,7 +24,7 @@
 //                 (.cta_group::2) completes its bytes on the leader's barrier
 //   EMPTY_A/B[s]  both: tcgen05.commit multicast from the leader after the MMAs that read stage s
 //   SFULL[b]      both: commit multicast (logits buffer b complete)         SEMPTY[b]  leader: one arrival per
-//                 epilogue warp of both CTAs (remote arrive, release.cluster)
+//                 epilogue warp of both CTAs (remote mbarrier.arrive, CTA-scope release -- see ptx::mbar_arrive_cluster)
 //   GFULL[kc]     leader: the 2 warps per CTA that wrote gradient box kc     GEMPTY[kc] both: commit multicast
 #pragma once
 #include <cuda.h>

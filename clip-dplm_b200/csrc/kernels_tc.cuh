@@ -97,11 +97,11 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// exp2 on the FMA/ALU pipes.  MUFU.EX2 issues one warp instruction per 32 clk per SM sub-partition on B200 (ncu: the XU
-// pipe sat at 113 % of its sustained peak with the forward at 4 exp/clk/SM), which made the exponential -- not the tensor
-// pipe -- the limiter of the forward.  Range reduction by the 1.5*2^23 rounding trick, degree-5 minimax polynomial for
-// 2^f on [-0.5, 0.5] (max relative error 2.4e-7, the same class as MUFU.EX2), exponent spliced in with an integer add.
-// Valid for x in [-125, 1]; the tensor-core path guarantees x >= -2 s log2(e) >= -124.1.
+// exp2 on the FMA/ALU pipes: range reduction by the 1.5*2^23 rounding trick, degree-5 minimax polynomial for 2^f on
+// [-0.5, 0.5] (max relative error 2.4e-7, the same class as MUFU.EX2), exponent spliced in with an integer add.  Valid
+// for x in [-125, 1]; the tensor-core path guarantees x >= -2 s log2(e) >= -124.1.  These single-CTA kernels split the
+// exponentials 1:3 between MUFU and this polynomial; tools/umma_probe.cu later measured MUFU.EX2 at 16 results/clk/SM
+// against 11.7 for the polynomial (issue-bound), so the pair kernels (kernels_pair.cuh) simply use MUFU.
 __device__ __forceinline__ float ex2_poly(float x) {
   const float t = x + 12582912.0f;
   const float f = x - (t - 12582912.0f);
