@@ -553,7 +553,7 @@ int clipnce_topk_workspace_bytes(int64_t n_q, int64_t n_lib, int64_t d, int k, i
   TopkPlan pl;
   int rc = topk_plan(n_q, n_lib, d, k, dtype, &pl);
   if (rc) return rc;
-  *out = pl.cand_elems * 8 + 256;
+  *out = pl.cand_elems * 8 + sizeof(int) * (size_t)n_q + 256;
   return 0;
 }
 
@@ -567,7 +567,8 @@ int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const floa
   int rc = topk_plan(n_q, n_lib, d, k, dtype, &pl);
   if (rc) return rc;
   if ((rc = check_device_sm100())) return rc;
-  if (workspace_bytes < pl.cand_elems * 8) return fail(CLIPNCE_EWORKSPACE, "topk: workspace %zu < %zu", workspace_bytes, pl.cand_elems * 8);
+  const size_t need = pl.cand_elems * 8 + sizeof(int) * (size_t)n_q;
+  if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "topk: workspace %zu < %zu", workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
   pair::FwdParams p;
   memset(&p, 0, sizeof p);
@@ -576,6 +577,8 @@ int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const floa
   p.rinv_x = rinv_q; p.rinv_y = rinv_lib; p.col_offset = col_offset;
   p.cand_score = reinterpret_cast<float*>(workspace);
   p.cand_idx = reinterpret_cast<int*>(p.cand_score + pl.cand_elems);
+  p.row_thr = p.cand_idx + pl.cand_elems;
+  CUDA_TRY(cudaMemsetAsync(p.row_thr, 0x80, sizeof(int) * (size_t)n_q, st));   // key 0x80808080: below every real score
   if (pl.kt == 1) rc = launch_pair_fwd<128, 1, 1>(8, q, lib, p, st);
   else if (pl.kt == 10) rc = launch_pair_fwd<128, 1, 10>(9, q, lib, p, st);
   else rc = launch_pair_fwd<128, 1, 16>(10, q, lib, p, st);

@@ -55,6 +55,12 @@ __device__ __forceinline__ float ex2(float x) { return tc::ex2(x); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// order-preserving float <-> int key (for atomicMax on scores of either sign)
+__device__ __forceinline__ int float_key(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -410,6 +416,8 @@ struct FwdParams {
   // retrieval (MODE 1): per work item and column group, every row's K best columns
   float* cand_score;  // [n_split * 4][n_rows][KT]   rinv_x[i] rinv_y[j] <x_i, y_j>  (cosine similarity)
   int* cand_idx;      // same shape: col_offset + j, or -1
+  int* row_thr;       // [n_rows] order-preserving int key of a lower bound on each row's final K-th best score, shared
+                      // by all work items of the row through atomicMax (initialised to a very negative key)
   long long col_offset;
 };
 
@@ -547,6 +555,20 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
     int bi[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) { bv[k] = -INFINITY; bi[k] = -1; }
+    // Shared threshold.  Every thread's K-th best is a lower bound on its row's final K-th best, so the maximum over
+    // all threads that ever worked on the row (other column groups, other work items, earlier waves) is one too:
+    // columns strictly below it can be skipped without changing the result (ties are kept: >=).  Work items that start
+    // after the first wave begin with a warm threshold and insert almost nothing -- the sorted insertion, executed by
+    // the whole warp whenever one lane needs it, was 55 % of the sweep time with cold lists (k = 10, 125 k-row shard).
+    // Lists hold the UNSCALED score acc * rinv_y[j]; the shared key is of the scaled score (* rinv_x[i] > 0).
+    const float rxp = row_ok ? p.rinv_x[i_glob] : 1.f;
+    const float rxp_inv = 1.f / fmaxf(rxp, 1e-30f);
+    auto shared_bound = [&]() -> float {   // the row's published bound in list units, nudged DOWN past every rounding
+      const float u = key_float(__ldcg(p.row_thr + i_glob)) * rxp_inv;
+      return u - (fabsf(u) * 4e-7f + 1e-37f);
+    };
+    float thr = row_ok ? shared_bound() : INFINITY;   // rows past the end: skip all
+    float published = -INFINITY;
 
     float ry_n = 0.f;
     if (te < STEP_J) {
@@ -562,6 +584,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         cv[256 + te] = ry_n < 0.f ? -INFINITY : 0.f;       // columns past the end never enter a list
         const long long jn = (long long)(t + 1) * STEP_J + te;
         ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
+      }
+      if ((tl & 3) == 3 && row_ok) {   // every 4 steps: publish this thread's bound, pick up everybody else's
+        if (bv[KT - 1] > published) {
+          published = bv[KT - 1];
+          atomicMax(p.row_thr + i_glob, float_key(published * rxp));
+        }
+        thr = fmaxf(thr, shared_bound());
       }
       named_bar_sync(1, EPI_THREADS);
       ptx::mbar_wait(bar(B_SFULL + sb), (tl >> 1) & 1);
@@ -587,12 +616,13 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
           float v4[4];
 #pragma unroll
           for (int xx = 0; xx < 4; ++xx) v4[xx] = fmaf(__uint_as_float(r[4 * x4 + xx]), ryv[xx], c0v[xx]);
-          // one test per four columns: insertions are rare after the first few steps (~KT ln(columns / KT) per row)
-          if (fmaxf(fmaxf(v4[0], v4[1]), fmaxf(v4[2], v4[3])) > bv[KT - 1]) {
+          // one test per four columns: insertions are rare once the threshold is warm
+          const float cut = fmaxf(bv[KT - 1], thr);
+          if (fmaxf(fmaxf(v4[0], v4[1]), fmaxf(v4[2], v4[3])) >= cut) {
 #pragma unroll
             for (int xx = 0; xx < 4; ++xx) {
               const float v = v4[xx];
-              if (v > bv[KT - 1]) {
+              if (v > bv[KT - 1] && v >= thr) {
                 const int j = jbase + 4 * x4 + xx;
 #pragma unroll
                 for (int k = KT - 1; k > 0; --k) {
@@ -608,6 +638,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         }
       }
     }
+    if (row_ok && bv[KT - 1] > published) atomicMax(p.row_thr + i_glob, float_key(bv[KT - 1] * rxp));
     if (row_ok) {
       const float rx = p.rinv_x[i_glob];
       const long long o = (((long long)split * 4 + cgp) * p.n_rows + i_glob) * KT;

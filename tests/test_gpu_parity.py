@@ -350,3 +350,22 @@ def test_top1_accuracy_matches_argmax(eng):
     with pytest.raises(RuntimeError):
         eng.topk(torch.zeros(8, 64, device="cuda", dtype=torch.bfloat16), torch.zeros(8, 64, device="cuda", dtype=torch.bfloat16),
                  torch.ones(8, device="cuda"), torch.ones(8, device="cuda"), 3)      # d = 64: not served -> loud
+
+
+def test_topk_negative_scores_and_shared_threshold(eng, monkeypatch):
+    """Queries anti-correlated with most of the library: the k best similarities are negative, so the threshold that
+    work items share through atomicMax (an order-preserving int key) and its safety margin are exercised below zero;
+    many short work items (forced split) make later items start from earlier items' bounds."""
+    monkeypatch.setenv("CLIPNCE_SPLIT_STEPS", "8")
+    from clip_dplm_b200.retrieval import topk_similarity
+    g = torch.Generator().manual_seed(29)
+    n_q, n_lib, d, k = 256, 30000, 128, 10
+    base = torch.randn(1, d, generator=g)
+    q = (base + 0.3 * torch.randn(n_q, d, generator=g)).bfloat16()
+    lib = (-base + 0.6 * torch.randn(n_lib, d, generator=g)).bfloat16()
+    s_ref, i_ref, sim = O.ref_topk(q.double(), lib.double(), k)
+    assert float(s_ref.max()) < 0
+    s, i = topk_similarity(q.cuda(), lib.cuda(), k)
+    torch.cuda.synchronize()
+    assert torch.allclose(s.cpu().double(), s_ref, atol=2e-5, rtol=0)
+    assert torch.allclose(torch.gather(sim, 1, i.cpu()), s_ref, atol=2e-5, rtol=0)
