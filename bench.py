@@ -213,11 +213,32 @@ def run_ours(args, rank, local_rank, world):
             self.launches += 1
             return super().loss(*a, **k)
 
+        # the exchange kernels over NVLink peer memory (one launch each)
+        def link_push_rows(self, *a, **k):
+            self.launches += 1
+            return super().link_push_rows(*a, **k)
+
+        def link_barrier(self, *a, **k):
+            self.launches += 1
+            return super().link_barrier(*a, **k)
+
+        def link_push_f32(self, *a, **k):
+            self.launches += 1
+            return super().link_push_f32(*a, **k)
+
+        def link_sum_scalars(self, *a, **k):
+            self.launches += 1
+            return super().link_sum_scalars(*a, **k)
+
+        def combine_partials(self, *a, **k):
+            self.launches += 1
+            return super().combine_partials(*a, **k)
+
     eng = TimedEngine()
     trace = {}
     if args.trace:
         # per-phase device timeline of one step: CUDA events around every engine call and every collective
-        from clip_dplm_b200 import step as _step_mod
+        from clip_dplm_b200 import exchange as _xchg_mod
 
         def wrap(name, fn):
             def inner(*a, **k):
@@ -240,10 +261,10 @@ def run_ours(args, rank, local_rank, world):
                 return out
             return inner
 
-        for nm in ("normalize", "stage", "softmax_weights", "combine_lse", "normalize_backward", "loss"):
+        for nm in ("normalize", "stage", "softmax_weights", "combine_lse", "normalize_backward", "loss", "link_push_rows",
+                   "link_barrier", "link_push_f32", "link_sum_scalars", "combine_partials"):
             setattr(eng, nm, wrap(nm, getattr(eng, nm)))
-        _step_mod._all_gather_rows = wrap("all_gather", _step_mod._all_gather_rows)
-        _step_mod._reduce_scatter_rows = wrap("reduce_scatter(issue->done)", _step_mod._reduce_scatter_rows)
+        _xchg_mod._all_gather = wrap("all_gather", _xchg_mod._all_gather)
         _orig_ar = dist.all_reduce
         dist.all_reduce = wrap("all_reduce", _orig_ar)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -363,8 +384,21 @@ def run_ours(args, rank, local_rank, world):
         e2e_fn()
     ms_e2e = timed(e2e_fn, args.steps)
 
+    comm = "none"
+    if world > 1:
+        from clip_dplm_b200 import exchange as _xchg
+        comm = _xchg.comm_kind(group)
+        torch.cuda.synchronize()
+        for fl in _xchg._Pool.free.values():     # a barrier that timed out would have left its mark here
+            for x in fl:
+                x.check()
+    final_loss = float((gstep.out[0] if gstep is not None else step_resident()).detach())
+    if not math.isfinite(final_loss):
+        raise RuntimeError(f"bench: loss is not finite ({final_loss})")
     if gstep is not None:
         gstep.close()     # before the process group goes away
+    if world > 1:
+        _xchg.reset()
     if rank != 0:
         return
     if args.trace:
@@ -395,6 +429,9 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": f"symmetric InfoNCE fwd+bwd, global batch {n_global}, d={d}, bf16 embeddings "
                                f"(b = 0.5a + 0.5 noise), logit_scale = ln(1/0.07)", "global_batch": n_global, "d": d,
                    "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                   "comm": {"link": "own kernels over NVLink peer memory (fused normalise+gather, pushes, device barriers)",
+                            "nccl": "NCCL collectives", "none": "none"}.get(comm, comm),
+                   "loss": final_loss,
                    "l2": "operands+outputs per step (>= 450 MB at N=65536) exceed the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_local * d * 2, "d2h_bytes_per_step": 4,
@@ -427,8 +464,13 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")
     ap.add_argument("--timeline", default=None, help="write a kernel timeline of three steps (torch.profiler) to this file")
     ap.add_argument("--trace", action="store_true", help="print a per-phase device-time breakdown of the step to stderr")
+    ap.add_argument("--comm", default="auto", choices=["auto", "link", "nccl"],
+                    help="multi-GPU exchange: this repository's kernels over NVLink peer memory (link; the default where "
+                         "available) or the NCCL collectives it is measured against")
     args = ap.parse_args()
 
+    if args.comm != "auto":
+        os.environ["CLIPNCE_COMM"] = args.comm
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

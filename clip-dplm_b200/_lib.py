@@ -43,6 +43,13 @@ SIGNATURES = {
     "clipnce_topk_workspace_bytes": [_i64, _i64, _i64, _int, _int, ctypes.POINTER(_sz)],
     "clipnce_topk": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp],
     "clipnce_loss": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp],
+    "clipnce_link_control_bytes": [ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
+    "clipnce_link_barrier": [ctypes.POINTER(_vp), _int, _int, _int, _vp],
+    "clipnce_link_push_rows": [_vp, _int, _i64, _i64, _int, ctypes.POINTER(_vp), _int, _i64, _i64, _i64, _vp],
+    "clipnce_link_push_f32": [ctypes.POINTER(_vp), ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, ctypes.POINTER(_vp),
+                              _int, _vp],
+    "clipnce_link_sum_scalars": [_vp, _int, ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp],
+    "clipnce_combine_partials": [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp],
 }
 _RESTYPES = {"clipnce_last_error": ctypes.c_char_p}
 
@@ -79,7 +86,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError here == header/library mismatch
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if lib.clipnce_version() != 101:
+        if lib.clipnce_version() != 102:
             raise RuntimeError("clip_dplm_b200: libclipnce.so version mismatch; rebuild")
         _lib = lib
         return lib

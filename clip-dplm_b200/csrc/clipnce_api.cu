@@ -14,6 +14,7 @@
 
 #include "../../include/clipnce.h"
 #include "kernels_aux.cuh"
+#include "kernels_link.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
@@ -631,6 +632,117 @@ int clipnce_loss(const float* row_m, const float* row_l, const float* col_m, con
   const double inv = 1.0 / ((symmetric ? 2.0 : 1.0) * (double)n_global);
   aux::loss_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_m, row_l, col_m, col_l, diag, n_rows, diag_offset, inv,
                                                        symmetric, loss);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- exchange over NVLink peer memory (kernels_link.cuh) ------------------------------------------------------------
+namespace {
+int make_peers(void* const* peer_base, int world, int rank, link::Peers* out) {
+  if (!peer_base || world < 1 || world > link::MAX_WORLD || rank < 0 || rank >= world)
+    return fail(CLIPNCE_EINVAL, "link: need 1 <= world <= %d peer buffers and 0 <= rank < world", link::MAX_WORLD);
+  memset(out, 0, sizeof *out);
+  for (int r = 0; r < world; ++r) {
+    if (!peer_base[r] || !aligned16(peer_base[r])) return fail(CLIPNCE_EINVAL, "link: peer buffer %d is null or unaligned", r);
+    out->base[r] = peer_base[r];
+  }
+  return 0;
+}
+unsigned long long link_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* e = getenv("CLIPNCE_LINK_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 10000;
+    return (unsigned long long)(ms > 0 ? ms : 10000) * 1000000ull;
+  }();
+  return ns;
+}
+}  // namespace
+
+int clipnce_link_control_bytes(int64_t* control_bytes, int64_t* status_offset) {
+  if (!control_bytes) return fail(CLIPNCE_EINVAL, "link_control_bytes: null pointer");
+  *control_bytes = link::CONTROL_BYTES;
+  if (status_offset) *status_offset = link::OFF_STATUS;
+  return 0;
+}
+
+int clipnce_link_barrier(void* const* peer_base, int world, int rank, int phase, void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, rank, &peers);
+  if (rc) return rc;
+  if (phase < 0 || phase >= link::MAX_PHASE) return fail(CLIPNCE_EINVAL, "link_barrier: bad phase %d", phase);
+  link::barrier<<<1, 32, 0, as_stream(stream)>>>(peers, world, rank, phase, link_timeout_ns());
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, int c_dtype, void* const* peer_base,
+                           int world, int64_t rows_offset, int64_t rinv_offset, int64_t row0, void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, 0, &peers);
+  if (rc) return rc;
+  if (!x || n < 1 || d < 1 || row0 < 0) return fail(CLIPNCE_EINVAL, "link_push_rows: bad argument");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (c_dtype != CLIPNCE_BF16 && c_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "link_push_rows: bad dtype");
+  if (rows_offset < link::CONTROL_BYTES || rows_offset % 16 != 0 || rinv_offset < link::CONTROL_BYTES || rinv_offset % 4 != 0)
+    return fail(CLIPNCE_EINVAL, "link_push_rows: offsets must lie behind the control block and be aligned");
+  if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_BF16 && (d % 8 != 0 || !aligned16(x)))
+    return fail(CLIPNCE_EINVAL, "link_push_rows: bf16 rows need d %% 8 == 0 and 16-byte alignment");
+  cudaStream_t st = as_stream(stream);
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
+  const int di = (int)d;
+  if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_BF16)
+    link::push_rows<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+  else if (in_dtype == CLIPNCE_F32 && c_dtype == CLIPNCE_BF16)
+    link::push_rows<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+  else if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_F32)
+    link::push_rows<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+  else
+    link::push_rows<float, float><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_link_push_f32(const float* const* src, const int64_t* n, const int64_t* dst_offset, int n_seg,
+                          void* const* peer_base, int world, void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, 0, &peers);
+  if (rc) return rc;
+  if (!src || !n || !dst_offset || n_seg < 1 || n_seg > 4) return fail(CLIPNCE_EINVAL, "link_push_f32: 1..4 segments");
+  link::PushSegs s;
+  memset(&s, 0, sizeof s);
+  int64_t n_max = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (!src[i] || n[i] < 1 || dst_offset[i] < link::CONTROL_BYTES || dst_offset[i] % 4 != 0)
+      return fail(CLIPNCE_EINVAL, "link_push_f32: bad segment %d", i);
+    s.src[i] = src[i]; s.n[i] = n[i]; s.dst_off[i] = dst_offset[i];
+    if (n[i] > n_max) n_max = n[i];
+  }
+  s.n_seg = n_seg;
+  int64_t gx = ceil_div(n_max, 256);
+  if (gx > 1024) gx = 1024;
+  link::push_f32<<<dim3((unsigned)gx, (unsigned)n_seg), 256, 0, as_stream(stream)>>>(s, peers, world);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_link_sum_scalars(const float* vals, int cnt, void* const* peer_base, int world, int rank, int phase,
+                             float* out, void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, rank, &peers);
+  if (rc) return rc;
+  if (!vals || !out || cnt < 1 || cnt > link::MAX_SCALARS) return fail(CLIPNCE_EINVAL, "link_sum_scalars: 1..%d values", link::MAX_SCALARS);
+  if (phase < 0 || phase >= link::MAX_PHASE) return fail(CLIPNCE_EINVAL, "link_sum_scalars: bad phase %d", phase);
+  link::sum_scalars<<<1, 128, 0, as_stream(stream)>>>(vals, cnt, peers, world, rank, phase, link_timeout_ns(), out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_combine_partials(const float* part_m, const float* part_l, int n_part, int64_t ld, int64_t n, float* out_m,
+                             float* out_l, void* stream) {
+  if (!part_m || !part_l || !out_m || !out_l || n_part < 1 || n < 1 || ld < n)
+    return fail(CLIPNCE_EINVAL, "combine_partials: bad argument");
+  aux::reduce_ml_partials<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(part_m, part_l, n_part, ld, n, out_m, out_l);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

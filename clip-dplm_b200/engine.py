@@ -166,6 +166,45 @@ class CudaEngine:
                                          _DT[q.dtype], _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "topk")
         return scores, idx
 
+    # ------------------------------------------------------------------ exchange over NVLink peer memory
+    def link_layout(self):
+        """-> (control_bytes, status_offset) of the control block at the start of every symmetric buffer."""
+        cb, so = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self.lib.clipnce_link_control_bytes(ctypes.byref(cb), ctypes.byref(so)), "link_control_bytes")
+        return cb.value, so.value
+
+    def link_barrier(self, peers, world, rank, phase):
+        _lib.check(self.lib.clipnce_link_barrier(peers, world, rank, phase, _stream()), "link_barrier")
+
+    def link_push_rows(self, x, c_dtype, peers, world, rows_off, rinv_off, row0):
+        self._chk(x, (torch.bfloat16, torch.float32), "embedding")
+        n, d = x.shape
+        _lib.check(self.lib.clipnce_link_push_rows(_p(x), _DT[x.dtype], n, d, _DT[c_dtype], peers, world, rows_off, rinv_off,
+                                                   row0, _stream()), "link_push_rows")
+
+    def link_push_f32(self, srcs, dst_offs, peers, world):
+        k = len(srcs)
+        for t in srcs:
+            self._chk(t, (torch.float32,), "statistics vector")
+        src = (ctypes.c_void_p * k)(*[t.data_ptr() for t in srcs])
+        n = (ctypes.c_int64 * k)(*[t.numel() for t in srcs])
+        off = (ctypes.c_int64 * k)(*dst_offs)
+        _lib.check(self.lib.clipnce_link_push_f32(src, n, off, k, peers, world, _stream()), "link_push_f32")
+
+    def link_sum_scalars(self, vals, peers, world, rank, phase):
+        self._chk(vals, (torch.float32,), "scalars")
+        out = torch.empty_like(vals)
+        _lib.check(self.lib.clipnce_link_sum_scalars(_p(vals), vals.numel(), peers, world, rank, phase, _p(out), _stream()),
+                   "link_sum_scalars")
+        return out
+
+    def combine_partials(self, part_m, part_l, n_part, ld, n):
+        out_m = torch.empty(n, dtype=torch.float32, device=part_m.device)
+        out_l = torch.empty(n, dtype=torch.float32, device=part_m.device)
+        _lib.check(self.lib.clipnce_combine_partials(_p(part_m), _p(part_l), n_part, ld, n, _p(out_m), _p(out_l), _stream()),
+                   "combine_partials")
+        return out_m, out_l
+
     def loss(self, row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric):
         out = torch.empty(1, dtype=torch.float32, device=row_m.device)
         _lib.check(self.lib.clipnce_loss(_p(row_m), _p(row_l), _p(col_m), _p(col_l), _p(diag), row_m.numel(),

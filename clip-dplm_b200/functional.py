@@ -70,8 +70,11 @@ class _ScaleHint:
 class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, logit_scale, extra, symmetric, scale_is_log, clamp_max, group, compute_dtype, flags, engine,
-                want_stats=True):
-        need_grad = a.requires_grad or b.requires_grad or (torch.is_tensor(logit_scale) and logit_scale.requires_grad)
+                want_stats=True, grad_mode=True):
+        # grad_mode: autograd's mode at the call (always off inside forward()).  Without a backward to come the step
+        # neither gathers the rows side B would stream nor keeps its exchange buffers (step.py)
+        need_grad = grad_mode and (a.requires_grad or b.requires_grad or
+                                   (torch.is_tensor(logit_scale) and logit_scale.requires_grad))
         info = {}
         s_dev = raw_dev = None
         if torch.is_tensor(logit_scale) and logit_scale.is_cuda:
@@ -125,7 +128,7 @@ class _FusedClipLoss(torch.autograd.Function):
                 coef = 1.0 if scale_is_log else 1.0 / s
                 d_ls = (ds * g * coef).reshape(()).to(device=ctx.ls_meta[1], dtype=ctx.ls_meta[0])
         ctx.st = None
-        return da, db, d_ls, None, None, None, None, None, None, None, None, None
+        return da, db, d_ls, None, None, None, None, None, None, None, None, None, None
 
 
 def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: bool = True,
@@ -141,7 +144,7 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
                   queue tong/utils/losses.py:10-11), used as stored, no gradient.  ``extra_normalized=False``
                   (rows of arbitrary norm) routes to the exact kernels.
     group         torch.distributed process group: rows are this rank's shard of a global batch; negatives
-                  are global, gradients are exact (reduce-scattered), the returned loss is the global mean.
+                  are global, gradients are exact (both sides complete on their owner), the returned loss is the global mean.
     compute_dtype torch.bfloat16 (tcgen05 tensor-core kernels) or torch.float32 (exact check mode).
                   Default: bf16 for bf16/fp16 inputs or under autocast, else fp32 (the reference's numerics).
     """
@@ -157,7 +160,8 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
     if extra_cols is not None and not extra_normalized:
         flags |= _step.FLAG_FORCE_EXACT
     loss, row_lse, col_lse, diag = _FusedClipLoss.apply(a, b, logit_scale, extra_cols, symmetric, scale_is_log,
-                                                        clamp_max, group, compute_dtype, flags, engine, bool(return_stats))
+                                                        clamp_max, group, compute_dtype, flags, engine, bool(return_stats),
+                                                        torch.is_grad_enabled())
     if return_stats:
         return loss, {"row_lse": row_lse, "col_lse": col_lse, "diag": diag}
     return loss

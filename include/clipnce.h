@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 101
+#define CLIPNCE_VERSION 102
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -181,6 +181,50 @@ int clipnce_topk_workspace_bytes(int64_t n_q, int64_t n_lib, int64_t d, int k, i
 int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const float* rinv_lib,
                  int64_t n_q, int64_t n_lib, int64_t d, int64_t col_offset, int k, int dtype,
                  float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Exchange steps of the row-sharded global batch over NVLink / NVSwitch peer memory.  Replaces the reference's
+ *   dist.all_gather(...) x2 + torch.cat      old/clip_opt.py:102-112   run1/full.py:77-84
+ * (which also cuts autograd: the gathered negatives carry no gradient there; here gradients stay exact).
+ *
+ * Every rank allocates ONE buffer of the same size and layout and maps all ranks' buffers into its address space
+ * (CUDA VMM / IPC handles, exchanged once by the host -- torch symmetric memory in this repository's Python host).
+ * peer_base is a HOST array of `world` DEVICE pointers: peer_base[r] = rank r's buffer as addressed from this GPU
+ * (peer_base[rank] = the own buffer).  The first clipnce_link_control_bytes() bytes of every buffer are the control
+ * block (arrival flags, device-side epoch counters, a status word, scalar slots): zero it once before the first call
+ * and leave it alone.  Everything else is laid out by the caller and addressed by BYTE OFFSETS from the base.
+ * All calls enqueue on `stream`, never synchronise the host, and keep their epochs on the device, so a step that
+ * contains them can be captured once in a CUDA graph and replayed.  Ranks must issue the same sequence of calls.
+ * A peer that does not arrive within CLIPNCE_LINK_TIMEOUT_MS (default 10000) sets the status word
+ * (u32 at status_offset of the own buffer: 1 + phase) instead of hanging the GPU; later barriers then return at once.
+ */
+int clipnce_link_control_bytes(int64_t* control_bytes, int64_t* status_offset);
+
+/* Barrier `phase` (0..7; use a different phase for every exchange point of a step): every store this GPU issued
+ * before it -- into peer buffers too -- is visible to kernels the peers launch after THEIR barrier of the same phase. */
+int clipnce_link_barrier(void* const* peer_base, int world, int rank, int phase, void* stream);
+
+/* Fused F.normalize row norms + all-gather: x [n,d] (in_dtype) -> rinv_i = 1 / max(|x_i|, 1e-12) and the rows,
+ * converted to c_dtype, are stored into EVERY rank's buffer: rows at rows_offset + (row0 + i) * d * sizeof(c_dtype),
+ * rinv at rinv_offset + (row0 + i) * 4.  row0 = rank * n.  Publish with clipnce_link_barrier. */
+int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, int c_dtype, void* const* peer_base,
+                           int world, int64_t rows_offset, int64_t rinv_offset, int64_t row0, void* stream);
+
+/* Copy n_seg (<= 4) local f32 vectors src[k][0..n[k]) to byte offset dst_offset[k] of every rank's buffer
+ * (the statistics exchange after the forward sweep).  src, n, dst_offset are HOST arrays.  Publish with a barrier. */
+int clipnce_link_push_f32(const float* const* src, const int64_t* n, const int64_t* dst_offset, int n_seg,
+                          void* const* peer_base, int world, void* stream);
+
+/* out[c] = sum over ranks of vals[c], c < cnt <= 8, in ONE kernel (push + barrier `phase` + fixed-order sum: every
+ * rank gets bit-identical results).  Used for the scalar loss and for d logit_scale; being a barrier it also closes
+ * the step: no peer touches this rank's gathered rows after it. */
+int clipnce_link_sum_scalars(const float* vals, int cnt, void* const* peer_base, int world, int rank, int phase,
+                             float* out, void* stream);
+
+/* Combine n_part partial (shift, sum) pairs per entry, part_*[p * ld + i], in fixed order:
+ * M_i = max_p m, L_i = sum_p l * exp(m - M_i)   (the column statistics of the ranks' row blocks). */
+int clipnce_combine_partials(const float* part_m, const float* part_l, int n_part, int64_t ld, int64_t n, float* out_m,
+                             float* out_l, void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,12 +82,12 @@ def test_known_answers():
 def test_library_exports_every_declared_symbol():
     from clip_dplm_b200 import _lib
     header = open(os.path.join(ROOT, "include", "clipnce.h")).read()
-    declared = set(re.findall(r"\b(clipnce_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(clipnce_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.clipnce_version() == 101
+    assert lib.clipnce_version() == 102
 
 
 def test_host_only_entry_points():
@@ -138,43 +138,46 @@ def test_step_logic_matches_oracle(kw, n_extra):
     assert abs(float(t.grad) / 2.5 - float(ref["d_logit_scale"])) < 1e-9
 
 
-def _gloo_worker(rank, world, port, n, d, symmetric, q):
+def _gloo_worker(rank, world, port, n, d, symmetric, n_extra, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from clip_dplm_b200 import fused_clip_loss
         torch.set_num_threads(1)
-        a, b = O.make_inputs(n, d, seed=21)
+        a, b = O.make_inputs(n, d, n_cols=n + n_extra, seed=21)
+        extra = torch.nn.functional.normalize(b[n:].double(), dim=-1) if n_extra else None
         nl = n // world
         ac = a[rank * nl:(rank + 1) * nl].double().requires_grad_(True)
         bc = b[rank * nl:(rank + 1) * nl].double().requires_grad_(True)
         t = torch.tensor(O.LOGIT_SCALE_INIT, dtype=torch.float64, requires_grad=True)
         loss = fused_clip_loss(ac, bc, t, engine=TorchCpuEngine(), compute_dtype=torch.float64, group=dist.group.WORLD,
-                               symmetric=symmetric)
+                               symmetric=symmetric, extra_cols=extra)
         loss.backward()
         q.put((rank, float(loss.detach()), ac.grad.numpy(), bc.grad.numpy(), float(t.grad)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("symmetric", [True, False])
-def test_row_sharded_global_batch_gloo(symmetric):
-    """world_size 2 over gloo: global negatives, exact gradients through the gather (reduce-scatter),
-    compared with the single-process reference on the concatenated batch."""
+@pytest.mark.parametrize("symmetric,n_extra", [(True, 0), (False, 0), (True, 24)])
+def test_row_sharded_global_batch_gloo(symmetric, n_extra):
+    """world_size 2 over gloo: global negatives (plus shared hard-negative cache columns), exact gradients -- side B of the
+    backward runs on the gathered rows -- compared with the single-process reference on the concatenated batch
+    (SURVEY.md section 8e)."""
     world, n, d = 2, 96, 32
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, d, symmetric, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, d, symmetric, n_extra, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    a, b = O.make_inputs(n, d, seed=21)
-    ref = O.ref_step(a.double(), b.double(), O.LOGIT_SCALE_INIT, symmetric=symmetric)
+    a, b = O.make_inputs(n, d, n_cols=n + n_extra, seed=21)
+    okw = {"extra_cols": torch.nn.functional.normalize(b[n:].double(), dim=-1)} if n_extra else {}
+    ref = O.ref_step(a.double(), b[:n].double(), O.LOGIT_SCALE_INIT, symmetric=symmetric, **okw)
     nl = n // world
     for rank, loss, da, db, dt in out:
         assert abs(loss - float(ref["loss"])) < 1e-12
