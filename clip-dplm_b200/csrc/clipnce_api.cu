@@ -676,9 +676,10 @@ int clipnce_link_barrier(void* const* peer_base, int world, int rank, int phase,
 }
 
 int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, int c_dtype, void* const* peer_base,
-                           int world, int64_t rows_offset, int64_t rinv_offset, int64_t row0, void* stream) {
+                           int world, int rank, int64_t rows_offset, int64_t rinv_offset, int64_t row0, int max_blocks,
+                           void* stream) {
   link::Peers peers;
-  int rc = make_peers(peer_base, world, 0, &peers);
+  int rc = make_peers(peer_base, world, rank, &peers);
   if (rc) return rc;
   if (!x || n < 1 || d < 1 || row0 < 0) return fail(CLIPNCE_EINVAL, "link_push_rows: bad argument");
   if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (c_dtype != CLIPNCE_BF16 && c_dtype != CLIPNCE_F32))
@@ -688,25 +689,28 @@ int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, in
   if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_BF16 && (d % 8 != 0 || !aligned16(x)))
     return fail(CLIPNCE_EINVAL, "link_push_rows: bf16 rows need d %% 8 == 0 and 16-byte alignment");
   cudaStream_t st = as_stream(stream);
-  const int wpb = 8;
-  dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
+  // foreground: one warp per row over the whole GPU; background (max_blocks > 0): a few fat blocks, grid-stride
+  const int wpb = max_blocks > 0 ? 32 : 8;
+  int64_t nblk = ceil_div(n, wpb);
+  if (max_blocks > 0 && nblk > max_blocks) nblk = max_blocks;
+  dim3 grid((unsigned)nblk), block(32 * wpb);
   const int di = (int)d;
   if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_BF16)
-    link::push_rows<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+    link::push_rows<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, peers, world, rank, rows_offset, rinv_offset, row0);
   else if (in_dtype == CLIPNCE_F32 && c_dtype == CLIPNCE_BF16)
-    link::push_rows<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+    link::push_rows<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rank, rows_offset, rinv_offset, row0);
   else if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_F32)
-    link::push_rows<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+    link::push_rows<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, peers, world, rank, rows_offset, rinv_offset, row0);
   else
-    link::push_rows<float, float><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rows_offset, rinv_offset, row0);
+    link::push_rows<float, float><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rank, rows_offset, rinv_offset, row0);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int clipnce_link_push_f32(const float* const* src, const int64_t* n, const int64_t* dst_offset, int n_seg,
-                          void* const* peer_base, int world, void* stream) {
+                          void* const* peer_base, int world, int rank, void* stream) {
   link::Peers peers;
-  int rc = make_peers(peer_base, world, 0, &peers);
+  int rc = make_peers(peer_base, world, rank, &peers);
   if (rc) return rc;
   if (!src || !n || !dst_offset || n_seg < 1 || n_seg > 4) return fail(CLIPNCE_EINVAL, "link_push_f32: 1..4 segments");
   link::PushSegs s;
@@ -721,7 +725,7 @@ int clipnce_link_push_f32(const float* const* src, const int64_t* n, const int64
   s.n_seg = n_seg;
   int64_t gx = ceil_div(n_max, 256);
   if (gx > 1024) gx = 1024;
-  link::push_f32<<<dim3((unsigned)gx, (unsigned)n_seg), 256, 0, as_stream(stream)>>>(s, peers, world);
+  link::push_f32<<<dim3((unsigned)gx, (unsigned)n_seg), 256, 0, as_stream(stream)>>>(s, peers, world, rank);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -22,6 +22,35 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr float kNormEps = 1e-12f;  // F.normalize default eps
 
+// One lane's share of a row's sum of squares (the caller adds the lanes with warp_sum).  bf16 rows with d % 8 == 0 are read
+// as 16-byte chunks.  Every kernel that needs 1/|x| goes through this function, so that a row's norm has the same bits
+// wherever it is computed (normalize_rows on the owner, link::push_rows for the gathered copies).
+template <typename TI>
+__device__ __forceinline__ float row_sumsq_lane(const TI* __restrict__ xr, int d, int lane) {
+  float ss = 0.f;
+  if constexpr (sizeof(TI) == 2) {
+    if ((d & 7) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {
+      const uint4* xv = reinterpret_cast<const uint4*>(xr);
+      for (int c = lane; c < (d >> 3); c += 32) {
+        const uint4 v = xv[c];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          ss = fmaf(f.x, f.x, ss);
+          ss = fmaf(f.y, f.y, ss);
+        }
+      }
+      return ss;
+    }
+  }
+  for (int k = lane; k < d; k += 32) {
+    const float v = ld_f(xr + k);
+    ss = fmaf(v, v, ss);
+  }
+  return ss;
+}
+
 // One warp per row: rinv = 1 / max(|x|, eps), optionally x_hat = x / max(|x|, eps)   (old/clip.py:63-64).
 template <typename TI, typename TO>
 __global__ void normalize_rows(const TI* __restrict__ x, int64_t n, int d, TO* __restrict__ xh, float* __restrict__ rinv) {
@@ -29,12 +58,7 @@ __global__ void normalize_rows(const TI* __restrict__ x, int64_t n, int d, TO* _
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const TI* xr = x + row * d;
-  float ss = 0.f;
-  for (int k = lane; k < d; k += 32) {
-    float v = ld_f(xr + k);
-    ss = fmaf(v, v, ss);
-  }
-  ss = warp_sum(ss);
+  const float ss = warp_sum(row_sumsq_lane(xr, d, lane));
   const float denom = fmaxf(sqrtf(ss), kNormEps);
   if (xh != nullptr) {
     TO* o = xh + row * d;

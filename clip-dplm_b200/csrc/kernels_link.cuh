@@ -101,47 +101,43 @@ __global__ void barrier(Peers peers, int world, int rank, int phase, unsigned lo
 
 // Fused normalise + all-gather: one warp per local row computes rinv = 1 / max(|x|, eps) (F.normalize, old/clip.py:63-64)
 // from the caller's rows and stores the row (in the compute type TO) and rinv into EVERY rank's gathered buffers at
-// global row  row0 + i  (the own copy included: the gathered matrix is complete on every rank).
+// global row  row0 + i  (the own copy included: the gathered matrix is complete on every rank).  Destinations are
+// visited starting behind the own rank, so that at any moment the ranks store to different peers (no ingress hot
+// spot at the switch).  Grid-stride over rows: a launch with few blocks is the background variant that leaves the SMs
+// to a contraction kernel running beside it.
 template <typename TI, typename TO>
-__global__ void push_rows(const TI* __restrict__ x, int64_t n, int d, Peers peers, int world, int64_t rows_off,
+__global__ void push_rows(const TI* __restrict__ x, int64_t n, int d, Peers peers, int world, int rank, int64_t rows_off,
                           int64_t rinv_off, int64_t row0) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n) return;
-  const TI* xr = x + row * d;
-  float ss = 0.f;
+  const int wpb = blockDim.x >> 5;
   constexpr bool kVec = sizeof(TI) == 2 && sizeof(TO) == 2;   // bf16 -> bf16: 16-byte chunks (d % 8 == 0 checked by the host)
-  if constexpr (kVec) {
-    const uint4* xv = reinterpret_cast<const uint4*>(xr);
-    const int nv = d >> 3;
-    for (int c = lane; c < nv; c += 32) {
-      const uint4 v = xv[c];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __bfloat1622float2(h[k]);
-        ss = fmaf(f.x, f.x, ss);
-        ss = fmaf(f.y, f.y, ss);
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * wpb) {
+    const TI* xr = x + row * d;
+    const float ss = aux::warp_sum(aux::row_sumsq_lane(xr, d, lane));   // the same bits as aux::normalize_rows
+    if constexpr (kVec) {
+      const uint4* xv = reinterpret_cast<const uint4*>(xr);
+      const int nv = d >> 3;
+      for (int c = lane; c < nv; c += 32) {
+        const uint4 v = xv[c];
+        for (int k = 1; k <= world; ++k) {
+          int r = rank + k;
+          r = r >= world ? r - world : r;
+          at<uint4>(peers.base[r], rows_off)[(row0 + row) * nv + c] = v;
+        }
+      }
+    } else {
+      for (int k = lane; k < d; k += 32) {
+        TO v;
+        aux::st_f(&v, aux::ld_f(xr + k));
+        for (int q = 1; q <= world; ++q) {
+          int r = rank + q;
+          r = r >= world ? r - world : r;
+          at<TO>(peers.base[r], rows_off)[(row0 + row) * d + k] = v;
+        }
       }
     }
-    ss = aux::warp_sum(ss);
-    for (int c = lane; c < nv; c += 32) {
-      const uint4 v = xv[c];
-      for (int r = 0; r < world; ++r) at<uint4>(peers.base[r], rows_off)[(row0 + row) * nv + c] = v;
-    }
-  } else {
-    for (int k = lane; k < d; k += 32) {
-      const float v = aux::ld_f(xr + k);
-      ss = fmaf(v, v, ss);
-    }
-    ss = aux::warp_sum(ss);
-    for (int k = lane; k < d; k += 32) {
-      TO v;
-      aux::st_f(&v, aux::ld_f(xr + k));
-      for (int r = 0; r < world; ++r) at<TO>(peers.base[r], rows_off)[(row0 + row) * d + k] = v;
-    }
+    if (lane < world) at<float>(peers.base[lane], rinv_off)[row0 + row] = 1.f / fmaxf(sqrtf(ss), aux::kNormEps);
   }
-  if (lane < world) at<float>(peers.base[lane], rinv_off)[row0 + row] = 1.f / fmaxf(sqrtf(ss), aux::kNormEps);
 }
 
 // Copy up to four local f32 vectors into every rank's buffer (statistics exchange after the forward sweep: this rank's
@@ -152,14 +148,18 @@ struct PushSegs {
   int64_t dst_off[4];   // bytes from the buffer base
   int n_seg;
 };
-__global__ void push_f32(PushSegs s, Peers peers, int world) {
+__global__ void push_f32(PushSegs s, Peers peers, int world, int rank) {
   const int seg = blockIdx.y;
   if (seg >= s.n_seg) return;
   const float* src = s.src[seg];
   const int64_t n = s.n[seg];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = src[i];
-    for (int r = 0; r < world; ++r) at<float>(peers.base[r], s.dst_off[seg])[i] = v;
+    for (int k = 1; k <= world; ++k) {
+      int r = rank + k;
+      r = r >= world ? r - world : r;
+      at<float>(peers.base[r], s.dst_off[seg])[i] = v;
+    }
   }
 }
 

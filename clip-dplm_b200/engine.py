@@ -176,20 +176,20 @@ class CudaEngine:
     def link_barrier(self, peers, world, rank, phase):
         _lib.check(self.lib.clipnce_link_barrier(peers, world, rank, phase, _stream()), "link_barrier")
 
-    def link_push_rows(self, x, c_dtype, peers, world, rows_off, rinv_off, row0):
+    def link_push_rows(self, x, c_dtype, peers, world, rank, rows_off, rinv_off, row0, max_blocks=0):
         self._chk(x, (torch.bfloat16, torch.float32), "embedding")
         n, d = x.shape
-        _lib.check(self.lib.clipnce_link_push_rows(_p(x), _DT[x.dtype], n, d, _DT[c_dtype], peers, world, rows_off, rinv_off,
-                                                   row0, _stream()), "link_push_rows")
+        _lib.check(self.lib.clipnce_link_push_rows(_p(x), _DT[x.dtype], n, d, _DT[c_dtype], peers, world, rank, rows_off,
+                                                   rinv_off, row0, max_blocks, _stream()), "link_push_rows")
 
-    def link_push_f32(self, srcs, dst_offs, peers, world):
+    def link_push_f32(self, srcs, dst_offs, peers, world, rank):
         k = len(srcs)
         for t in srcs:
             self._chk(t, (torch.float32,), "statistics vector")
         src = (ctypes.c_void_p * k)(*[t.data_ptr() for t in srcs])
         n = (ctypes.c_int64 * k)(*[t.numel() for t in srcs])
         off = (ctypes.c_int64 * k)(*dst_offs)
-        _lib.check(self.lib.clipnce_link_push_f32(src, n, off, k, peers, world, _stream()), "link_push_f32")
+        _lib.check(self.lib.clipnce_link_push_f32(src, n, off, k, peers, world, rank, _stream()), "link_push_f32")
 
     def link_sum_scalars(self, vals, peers, world, rank, phase):
         self._chk(vals, (torch.float32,), "scalars")

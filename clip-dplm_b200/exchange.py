@@ -27,6 +27,9 @@ import torch
 import torch.distributed as dist
 
 PHASE_COLS, PHASE_STATS, PHASE_LOSS, PHASE_CLOSE = 0, 1, 2, 3
+# thread blocks (of 1024 threads) of the background push of the A rows: it has the whole forward sweep to finish in, and
+# every block costs the sweep an SM (measured on 8 GPUs: a full-grid push beside the sweep slowed it from 365 to 435 us)
+BACKGROUND_BLOCKS = int(os.environ.get("CLIPNCE_LINK_BG_BLOCKS", "8"))
 
 
 def _all_gather(x, group):
@@ -161,7 +164,7 @@ class PeerExchange:
     # ---------------------------------------------------------------- the exchange steps
     def gather_cols(self, b, compute_dtype):
         e, lo = self.engine, self.rank * self.n
-        e.link_push_rows(b, compute_dtype, self.peers, self.world, self.o_y, self.o_rinv_y, lo)
+        e.link_push_rows(b, compute_dtype, self.peers, self.world, self.rank, self.o_y, self.o_rinv_y, lo)
         e.link_barrier(self.peers, self.world, self.rank, PHASE_COLS)
         return self.y[lo:lo + self.n], self.rinv_y[lo:lo + self.n], self.y, self.rinv_y
 
@@ -169,8 +172,8 @@ class PeerExchange:
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)          # behind barrier 0: the columns have the links to themselves
         with torch.cuda.stream(self.side):
-            self.engine.link_push_rows(a, compute_dtype, self.peers, self.world, self.o_xa, self.o_rinv_xa,
-                                       self.rank * self.n)
+            self.engine.link_push_rows(a, compute_dtype, self.peers, self.world, self.rank, self.o_xa, self.o_rinv_xa,
+                                       self.rank * self.n, max_blocks=BACKGROUND_BLOCKS)
         self._side_busy = True
 
     def gather_rows_end(self):
@@ -183,7 +186,7 @@ class PeerExchange:
         if need_rows:
             srcs += [row_m, row_l]
             offs += [self.o_rowm + 4 * r * self.n, self.o_rowl + 4 * r * self.n]
-        e.link_push_f32(srcs, offs, self.peers, self.world)
+        e.link_push_f32(srcs, offs, self.peers, self.world, r)
         if self._side_busy:                 # the A rows must have left before this rank arrives at the barrier
             torch.cuda.current_stream().wait_stream(self.side)
             self._side_busy = False

@@ -106,12 +106,20 @@ class _FusedClipLoss(torch.autograd.Function):
         else:   # two launches nobody reads
             row_lse = col_lse = st.diag
         ctx.mark_non_differentiable(row_lse, col_lse, st.diag)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradients" for the three statistics outputs (three launches)
         return loss.reshape(()), row_lse, col_lse, st.diag
 
     @staticmethod
     def backward(ctx, g_loss, _g1, _g2, _g3):
         st, engine = ctx.st, ctx.engine
         s, clamped, scale_is_log, s_dev, raw_dev, clamp_max = ctx.scale_info
+        if g_loss is None:   # the loss did not take part in the differentiated graph
+            if st.xchg is not None:   # still close the step on every rank and hand the exchange buffers back
+                st.xchg.sum_scalars(torch.zeros(1, dtype=torch.float32, device=st.diag.device), _step._exchange.PHASE_CLOSE)
+                st.xchg.release()
+                st.xchg = None
+            ctx.st = None
+            return (None,) * 13
         g = g_loss.reshape(1).to(torch.float32).contiguous()
         da, db, ds = _step.contrastive_backward(engine, st, grad_scale=g)
         d_ls = None

@@ -131,8 +131,11 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     if st.xa is None:
         raise RuntimeError("clip_dplm_b200: this step was run without need_grad")
     coef = 1.0 / ((2.0 if st.symmetric else 1.0) * n_glob)
-    row_w = engine.softmax_weights(st.row_l, coef)
-    row_w_all = row_w if st.row_l_all is st.row_l else engine.softmax_weights(st.row_l_all, coef)
+    if st.row_l_all is st.row_l:
+        row_w = row_w_all = engine.softmax_weights(st.row_l, coef)
+    else:   # the gathered row statistics hold the local block too
+        row_w_all = engine.softmax_weights(st.row_l_all, coef)
+        row_w = row_w_all[off:off + n]
     col_m = st.col_m
     col_w = engine.softmax_weights(st.col_l, coef) if st.symmetric else torch.zeros_like(st.col_l)
     diag_w = 1.0 / n_glob

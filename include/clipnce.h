@@ -206,14 +206,18 @@ int clipnce_link_barrier(void* const* peer_base, int world, int rank, int phase,
 
 /* Fused F.normalize row norms + all-gather: x [n,d] (in_dtype) -> rinv_i = 1 / max(|x_i|, 1e-12) and the rows,
  * converted to c_dtype, are stored into EVERY rank's buffer: rows at rows_offset + (row0 + i) * d * sizeof(c_dtype),
- * rinv at rinv_offset + (row0 + i) * 4.  row0 = rank * n.  Publish with clipnce_link_barrier. */
+ * rinv at rinv_offset + (row0 + i) * 4.  row0 = rank * n.  Publish with clipnce_link_barrier.
+ * max_blocks = 0: the whole GPU pushes (nothing else is running: the columns, before the forward sweep);
+ * max_blocks > 0: at most that many thread blocks -- the background variant for rows that travel beside a contraction
+ * kernel (the A rows, needed by the backward only), which then loses that many SMs at most. */
 int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, int c_dtype, void* const* peer_base,
-                           int world, int64_t rows_offset, int64_t rinv_offset, int64_t row0, void* stream);
+                           int world, int rank, int64_t rows_offset, int64_t rinv_offset, int64_t row0, int max_blocks,
+                           void* stream);
 
 /* Copy n_seg (<= 4) local f32 vectors src[k][0..n[k]) to byte offset dst_offset[k] of every rank's buffer
  * (the statistics exchange after the forward sweep).  src, n, dst_offset are HOST arrays.  Publish with a barrier. */
 int clipnce_link_push_f32(const float* const* src, const int64_t* n, const int64_t* dst_offset, int n_seg,
-                          void* const* peer_base, int world, void* stream);
+                          void* const* peer_base, int world, int rank, void* stream);
 
 /* out[c] = sum over ranks of vals[c], c < cnt <= 8, in ONE kernel (push + barrier `phase` + fixed-order sum: every
  * rank gets bit-identical results).  Used for the scalar loss and for d logit_scale; being a barrier it also closes
