@@ -189,6 +189,11 @@ def run_ours(args, rank, local_rank, world):
             self.launches += 2 if k.get("want_dscale", True) else 1
             return self._timed("bwd", super().backward, *a, **k)
 
+        def backward_dx(self, *a, **k):
+            # contraction kernel + finish_rows (split sum, row dots, normalise backward) [+ the scalar reduction]
+            self.launches += 3 if k.get("want_dscale", True) else 2
+            return self._timed("bwd", super().backward_dx, *a, **k)
+
         def normalize(self, *a, **k):
             self.launches += 1
             return super().normalize(*a, **k)

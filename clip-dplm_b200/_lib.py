@@ -37,6 +37,8 @@ SIGNATURES = {
                         _sz, _vp],
     "clipnce_backward": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
                          _int, _int, _vp, _vp, _vp, _sz, _vp],
+    "clipnce_backward_dx": [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _f32,
+                            _int, _int, _vp, _int, _vp, _vp, _int, _vp, _vp, _sz, _vp],
     "clipnce_softmax_weights": [_vp, _i64, _f32, _vp, _vp],
     "clipnce_combine_lse": [_vp, _vp, _i64, _vp, _vp],
     "clipnce_normalize_backward": [_vp, _int, _vp, _vp, _vp, _i64, _i64, _vp, _int, _vp],

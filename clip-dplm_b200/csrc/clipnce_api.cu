@@ -279,7 +279,8 @@ int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype
   if (tc_bwd > m) m = tc_bwd;
   if (w.bytes > m) m = w.bytes;
   if (simt_bwd > m) m = simt_bwd;
-  *out = m + 256;
+  // clipnce_backward_dx keeps the fp32 gradient of the normalised rows in the workspace instead of a caller buffer
+  *out = round_up(m + 256, 256) + round_up(sizeof(float) * (size_t)n_rows * (size_t)d, 256);
   return 0;
 }
 
@@ -419,11 +420,22 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
   return 0;
 }
 
-int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
-                     const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
-                     const float* scale_dev, const float* row_m, const float* row_w, const float* col_m, const float* col_w, float diag_w,
-                     float grad_out, int dtype, int flags, float* dx_hat, float* d_scale_sum, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+// What clipnce_backward_dx asks the contraction to leave undone: the pair kernels' split partials stay unsummed and the
+// row dots untaken -- finish_rows does all of it in one pass together with the normalise backward.
+struct Deferred {
+  const float* parts = nullptr;
+  int n_split = 1;
+  bool ds_pending = false;
+};
+
+int backward_impl(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
+                  const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                  const float* scale_dev, const float* row_m, const float* row_w, const float* col_m, const float* col_w, float diag_w,
+                  float grad_out, int dtype, int flags, float* dx_hat, float* d_scale_sum, void* workspace,
+                  size_t workspace_bytes, void* stream, Deferred* defer) {
   if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !dx_hat || !workspace)
     return fail(CLIPNCE_EINVAL, "backward: null pointer");
   if ((col_m == nullptr) != (col_w == nullptr)) return fail(CLIPNCE_EINVAL, "backward: col_m and col_w go together");
@@ -456,6 +468,12 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
     float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part_bytes);
     p.dx = n_split > 1 ? dx_part : dx_hat;
     if ((rc = launch_pair_bwd(x, y, p, st))) return rc;
+    if (defer) {
+      defer->parts = p.dx;
+      defer->n_split = n_split;
+      defer->ds_pending = d_scale_sum != nullptr;
+      return 0;
+    }
     if (n_split > 1) {
       const int64_t n4 = n_rows * d / 4;
       aux::sum_splits<<<(unsigned)ceil_div(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(dx_part), n_split, n4,
@@ -528,6 +546,81 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
   return 0;
 }
 
+}  // namespace
+
+extern "C" {
+
+int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
+                     const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                     const float* scale_dev, const float* row_m, const float* row_w, const float* col_m, const float* col_w, float diag_w,
+                     float grad_out, int dtype, int flags, float* dx_hat, float* d_scale_sum, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return backward_impl(x, y, y_t, ld_t, rinv_x, rinv_y, n_rows, n_cols, d, diag_offset, scale, scale_dev, row_m, row_w, col_m,
+                       col_w, diag_w, grad_out, dtype, flags, dx_hat, d_scale_sum, workspace, workspace_bytes, stream, nullptr);
+}
+
+int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t ld_t, const float* rinv_x,
+                        const float* rinv_y, int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                        const float* scale_dev, const float* row_m, const float* row_w, const float* col_m,
+                        const float* col_w, float diag_w, int dtype, int flags, const void* x_orig, int in_dtype,
+                        const float* grad_scale, void* dx, int out_dtype, float* d_scale_sum, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!x_orig || !dx) return fail(CLIPNCE_EINVAL, "backward_dx: null pointer");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "backward_dx: bad dtype");
+  if (n_rows < 1 || d < 1) return fail(CLIPNCE_EINVAL, "backward_dx: bad shape");
+  if (in_dtype == dtype && x_orig != x) return fail(CLIPNCE_EINVAL, "backward_dx: x_orig of the compute type must be x itself");
+  if (dtype == CLIPNCE_F32 && in_dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "backward_dx: fp32 compute needs fp32 rows");
+  const size_t slab = round_up(sizeof(float) * (size_t)n_rows * (size_t)d, 256);
+  if (!workspace || workspace_bytes < slab + 256) return fail(CLIPNCE_EWORKSPACE, "backward_dx: workspace %zu too small", workspace_bytes);
+  const size_t core_bytes = (workspace_bytes - slab) & ~(size_t)255;
+  float* dx_hat = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + core_bytes);
+  Deferred df;
+  df.parts = dx_hat;
+  int rc = backward_impl(x, y, y_t, ld_t, rinv_x, rinv_y, n_rows, n_cols, d, diag_offset, scale, scale_dev, row_m, row_w, col_m,
+                         col_w, diag_w, 1.0f, dtype, flags, dx_hat, d_scale_sum, workspace, core_bytes, stream, &df);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const int64_t n_blk = ceil_div(n_rows, 8);
+  const int di = (int)d;
+  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  if (smem > 48 * 1024) {   // rows too long to stage: the three separate passes
+    if (df.n_split > 1) {
+      const int64_t n4 = n_rows * d / 4;
+      aux::sum_splits<<<(unsigned)ceil_div(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(df.parts), df.n_split, n4,
+                                                                     reinterpret_cast<float4*>(dx_hat));
+    }
+    if (df.ds_pending) {
+      float* part = reinterpret_cast<float*>(workspace);
+      aux::rowdot_partials<<<(unsigned)n_blk, 256, 0, st>>>((const __nv_bfloat16*)x, rinv_x, dx_hat, n_rows, di, part);
+      aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(part, (int)n_blk, 1.f, d_scale_sum);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return clipnce_normalize_backward(x_orig, in_dtype, rinv_x, dx_hat, grad_scale, n_rows, d, dx, out_dtype, stream);
+  }
+  float* ds_part = df.ds_pending ? reinterpret_cast<float*>(workspace) : nullptr;   // [n_blk] at the workspace start
+  const int64_t slab_elems = n_rows * d;
+  const unsigned grid = (unsigned)n_blk;
+#define FINISH(TC, TI, TO)                                                                                              \
+  aux::finish_rows<TC, TI, TO><<<grid, 256, smem, st>>>(df.parts, df.n_split, slab_elems, (const TC*)x, (const TI*)x_orig, \
+                                                        rinv_x, grad_scale, n_rows, di, (TO*)dx, ds_part)
+  if (dtype == CLIPNCE_BF16 && in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+  else if (dtype == CLIPNCE_BF16 && in_dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, __nv_bfloat16, float);
+  else if (dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, float, __nv_bfloat16);
+  else if (dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, float, float);
+  else if (out_dtype == CLIPNCE_BF16) FINISH(float, float, __nv_bfloat16);
+  else FINISH(float, float, float);
+#undef FINISH
+  CUDA_TRY(cudaGetLastError());
+  if (df.ds_pending) {
+    aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)n_blk, 1.f, d_scale_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"
+
 namespace {
 int topk_kt(int k) { return k <= 1 ? 1 : (k <= 10 ? 10 : 16); }
 struct TopkPlan {
@@ -548,6 +641,8 @@ int topk_plan(int64_t n_q, int64_t n_lib, int64_t d, int k, int dtype, TopkPlan*
   return 0;
 }
 }  // namespace
+
+extern "C" {
 
 int clipnce_topk_workspace_bytes(int64_t n_q, int64_t n_lib, int64_t d, int k, int dtype, size_t* out) {
   if (!out) return fail(CLIPNCE_EINVAL, "topk_workspace_bytes: null pointer");

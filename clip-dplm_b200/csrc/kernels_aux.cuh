@@ -257,6 +257,57 @@ __global__ void rowdot_partials(const TI* __restrict__ x, const float* __restric
   if (threadIdx.x == 0) part[blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) + ((sh[4] + sh[5]) + (sh[6] + sh[7]));
 }
 
+// The tail of one backward side in ONE pass over the gradient (one warp per row, the row staged in shared memory):
+//   g_i   = sum over the n_split partial slabs of the column-sweep work items (fixed order; n_split = 1: the finished row)
+//   part  = sum over the block's 8 rows of rinv_i <xc_i, g_i>        (= <xhat_i, dxhat_i>: sum G.S, d logit_scale)
+//   dx_i  = rinv_i (g_i - xhat_i (xhat_i . g_i)) * grad_scale        (normalise backward; clamped rows: g_i rinv_i)
+// xc = the rows the contraction saw (compute type), xo = the caller's rows (their own type): the same pointer for bf16
+// inputs.  Replaces sum_splits + rowdot_partials + normalize_rows_bwd (three passes over [n,d] fp32).
+template <typename TC, typename TI, typename TO>
+__global__ void finish_rows(const float* __restrict__ parts, int n_split, int64_t slab, const TC* __restrict__ xc,
+                            const TI* __restrict__ xo, const float* __restrict__ rinv,
+                            const float* __restrict__ grad_scale, int64_t n, int d, TO* __restrict__ dx,
+                            float* __restrict__ ds_part) {
+  extern __shared__ float g_sh[];   // [8][d]
+  __shared__ float dot_sh[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 8 + w;
+  float* g = g_sh + (size_t)w * d;
+  float dot_c = 0.f;
+  if (row < n) {
+    const float ri = rinv[row];
+    const float gs = grad_scale ? grad_scale[0] : 1.f;
+    const float* pr = parts + row * d;
+    const TC* xcr = xc + row * d;
+    const TI* xor_ = xo + row * d;
+    const bool same = reinterpret_cast<const void*>(xc) == reinterpret_cast<const void*>(xo);
+    float dot_o = 0.f;
+    for (int k = lane; k < d; k += 32) {
+      float acc = pr[k];
+      for (int s = 1; s < n_split; ++s) acc += pr[(int64_t)s * slab + k];
+      g[k] = acc;
+      const float vc = ld_f(xcr + k);
+      dot_c = fmaf(vc, acc, dot_c);
+      if (!same) dot_o = fmaf(ld_f(xor_ + k), acc, dot_o);
+    }
+    dot_c = warp_sum(dot_c) * ri;
+    dot_o = same ? dot_c : warp_sum(dot_o) * ri;
+    const bool clamped = ri >= 0.5f / kNormEps;
+    if (clamped) dot_o = 0.f;
+    __syncwarp();
+    for (int k = lane; k < d; k += 32) {
+      const float xh = ld_f(xor_ + k) * ri;
+      st_f(dx + row * d + k, (g[k] - xh * dot_o) * (ri * gs));
+    }
+  }
+  if (ds_part != nullptr) {
+    if (lane == 0) dot_sh[w] = dot_c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      ds_part[blockIdx.x] = ((dot_sh[0] + dot_sh[1]) + (dot_sh[2] + dot_sh[3])) + ((dot_sh[4] + dot_sh[5]) + (dot_sh[6] + dot_sh[7]));
+  }
+}
+
 // *dst += coef * sum_p part[p]: 256 threads, strided fp64 partial sums + a fixed-order tree (deterministic).
 __global__ void reduce_scalar_partials_par(const float* __restrict__ part, int n_part, float coef, float* __restrict__ dst) {
   __shared__ double sh[256];

@@ -132,6 +132,26 @@ class CudaEngine:
                                              _p(ws), ws.numel(), _stream()), "backward")
         return dx, ds
 
+    def backward_dx(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, x_orig,
+                    out_dtype, grad_scale=None, flags=0, want_dscale=True, scale_dev=None):
+        """One backward side including the normalise backward -> dx [n_rows,d] in ``out_dtype`` (gradient of the caller's
+        rows ``x_orig``), d_scale_sum [1] f32 (or None).  The fp32 gradient of the normalised rows stays in the workspace."""
+        n_rows, d = x.shape
+        n_cols = y.shape[0]
+        dev = x.device
+        self._chk(x_orig, (torch.bfloat16, torch.float32), "x_orig")
+        ws = self.workspace(n_rows, n_cols, d, x.dtype, flags, dev)
+        dx = torch.empty((n_rows, d), dtype=out_dtype, device=dev)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+        ld_t = y_t.shape[1] if y_t is not None else 0
+        xo = x if x_orig.dtype == x.dtype else x_orig
+        _lib.check(self.lib.clipnce_backward_dx(_p(x), _p(y), _p(y_t), ld_t, _p(rinv_x), _p(rinv_y), n_rows, n_cols, d,
+                                                int(diag_offset), float(scale), _p(scale_dev), _p(row_m), _p(row_w),
+                                                _p(col_m), _p(col_w), float(diag_w), _DT[x.dtype], flags, _p(xo),
+                                                _DT[xo.dtype], _p(grad_scale), _p(dx), _DT[out_dtype], _p(ds), _p(ws),
+                                                ws.numel(), _stream()), "backward_dx")
+        return dx, ds
+
     def softmax_weights(self, l, coef):
         out = torch.empty_like(l)
         _lib.check(self.lib.clipnce_softmax_weights(_p(l), l.numel(), float(coef), _p(out), _stream()), "softmax_weights")

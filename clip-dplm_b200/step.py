@@ -141,19 +141,19 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     diag_w = 1.0 / n_glob
     kw = {"scale_dev": st.scale_dev} if st.scale_dev is not None else {}
 
-    # side A: local rows of A x all columns -> dA_hat (complete) and sum G.S over the local row block
-    da_hat, ds = engine.backward(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w,
-                                 col_m, col_w, diag_w, 1.0, st.flags, want_dscale=True, **kw)
-    da = engine.normalize_backward(st.a, st.rinv_a, da_hat, grad_dtype_a or st.a.dtype, grad_scale)
-    # side B: local rows of B (the positive-carrying columns of this rank) x ALL rows of A -> dB_hat, complete as well:
+    # side A: local rows of A x all columns -> dA (normalise backward fused into the tail) and sum G.S over the local
+    # row block
+    da, ds = engine.backward_dx(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w, col_m, col_w,
+                                diag_w, st.a, grad_dtype_a or st.a.dtype, grad_scale, st.flags, want_dscale=True, **kw)
+    # side B: local rows of B (the positive-carrying columns of this rank) x ALL rows of A -> dB, complete as well:
     # the column statistics of the local block play the row role, the gathered row statistics the column role
     xa_t = None
     if st.want_t:
         _, xa_t = engine.stage(st.xa, st.compute_dtype, want_t=True)
-    db_hat, _ = engine.backward(st.b_c, st.xa, xa_t, st.rinv_b, st.rinv_xa, off, st.scale,
-                                col_m[off:off + n].contiguous(), col_w[off:off + n].contiguous(),
-                                st.row_m_all, row_w_all, diag_w, 1.0, st.flags, want_dscale=False, **kw)
-    db = engine.normalize_backward(st.b, st.rinv_b, db_hat, grad_dtype_b or st.b.dtype, grad_scale)
+    db, _ = engine.backward_dx(st.b_c, st.xa, xa_t, st.rinv_b, st.rinv_xa, off, st.scale,
+                               col_m[off:off + n].contiguous(), col_w[off:off + n].contiguous(),
+                               st.row_m_all, row_w_all, diag_w, st.b, grad_dtype_b or st.b.dtype, grad_scale, st.flags,
+                               want_dscale=False, **kw)
     if st.xchg is not None:   # sum over the ranks' row blocks; as a barrier it also closes the step (exchange.py)
         ds = st.xchg.sum_scalars(ds, _exchange.PHASE_CLOSE)
         st.xchg.release()

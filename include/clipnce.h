@@ -141,6 +141,26 @@ int clipnce_backward(const void* x, const void* y, const void* y_t, int64_t ld_t
                      int dtype, int flags, float* dx_hat, float* d_scale_sum,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * clipnce_backward followed by clipnce_normalize_backward as ONE call: returns the gradient of the caller's rows,
+ *     dx_i = rinv_i (g_i - xhat_i (xhat_i . g_i)) * grad_scale,   g = s * G Yhat  (grad_out = 1),
+ * in out_dtype, and *d_scale_sum += sum_ij G_ij S_ij.  The fp32 gradient of the normalised rows never leaves the
+ * workspace: the per-work-item partial gradients of the CTA-pair kernels (column sweep split over the SMs when there
+ * are few row blocks -- the row-sharded step), the row dots <xhat_i, g_i> that give sum G.S, and the normalise backward
+ * are finished by one pass (`aux::finish_rows`) instead of three.
+ * x_orig [n_rows,d] in_dtype: the caller's rows (x itself when in_dtype == dtype; fp32 rows of a bf16 step otherwise).
+ * grad_scale: optional DEVICE scalar, the upstream gradient of the loss (NULL = 1).
+ * workspace: clipnce_workspace_bytes() for these shapes (it includes the [n_rows,d] fp32 slab this call uses).
+ */
+int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t ld_t,
+                        const float* rinv_x, const float* rinv_y,
+                        int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                        const float* scale_dev,
+                        const float* row_m, const float* row_w, const float* col_m, const float* col_w,
+                        float diag_w, int dtype, int flags,
+                        const void* x_orig, int in_dtype, const float* grad_scale, void* dx, int out_dtype,
+                        float* d_scale_sum, void* workspace, size_t workspace_bytes, void* stream);
+
 /* w_i = coef / l_i  (l = +inf -> 0).  Builds row_w / col_w from the forward's sums. */
 int clipnce_softmax_weights(const float* l, int64_t n, float coef, float* w, void* stream);
 

@@ -85,6 +85,12 @@ class TorchCpuEngine:
         ds = (grad_out * (G * S).sum()).reshape(1) if want_dscale else None
         return dx, ds
 
+    def backward_dx(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, x_orig,
+                    out_dtype, grad_scale=None, flags=0, want_dscale=True, scale_dev=None):
+        dx_hat, ds = self.backward(x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, 1.0,
+                                   flags, want_dscale=want_dscale, scale_dev=scale_dev)
+        return self.normalize_backward(x_orig, rinv_x, dx_hat, out_dtype, grad_scale), ds
+
     def softmax_weights(self, l, coef):
         return coef / l
 
