@@ -227,6 +227,9 @@ def run_ours(args, rank, local_rank, world):
             self.launches += 1
             return super().link_barrier(*a, **k)
 
+        def link_copy(self, *a, **k):      # copy engines: no kernel launch
+            return super().link_copy(*a, **k)
+
         def link_push_f32(self, *a, **k):
             self.launches += 1
             return super().link_push_f32(*a, **k)
@@ -267,7 +270,7 @@ def run_ours(args, rank, local_rank, world):
             return inner
 
         for nm in ("normalize", "stage", "softmax_weights", "combine_lse", "normalize_backward", "loss", "link_push_rows",
-                   "link_barrier", "link_push_f32", "link_sum_scalars", "combine_partials"):
+                   "link_barrier", "link_copy", "link_push_f32", "link_sum_scalars", "combine_partials"):
             setattr(eng, nm, wrap(nm, getattr(eng, nm)))
         _xchg_mod._all_gather = wrap("all_gather", _xchg_mod._all_gather)
         _orig_ar = dist.all_reduce

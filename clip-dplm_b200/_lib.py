@@ -48,6 +48,7 @@ SIGNATURES = {
     "clipnce_link_control_bytes": [ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
     "clipnce_link_barrier": [ctypes.POINTER(_vp), _int, _int, _int, _vp],
     "clipnce_link_push_rows": [_vp, _int, _i64, _i64, _int, ctypes.POINTER(_vp), _int, _int, _i64, _i64, _i64, _int, _vp],
+    "clipnce_link_copy": [_vp, _sz, ctypes.POINTER(_vp), _int, _int, _i64, _vp],
     "clipnce_link_push_f32": [ctypes.POINTER(_vp), ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, ctypes.POINTER(_vp),
                               _int, _int, _vp],
     "clipnce_link_sum_scalars": [_vp, _int, ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp],

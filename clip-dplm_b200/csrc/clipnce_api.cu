@@ -784,8 +784,12 @@ int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, in
   if (in_dtype == CLIPNCE_BF16 && c_dtype == CLIPNCE_BF16 && (d % 8 != 0 || !aligned16(x)))
     return fail(CLIPNCE_EINVAL, "link_push_rows: bf16 rows need d %% 8 == 0 and 16-byte alignment");
   cudaStream_t st = as_stream(stream);
-  // foreground: one warp per row over the whole GPU; background (max_blocks > 0): a few fat blocks, grid-stride
-  const int wpb = max_blocks > 0 ? 32 : 8;
+  // foreground: one warp per row over the whole GPU.  Background (max_blocks > 0): a few fat grid-stride blocks
+  // (measured on 2 GPUs beside the forward sweep: 8 x 1024 threads cost it 1.60 ms -> small blocks 1.74 ms: blocks of
+  // another kernel are not placed next to a resident CTA pair, they take SMs as pairs retire, and many small blocks
+  // take many).  The step itself moves the A rows with the copy engines instead (clipnce_link_copy).
+  static const int bg_warps = [] { const char* e = getenv("CLIPNCE_LINK_BG_WARPS"); const int v = e ? atoi(e) : 32; return v >= 1 && v <= 32 ? v : 32; }();
+  const int wpb = max_blocks > 0 ? bg_warps : 8;
   int64_t nblk = ceil_div(n, wpb);
   if (max_blocks > 0 && nblk > max_blocks) nblk = max_blocks;
   dim3 grid((unsigned)nblk), block(32 * wpb);
@@ -799,6 +803,20 @@ int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, in
   else
     link::push_rows<float, float><<<grid, block, 0, st>>>((const float*)x, n, di, peers, world, rank, rows_offset, rinv_offset, row0);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_link_copy(const void* src, size_t bytes, void* const* peer_base, int world, int rank, int64_t dst_offset,
+                      void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, rank, &peers);
+  if (rc) return rc;
+  if (!src || bytes < 1 || dst_offset < link::CONTROL_BYTES) return fail(CLIPNCE_EINVAL, "link_copy: bad argument");
+  cudaStream_t st = as_stream(stream);
+  for (int k = 1; k <= world; ++k) {   // start behind the own rank: the ranks' copies fan out over different peers
+    const int r = (rank + k) % world;
+    CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(peers.base[r]) + dst_offset, src, bytes, cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 

@@ -202,6 +202,12 @@ class CudaEngine:
         _lib.check(self.lib.clipnce_link_push_rows(_p(x), _DT[x.dtype], n, d, _DT[c_dtype], peers, world, rank, rows_off,
                                                    rinv_off, row0, max_blocks, _stream()), "link_push_rows")
 
+    def link_copy(self, src, peers, world, rank, dst_off):
+        """Copy-engine broadcast of a contiguous local tensor to byte offset ``dst_off`` of every rank's buffer."""
+        self._chk(src, (torch.bfloat16, torch.float32), "rows")
+        _lib.check(self.lib.clipnce_link_copy(_p(src), src.numel() * src.element_size(), peers, world, rank, dst_off,
+                                              _stream()), "link_copy")
+
     def link_push_f32(self, srcs, dst_offs, peers, world, rank):
         k = len(srcs)
         for t in srcs:

@@ -27,8 +27,11 @@ import torch
 import torch.distributed as dist
 
 PHASE_COLS, PHASE_STATS, PHASE_LOSS, PHASE_CLOSE = 0, 1, 2, 3
-# thread blocks (of 1024 threads) of the background push of the A rows: it has the whole forward sweep to finish in, and
-# every block costs the sweep an SM (measured on 8 GPUs: a full-grid push beside the sweep slowed it from 365 to 435 us)
+# The A rows travel beside the forward sweep.  Every SM a push kernel takes costs the sweep a CTA-pair slot and -- its grid
+# being sized in whole waves of slots -- part of an extra wave (a full-grid push: 365 -> 435 us on 8 GPUs; 8 fat blocks:
+# +20 us on 8 GPUs, +80 us on 2 and 4), so by default the copy engines move them (CLIPNCE_LINK_BG=kernel for the push kernel
+# with BACKGROUND_BLOCKS blocks of 1024 threads).
+BACKGROUND_COPY_ENGINE = os.environ.get("CLIPNCE_LINK_BG", "copy").lower() != "kernel"
 BACKGROUND_BLOCKS = int(os.environ.get("CLIPNCE_LINK_BG_BLOCKS", "8"))
 
 
@@ -171,9 +174,17 @@ class PeerExchange:
     def gather_rows_begin(self, a, a_c, rinv_a, compute_dtype):
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)          # behind barrier 0: the columns have the links to themselves
+        lo = self.rank * self.n
         with torch.cuda.stream(self.side):
-            self.engine.link_push_rows(a, compute_dtype, self.peers, self.world, self.rank, self.o_xa, self.o_rinv_xa,
-                                       self.rank * self.n, max_blocks=BACKGROUND_BLOCKS)
+            if BACKGROUND_COPY_ENGINE:
+                # the rows already exist in the compute type (a_c) and their norms too: nothing to compute, so the
+                # copy engines move them and the forward sweep keeps every SM
+                esz = a_c.element_size()
+                self.engine.link_copy(a_c, self.peers, self.world, self.rank, self.o_xa + lo * self.d * esz)
+                self.engine.link_copy(rinv_a, self.peers, self.world, self.rank, self.o_rinv_xa + lo * 4)
+            else:
+                self.engine.link_push_rows(a, compute_dtype, self.peers, self.world, self.rank, self.o_xa, self.o_rinv_xa,
+                                           lo, max_blocks=BACKGROUND_BLOCKS)
         self._side_busy = True
 
     def gather_rows_end(self):

@@ -234,6 +234,12 @@ int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, in
                            int world, int rank, int64_t rows_offset, int64_t rinv_offset, int64_t row0, int max_blocks,
                            void* stream);
 
+/* Copy `bytes` from src to byte offset dst_offset of every rank's buffer with the COPY ENGINES (cudaMemcpyAsync per
+ * peer, no SM involved): the background gather of rows that travel beside a contraction kernel -- the A rows, read by
+ * the backward only -- which keeps every SM.  Publish with a barrier on a stream that waited for this one. */
+int clipnce_link_copy(const void* src, size_t bytes, void* const* peer_base, int world, int rank, int64_t dst_offset,
+                      void* stream);
+
 /* Copy n_seg (<= 4) local f32 vectors src[k][0..n[k]) to byte offset dst_offset[k] of every rank's buffer
  * (the statistics exchange after the forward sweep).  src, n, dst_offset are HOST arrays.  Publish with a barrier. */
 int clipnce_link_push_f32(const float* const* src, const int64_t* n, const int64_t* dst_offset, int n_seg,

@@ -241,7 +241,7 @@ def _worker_single(rank, world, port, q):
             a = torch.randn(n, d, generator=g).cuda()
             b_c, rinv_b, y, rinv_y = x.gather_cols(b, torch.bfloat16)
             ra, _ = eng.normalize(a)
-            x.gather_rows_begin(a, None, ra, torch.bfloat16)
+            x.gather_rows_begin(a, a.bfloat16(), ra, torch.bfloat16)
             stats = [torch.rand(n, generator=g).cuda() + 0.5 for _ in range(2)] + \
                     [torch.rand(n + 7, generator=g).cuda() + 0.5 for _ in range(2)]
             cm, cl, rm, rl = x.exchange_stats(stats[0], stats[1], stats[2], stats[3], False, True)
