@@ -465,8 +465,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=65536, help="global batch")
-    ap.add_argument("--d", type=int, default=512)
+    # (--global-batch / --embed-dim: torchrun's own parser rejects "--n" as an ambiguous abbreviation of its options)
+    ap.add_argument("--n", "--global-batch", dest="n", type=int, default=65536, help="global batch")
+    ap.add_argument("--d", "--embed-dim", dest="d", type=int, default=512)
     ap.add_argument("--ref-rows", type=int, default=1024, help="row block of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")

@@ -601,9 +601,20 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
   float* ds_part = df.ds_pending ? reinterpret_cast<float*>(workspace) : nullptr;   // [n_blk] at the workspace start
   const int64_t slab_elems = n_rows * d;
   const unsigned grid = (unsigned)n_blk;
-#define FINISH(TC, TI, TO)                                                                                              \
-  aux::finish_rows<TC, TI, TO><<<grid, 256, smem, st>>>(df.parts, df.n_split, slab_elems, (const TC*)x, (const TI*)x_orig, \
-                                                        rinv_x, grad_scale, n_rows, di, (TO*)dx, ds_part)
+  // 16-byte accesses when every row base is 4-element aligned (always so for the tensor-core path: d % 8 == 0)
+  const bool v4 = d % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x_orig) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(df.parts) & 15u) == 0;
+#define FINISH(TC, TI, TO)                                                                                                 \
+  do {                                                                                                                     \
+    if (v4)                                                                                                                \
+      aux::finish_rows_v4<TC, TI, TO><<<grid, 256, smem, st>>>(df.parts, df.n_split, slab_elems, (const TC*)x,             \
+                                                               (const TI*)x_orig, rinv_x, grad_scale, n_rows, di, (TO*)dx, \
+                                                               ds_part);                                                   \
+    else                                                                                                                   \
+      aux::finish_rows<TC, TI, TO><<<grid, 256, smem, st>>>(df.parts, df.n_split, slab_elems, (const TC*)x,                \
+                                                            (const TI*)x_orig, rinv_x, grad_scale, n_rows, di, (TO*)dx,    \
+                                                            ds_part);                                                      \
+  } while (0)
   if (dtype == CLIPNCE_BF16 && in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
   else if (dtype == CLIPNCE_BF16 && in_dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, __nv_bfloat16, float);
   else if (dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH(__nv_bfloat16, float, __nv_bfloat16);

@@ -308,6 +308,87 @@ __global__ void finish_rows(const float* __restrict__ parts, int n_split, int64_
   }
 }
 
+// four consecutive elements (4-element aligned) as floats / from floats
+template <typename T> __device__ __forceinline__ float4 ld4_f(const T* p);
+template <> __device__ __forceinline__ float4 ld4_f<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4_f<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void st4_f(T* p, float4 v);
+template <> __device__ __forceinline__ void st4_f<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void st4_f<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// finish_rows with 16-byte accesses (d % 4 == 0, all row bases 4-element aligned): every lane owns four consecutive
+// features per 128-feature stripe; the n_split partial rows are independent 16-byte loads (memory-level parallelism is
+// what this pass lives on: at n_split = 8 the scalar version took 52 us for 8192 x 512 against 25 us of sum_splits alone).
+template <typename TC, typename TI, typename TO>
+__global__ void finish_rows_v4(const float* __restrict__ parts, int n_split, int64_t slab, const TC* __restrict__ xc,
+                               const TI* __restrict__ xo, const float* __restrict__ rinv,
+                               const float* __restrict__ grad_scale, int64_t n, int d, TO* __restrict__ dx,
+                               float* __restrict__ ds_part) {
+  extern __shared__ __align__(16) float g4_sh[];   // [8][d]
+  __shared__ float dot_sh[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 8 + w;
+  float* g = g4_sh + (size_t)w * d;
+  float dot_c = 0.f;
+  if (row < n) {
+    const float ri = rinv[row];
+    const float gs = grad_scale ? grad_scale[0] : 1.f;
+    const float* pr = parts + row * d;
+    const TC* xcr = xc + row * d;
+    const TI* xor_ = xo + row * d;
+    const bool same = reinterpret_cast<const void*>(xc) == reinterpret_cast<const void*>(xo);
+    float dot_o = 0.f;
+    for (int k = lane * 4; k < d; k += 128) {
+      float4 acc = ld4_f(pr + k);
+#pragma unroll 4
+      for (int s = 1; s < n_split; ++s) {
+        const float4 v = ld4_f(pr + (int64_t)s * slab + k);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(g + k) = acc;
+      const float4 vc = ld4_f(xcr + k);
+      dot_c = fmaf(vc.x, acc.x, dot_c); dot_c = fmaf(vc.y, acc.y, dot_c);
+      dot_c = fmaf(vc.z, acc.z, dot_c); dot_c = fmaf(vc.w, acc.w, dot_c);
+      if (!same) {
+        const float4 vo = ld4_f(xor_ + k);
+        dot_o = fmaf(vo.x, acc.x, dot_o); dot_o = fmaf(vo.y, acc.y, dot_o);
+        dot_o = fmaf(vo.z, acc.z, dot_o); dot_o = fmaf(vo.w, acc.w, dot_o);
+      }
+    }
+    dot_c = warp_sum(dot_c) * ri;
+    dot_o = same ? dot_c : warp_sum(dot_o) * ri;
+    if (ri >= 0.5f / kNormEps) dot_o = 0.f;   // clamped row: dx = g * rinv
+    const float k2 = ri * gs;
+    for (int k = lane * 4; k < d; k += 128) {   // every lane re-reads only what it wrote: no barrier needed
+      const float4 gv = *reinterpret_cast<const float4*>(g + k);
+      const float4 xv = ld4_f(xor_ + k);
+      float4 o;
+      o.x = (gv.x - xv.x * ri * dot_o) * k2;
+      o.y = (gv.y - xv.y * ri * dot_o) * k2;
+      o.z = (gv.z - xv.z * ri * dot_o) * k2;
+      o.w = (gv.w - xv.w * ri * dot_o) * k2;
+      st4_f(dx + row * d + k, o);
+    }
+  }
+  if (ds_part != nullptr) {
+    if (lane == 0) dot_sh[w] = dot_c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      ds_part[blockIdx.x] = ((dot_sh[0] + dot_sh[1]) + (dot_sh[2] + dot_sh[3])) + ((dot_sh[4] + dot_sh[5]) + (dot_sh[6] + dot_sh[7]));
+  }
+}
+
 // *dst += coef * sum_p part[p]: 256 threads, strided fp64 partial sums + a fixed-order tree (deterministic).
 __global__ void reduce_scalar_partials_par(const float* __restrict__ part, int n_part, float coef, float* __restrict__ dst) {
   __shared__ double sh[256];

@@ -369,3 +369,46 @@ def test_topk_negative_scores_and_shared_threshold(eng, monkeypatch):
     torch.cuda.synchronize()
     assert torch.allclose(s.cpu().double(), s_ref, atol=2e-5, rtol=0)
     assert torch.allclose(torch.gather(sim, 1, i.cpu()), s_ref, atol=2e-5, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# clipnce_backward_dx: backward side + split-partial sum + row dots + normalise backward in one call
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,split,in_dt,c_dt,out_dt", [
+    (3000, 512, 0, torch.bfloat16, torch.bfloat16, torch.bfloat16),     # 16-byte path, no split
+    (3000, 512, 3, torch.bfloat16, torch.bfloat16, torch.bfloat16),     # 16-byte path over split partials
+    (2100, 256, 2, torch.float32, torch.bfloat16, torch.float32),       # fp32 rows of a bf16 step (x_orig != x)
+    (1111, 128, 4, torch.bfloat16, torch.bfloat16, torch.float32),
+    (300, 50, 0, torch.float32, torch.float32, torch.float32),          # exact path, d % 4 != 0: scalar finish
+    (260, 192, 0, torch.bfloat16, torch.bfloat16, torch.bfloat16),      # single-CTA tensor-core kernels (transposed operand)
+])
+def test_backward_dx_matches_unfused(eng, monkeypatch, n, d, split, in_dt, c_dt, out_dt):
+    """The fused call against the two calls it replaces (clipnce_backward -> clipnce_normalize_backward), on the same
+    statistics, with an upstream gradient on the device and one all-zero row (the clamp_min sub-gradient branch)."""
+    if split:
+        monkeypatch.setenv("CLIPNCE_SPLIT_STEPS", str(split))
+    else:
+        monkeypatch.delenv("CLIPNCE_SPLIT_STEPS", raising=False)
+    scale = 1 / 0.07
+    a, b = O.make_inputs(n, d, seed=5, mix=0.4)
+    a[7] = 0
+    xo, yo = a.cuda().to(in_dt), b.cuda().to(in_dt)
+    x, _ = eng.stage(xo, c_dt)
+    y, _ = eng.stage(yo, c_dt)
+    want_t = eng.uses_tensor_cores(c_dt, d, scale) and eng.needs_transposed(c_dt, d, scale)
+    y_t = eng.stage(y, c_dt, want_t=True)[1] if want_t else None
+    rx, _ = eng.normalize(xo)
+    ry, _ = eng.normalize(yo)
+    row_m, row_l, col_m, col_l, diag = eng.forward(x, y, rx, ry, 0, scale)
+    coef = 1.0 / (2 * n)
+    rw, cw = eng.softmax_weights(row_l, coef), eng.softmax_weights(col_l, coef)
+    gs = torch.tensor([2.5], device="cuda")
+    dx_hat, ds_ref = eng.backward(x, y, y_t, rx, ry, 0, scale, row_m, rw, col_m, cw, 1.0 / n, 1.0)
+    want = eng.normalize_backward(xo, rx, dx_hat, out_dt, gs)
+    got, ds = eng.backward_dx(x, y, y_t, rx, ry, 0, scale, row_m, rw, col_m, cw, 1.0 / n, xo, out_dt, gs)
+    torch.cuda.synchronize()
+    tol = 1e-2 if out_dt == torch.bfloat16 else 2e-5     # one bf16 ulp / fp32 rounding of a reordered dot product
+    err = (got.float() - want.float()).abs().max()
+    assert float(err) <= tol * float(want.float().abs().max()), float(err)
+    assert torch.isfinite(got.float()).all()
+    assert abs(float(ds) - float(ds_ref)) <= 1e-4 * abs(float(ds_ref)) + 1e-7
