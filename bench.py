@@ -131,6 +131,12 @@ def reference_step_sample(n_global, d, rows, steps, warmup, threads):
     return rows / t_med, t_med
 
 
+def workload_desc(n, d):
+    """The same description on both arms (ours computes in bf16, the reference arm in fp32 on the same rounded values)."""
+    return (f"symmetric InfoNCE fwd+bwd, global batch {n}, d={d}, bf16 embeddings (b = 0.5a + 0.5 noise), "
+            f"logit_scale = ln(1/0.07)")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -142,8 +148,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_med, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"symmetric InfoNCE fwd+bwd, global batch {args.n}, d={args.d}", "global_batch": args.n,
-                       "d": args.d},
+            "config": {"workload": workload_desc(args.n, args.d), "global_batch": args.n, "d": args.d},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -434,8 +439,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"symmetric InfoNCE fwd+bwd, global batch {n_global}, d={d}, bf16 embeddings "
-                               f"(b = 0.5a + 0.5 noise), logit_scale = ln(1/0.07)", "global_batch": n_global, "d": d,
+        "config": {"workload": workload_desc(n_global, d), "global_batch": n_global, "d": d,
                    "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                    "comm": {"link": "own kernels over NVLink peer memory (fused normalise+gather, pushes, device barriers)",
                             "nccl": "NCCL collectives", "none": "none"}.get(comm, comm),
