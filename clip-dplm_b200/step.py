@@ -82,7 +82,9 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
     rinv_a, _ = engine.normalize(a)
     a_c, _ = engine.stage(a, compute_dtype)
     if world > 1:
-        xchg = _exchange.open_exchange(engine, group, n_local, d, n_global + n_extra, compute_dtype, a.device)
+        # the exchange buffers do not depend on the number of extra columns (a hard-negative cache that grows from step
+        # to step would otherwise need a new set -- a host-side rendezvous -- for every length)
+        xchg = _exchange.open_exchange(engine, group, n_local, d, n_global, compute_dtype, a.device)
         b_c, rinv_b, y, rinv_y = xchg.gather_cols(b, compute_dtype)
         if need_grad:   # side B of the backward streams every rank's A rows; they travel behind the forward sweep
             xchg.gather_rows_begin(a, a_c, rinv_a, compute_dtype)
@@ -107,10 +109,14 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
     if world > 1:
         fixed = getattr(engine, "fixed_shift", None)
         fixed = bool(fixed is not None and fixed(compute_dtype, d, scale, flags))
-        col_m, col_l, row_m_all, row_l_all = xchg.exchange_stats(row_m, row_l, col_m, col_l, fixed, need_grad)
+        # only the batch's own columns are exchanged: extra negatives carry no positives, so their column statistics are
+        # never used (no column loss, no column soft-max: the sum is set to +inf below)
+        gm, gl, row_m_all, row_l_all = xchg.exchange_stats(row_m, row_l, col_m[:n_global], col_l[:n_global], fixed, need_grad)
+        col_m = torch.cat([gm, col_m[n_global:]]) if n_extra else gm
+        col_l = torch.cat([gl, col_l[n_global:]]) if n_extra else gl
         xa, rinv_xa = xchg.gather_rows_end() if need_grad else (None, None)
     if n_extra:
-        col_l[n_global:] = float("inf")   # extra negatives carry no positives: no column loss, no column soft-max
+        col_l[n_global:] = float("inf")
     loss = engine.loss(row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric)
     if world > 1:
         loss = xchg.sum_scalars(loss, _exchange.PHASE_LOSS)
