@@ -154,6 +154,12 @@ def _gloo_worker(rank, world, port, n, d, symmetric, n_extra, q):
         loss = fused_clip_loss(ac, bc, t, engine=TorchCpuEngine(), compute_dtype=torch.float64, group=dist.group.WORLD,
                                symmetric=symmetric, extra_cols=extra)
         loss.backward()
+        from clip_dplm_b200 import exchange
+        assert exchange.comm_kind(dist.group.WORLD) == "nccl"      # CPU tensors over gloo: the collectives implementation
+        with torch.no_grad():                                       # evaluation: no rows gathered for a backward
+            le = fused_clip_loss(ac, bc, t, engine=TorchCpuEngine(), compute_dtype=torch.float64, group=dist.group.WORLD,
+                                 symmetric=symmetric, extra_cols=extra)
+        assert abs(float(le) - float(loss.detach())) < 1e-12
         q.put((rank, float(loss.detach()), ac.grad.numpy(), bc.grad.numpy(), float(t.grad)))
     finally:
         dist.destroy_process_group()
