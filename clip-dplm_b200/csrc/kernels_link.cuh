@@ -103,8 +103,9 @@ __global__ void barrier(Peers peers, int world, int rank, int phase, unsigned lo
 // from the caller's rows and stores the row (in the compute type TO) and rinv into EVERY rank's gathered buffers at
 // global row  row0 + i  (the own copy included: the gathered matrix is complete on every rank).  Destinations are
 // visited starting behind the own rank, so that at any moment the ranks store to different peers (no ingress hot
-// spot at the switch).  Grid-stride over rows: a launch with few blocks is the background variant that leaves the SMs
-// to a contraction kernel running beside it.
+// spot at the switch).  Grid-stride over rows: a launch with few (fat) blocks is a background variant that leaves most SMs
+// to a contraction kernel running beside it -- the step itself uses the copy engines for that (clipnce_link_copy), which
+// leave it all of them.
 template <typename TI, typename TO>
 __global__ void push_rows(const TI* __restrict__ x, int64_t n, int d, Peers peers, int world, int rank, int64_t rows_off,
                           int64_t rinv_off, int64_t row0) {

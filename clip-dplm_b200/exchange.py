@@ -11,7 +11,7 @@ What the reference does with ``dist.all_gather`` x2 + ``torch.cat`` (old/clip_op
 `PeerExchange` (the product path on GPUs): kernels of this repository that store straight into the peers' HBM over
 NVLink / NVSwitch (csrc/kernels_link.cuh, include/clipnce.h "clipnce_link_*"); torch symmetric memory only provides the
 mapping of every rank's buffer into every process.  The normalise is fused into the gather kernel, the A rows travel
-on a side stream behind the forward sweep, statistics and scalars are one-kernel pushes with a device-side barrier;
+on a side stream beside the forward sweep (copy engines: the sweep keeps every SM), statistics and scalars are one-kernel pushes with a device-side barrier;
 epochs live on the device, so the step replays inside a CUDA graph.
 `CollectiveExchange`: the same steps as torch.distributed collectives -- the gloo CPU tests, and the NCCL baseline the
 peer path is measured against (``CLIPNCE_COMM=nccl`` or ``bench.py --comm nccl``).
@@ -103,7 +103,8 @@ class PeerExchange:
     matrices are what the backward reads) and returned by `release()`.
 
     Protocol (every rank issues the same sequence; phases are device-side barriers with their own epoch counters):
-        push B rows -> barrier 0 -> [forward sweep | push A rows on the side stream] -> push statistics -> barrier 1
+        push B rows -> barrier 0 -> [forward sweep | A rows by the copy engines on the side stream] -> push statistics
+        -> barrier 1
         -> ... -> sum_scalars(loss) = barrier 2 -> [backward] -> sum_scalars(d scale) = barrier 3.
     A rank passes barrier 3 (or 2 in a step without backward) only after every peer finished reading this step's
     buffers, so the next step may overwrite them without any further synchronisation.
