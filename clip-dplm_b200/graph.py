@@ -1,10 +1,11 @@
 """`GraphedClipStep`: the fused loss forward + backward of one fixed shape captured in a CUDA graph.
 
-One training step of the hot path is ~30 launches (the three contraction kernels, the HBM-bound helpers around them
-and, row-sharded, five NCCL collectives).  At the headline size on one GPU their launch gaps are ~1 % of the step; on
-8 GPUs, where the same work takes 2.6 ms, launch latency and Python become a fifth of it.  Because the logit scale is
-read on the device (``scale_dev``, include/clipnce.h) nothing in the step needs the host, so the whole step -- collectives
-included -- replays as one graph:
+One training step of the hot path is ~25 launches (the three contraction kernels, the HBM-bound helpers around them
+and, row-sharded, the exchange kernels and copy-engine copies of exchange.py).  At the headline size on one GPU their
+launch gaps are ~1 % of the step; on 8 GPUs, where the same work takes 2.4 ms, launch latency and Python would become a
+fifth of it.  Because the logit scale is read on the device (``scale_dev``, include/clipnce.h) and the exchange keeps its
+barrier epochs on the device, nothing in the step needs the host, so the whole step -- exchange included -- replays as
+one graph:
 
     step = GraphedClipStep(n_local, d, group=group)        # captures once (after eager warm-up steps)
     loss, d_a, d_b, d_logit_scale = step(a, b, logit_scale)
@@ -63,7 +64,7 @@ class GraphedClipStep:
 
     def close(self):
         """Drop the captured graph.  Call before ``dist.destroy_process_group()``: a live graph that holds captured NCCL
-        kernels stalls the communicator's teardown."""
+        kernels (the collectives baseline) stalls the communicator's teardown."""
         if self.graph is not None:
             torch.cuda.synchronize(self.device)
             self.graph.reset()
