@@ -137,6 +137,13 @@ def workload_desc(n, d):
             f"logit_scale = ln(1/0.07)")
 
 
+def config_dict(n, d):
+    """`config` of the JSON line -- byte-identical on both arms (what differs between them lives under `run`)."""
+    return {"workload": workload_desc(n, d), "global_batch": n, "d": d,
+            "l2": f"no flush: operands + outputs + partials of one step (>= {max(1, 8 * n * d // 1000000)} MB at this size; "
+                  "450 MB at N=65536) exceed the 126 MB L2"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -148,10 +155,50 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_med, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(args.n, args.d), "global_batch": args.n, "d": args.d},
+            "config": config_dict(args.n, args.d),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ parity
+def parity_check(step_fn, a, b, logit_scale, group, rank, world, n_rows_sample):
+    """One extra step OUTSIDE the timed region, compared with the sampled-row CPU oracle (oracle/sampled.py) at the
+    benchmarked shape: the loss against a blockwise pass over all N x N logits on the host, d logit_scale, and the
+    gradient rows dA[i], dB[j] of `n_rows_sample` random GLOBAL indices against all N columns / rows in float64.
+    N > 1: inputs and gradients of every rank are gathered to rank 0 first (NCCL, untimed) -- the sample covers all ranks'
+    shards.  -> the `parity` dict on rank 0, None elsewhere."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    loss, da, db, dls = step_fn()
+    torch.cuda.synchronize()
+
+    def gathered(x):
+        if world == 1:
+            return x
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
+
+    a_all, b_all, da_all, db_all = gathered(a), gathered(b), gathered(da), gathered(db)
+    if rank != 0:
+        return None
+    from oracle import sampled as SO
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    n = a_all.shape[0]
+    rng = np.random.default_rng(20261018)
+    k = min(n_rows_sample, n)
+    rows_a = np.sort(rng.choice(n, size=k, replace=False))
+    rows_b = np.sort(rng.choice(n, size=k, replace=False))
+    s = math.exp(float(logit_scale.detach()))
+    ref = SO.sampled_reference(a_all.float().cpu(), b_all.float().cpu(), s, rows_a, rows_b)
+    out = SO.compare(ref, float(loss), da_all[torch.as_tensor(rows_a, device=da_all.device)].float().cpu().numpy(),
+                     db_all[torch.as_tensor(rows_b, device=db_all.device)].float().cpu().numpy(), float(dls))
+    out.update({"against": "oracle/sampled.py: blockwise host pass over all N^2 logits (loss, d logit_scale) + float64 "
+                           "gradient rows of the sampled global indices", "n": int(n), "host_seconds": round(time.perf_counter() - t0, 1)})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -408,6 +455,18 @@ def run_ours(args, rank, local_rank, world):
     final_loss = float((gstep.out[0] if gstep is not None else step_resident()).detach())
     if not math.isfinite(final_loss):
         raise RuntimeError(f"bench: loss is not finite ({final_loss})")
+    parity = None
+    if not args.no_parity:
+        def step_for_parity():   # the step that was timed (the graph when there is one), its outputs read back
+            if gstep is not None:
+                gstep.replay()
+                return gstep.out[0], gstep.out[1], gstep.out[2], gstep.out[3]
+            ar, br = a.detach().requires_grad_(True), b.detach().requires_grad_(True)
+            ls = logit_scale.detach().clone().requires_grad_(True)
+            loss = fused_clip_loss(ar, br, ls, group=group, engine=eng)
+            loss.backward()
+            return loss.detach(), ar.grad, br.grad, ls.grad
+        parity = parity_check(step_for_parity, a, b, logit_scale, group, rank, world, args.parity_rows)
     if gstep is not None:
         gstep.close()     # before the process group goes away
     if world > 1:
@@ -439,12 +498,12 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_desc(n_global, d), "global_batch": n_global, "d": d,
-                   "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
-                   "comm": {"link": "own kernels over NVLink peer memory (fused normalise+gather, pushes, device barriers)",
-                            "nccl": "NCCL collectives", "none": "none"}.get(comm, comm),
-                   "loss": final_loss,
-                   "l2": "operands+outputs per step (>= 450 MB at N=65536) exceed the 126 MB L2"},
+        "config": config_dict(n_global, d),
+        "run": {"rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                "comm": {"link": "own kernels over NVLink peer memory (fused normalise+gather, pushes, device barriers)",
+                         "nccl": "NCCL collectives", "none": "none"}.get(comm, comm),
+                "loss": final_loss},
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_local * d * 2, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -460,6 +519,9 @@ def run_ours(args, rank, local_rank, world):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    if parity is not None and not parity["ok"]:
+        print(f"bench: PARITY FAILED against the oracle: {parity}", file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 def main():
@@ -474,6 +536,8 @@ def main():
     ap.add_argument("--d", "--embed-dim", dest="d", type=int, default=512)
     ap.add_argument("--ref-rows", type=int, default=1024, help="row block of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check of the benchmarked step")
+    ap.add_argument("--parity-rows", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")
     ap.add_argument("--timeline", default=None, help="write a kernel timeline of three steps (torch.profiler) to this file")
     ap.add_argument("--trace", action="store_true", help="print a per-phase device-time breakdown of the step to stderr")

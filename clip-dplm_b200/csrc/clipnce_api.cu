@@ -757,8 +757,8 @@ int make_peers(void* const* peer_base, int world, int rank, link::Peers* out) {
 unsigned long long link_timeout_ns() {
   static const unsigned long long ns = [] {
     const char* e = getenv("CLIPNCE_LINK_TIMEOUT_MS");
-    const long long ms = e ? atoll(e) : 10000;
-    return (unsigned long long)(ms > 0 ? ms : 10000) * 1000000ull;
+    const long long ms = e ? atoll(e) : 600000;   // 10 minutes, the order of NCCL's watchdog; a timeout is fatal (trap)
+    return (unsigned long long)(ms > 0 ? ms : 600000) * 1000000ull;
   }();
   return ns;
 }

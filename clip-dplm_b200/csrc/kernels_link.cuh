@@ -22,8 +22,8 @@ constexpr int MAX_SCALARS = 8;
 constexpr int64_t OFF_FLAGS = 0;                                        // u32 [MAX_PHASE][MAX_WORLD]   written by peers
 constexpr int64_t OFF_EPOCH = OFF_FLAGS + 4 * MAX_PHASE * MAX_WORLD;    // u32 [MAX_PHASE]              local only
 constexpr int64_t OFF_STATUS = OFF_EPOCH + 4 * MAX_PHASE;               // u32 [4]: [0] != 0 -> a barrier timed out
-constexpr int64_t OFF_SCALARS = OFF_STATUS + 16;                        // f32 [2 parity][MAX_WORLD][MAX_SCALARS]
-constexpr int64_t CONTROL_BYTES = ((OFF_SCALARS + 4 * 2 * MAX_WORLD * MAX_SCALARS + 255) / 256) * 256;
+constexpr int64_t OFF_SCALARS = OFF_STATUS + 16;                        // f32 [MAX_PHASE][2 parity][MAX_WORLD][MAX_SCALARS]
+constexpr int64_t CONTROL_BYTES = ((OFF_SCALARS + 4 * MAX_PHASE * 2 * MAX_WORLD * MAX_SCALARS + 255) / 256) * 256;
 
 struct Peers {
   void* base[MAX_WORLD];
@@ -59,8 +59,9 @@ __device__ __forceinline__ T* at(void* base, int64_t byte_off) {
 // Arrive at phase `phase` on every peer and wait for every peer's arrival (threads 0..world-1 of one block).  Returns
 // the epoch.  Everything this GPU enqueued before the calling kernel -- its stores into peer memory included -- is
 // ordered before the flag by the release (cumulative over the kernel boundary); peers' stores are visible to kernels
-// launched after this one.  A peer that never arrives (a crashed rank) trips the timeout: status[0] is set, later
-// barriers return at once, and the host finds the status word instead of a hung GPU.
+// launched after this one.  A peer that never arrives (a crashed rank) trips the timeout (minutes by default, like
+// NCCL's watchdog): that is FATAL -- status[0] records the phase for the host's post-mortem and the kernel traps, so the
+// step can never go on with unsynchronised peer buffers (the CUDA error surfaces at the next host synchronisation).
 __device__ __forceinline__ uint32_t barrier_arrive_wait(const Peers& peers, int world, int rank, int phase,
                                                         unsigned long long timeout_ns, uint32_t* epoch_sh) {
   char* mine = reinterpret_cast<char*>(peers.base[rank]);
@@ -78,15 +79,14 @@ __device__ __forceinline__ uint32_t barrier_arrive_wait(const Peers& peers, int 
     __threadfence_system();
     st_release_sys(at<uint32_t>(peers.base[r], OFF_FLAGS) + phase * MAX_WORLD + rank, e);
     const uint32_t* flag = at<uint32_t>(mine, OFF_FLAGS) + phase * MAX_WORLD + r;
-    if (*reinterpret_cast<volatile uint32_t*>(status) == 0u) {
-      const unsigned long long t0 = globaltimer_ns();
-      while ((int32_t)(ld_acquire_sys(flag) - e) < 0) {
-        if (globaltimer_ns() - t0 > timeout_ns) {
-          atomicExch(status, 1u + (uint32_t)phase);
-          break;
-        }
-        __nanosleep(64);
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - e) < 0) {
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        atomicExch(status, 1u + (uint32_t)phase);
+        __threadfence_system();
+        __trap();
       }
+      __nanosleep(64);
     }
   }
   __syncthreads();
@@ -165,8 +165,9 @@ __global__ void push_f32(PushSegs s, Peers peers, int world, int rank) {
 }
 
 // All-reduce (sum) of up to MAX_SCALARS floats in ONE kernel: push the values into every peer's slot, barrier, sum the
-// slots in rank order (every rank forms bit-identical results).  Slots alternate with the epoch's parity, so the kernel may
-// be called back to back.  `add_to` != 0: out[c] += sum (out may hold a local contribution that is not exchanged).
+// slots in rank order (every rank forms bit-identical results).  Every phase has its own slots, alternating with the
+// phase's epoch parity: the kernel may be called back to back, and a fast rank that already entered the NEXT phase's sum
+// cannot overwrite values a slow peer has not read yet.
 __global__ void sum_scalars(const float* __restrict__ vals, int cnt, Peers peers, int world, int rank, int phase,
                             unsigned long long timeout_ns, float* __restrict__ out) {
   __shared__ uint32_t epoch_sh;
@@ -178,7 +179,7 @@ __global__ void sum_scalars(const float* __restrict__ vals, int cnt, Peers peers
   const int t = threadIdx.x;
   if (t < world * cnt) {
     const int r = t / cnt, c = t % cnt;
-    st_relaxed_sys_f32(at<float>(peers.base[r], OFF_SCALARS) + (par * MAX_WORLD + rank) * MAX_SCALARS + c, vals[c]);
+    st_relaxed_sys_f32(at<float>(peers.base[r], OFF_SCALARS) + ((phase * 2 + par) * MAX_WORLD + rank) * MAX_SCALARS + c, vals[c]);
   }
   __threadfence_system();
   __syncthreads();
@@ -186,7 +187,7 @@ __global__ void sum_scalars(const float* __restrict__ vals, int cnt, Peers peers
   if (t < cnt) {
     double acc = 0.0;
     for (int q = 0; q < world; ++q)
-      acc += (double)ld_relaxed_sys_f32(at<float>(mine, OFF_SCALARS) + (par * MAX_WORLD + q) * MAX_SCALARS + t);
+      acc += (double)ld_relaxed_sys_f32(at<float>(mine, OFF_SCALARS) + ((phase * 2 + par) * MAX_WORLD + q) * MAX_SCALARS + t);
     out[t] = (float)acc;
   }
 }

@@ -22,6 +22,28 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _guard(fn):
+    """Run an engine method on the device of its tensor arguments: the C library launches on the CURRENT device and on
+    the stream handed to it, so tensors on cuda:1 while cuda:0 is current would otherwise be worked on from the wrong
+    device.  All tensor arguments must share one device."""
+    import functools
+
+    @functools.wraps(fn)
+    def inner(self, *args, **kw):
+        dev = None
+        for t in list(args) + list(kw.values()):
+            if torch.is_tensor(t) and t.is_cuda:
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise RuntimeError(f"clip_dplm_b200: tensors on different devices ({dev} and {t.device}) in one call")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kw)
+    return inner
+
+
 def padded_ld(n: int) -> int:
     """Leading dimension of a transposed operand [d, ld]: rows stay 128-byte aligned for TMA."""
     return (n + 63) // 64 * 64
@@ -71,6 +93,7 @@ class CudaEngine:
         return ws
 
     # ------------------------------------------------------------------ stages
+    @_guard
     def normalize(self, x, want_hat=None):
         """-> (rinv [n] f32, x_hat [n,d] in dtype `want_hat` or None)   (F.normalize, old/clip.py:63-64)"""
         self._chk(x, (torch.bfloat16, torch.float32), "embedding")
@@ -81,6 +104,7 @@ class CudaEngine:
                                               _DT[want_hat] if want_hat is not None else 0, _stream()), "normalize")
         return rinv, xh
 
+    @_guard
     def stage(self, x, c_dtype, want_t=False):
         """-> (x_c [n,d] raw rows in the compute dtype (x itself when it already has it),
                x_c_t [d,ld] transposed copy or None)"""
@@ -96,6 +120,7 @@ class CudaEngine:
                                                       ld, _DT[c_dtype], _stream()), "stage_operand")
         return xc, xt
 
+    @_guard
     def forward(self, x, y, rinv_x, rinv_y, diag_offset, scale, flags=0, scale_dev=None):
         """-> row_m, row_l [n_rows], col_m, col_l [n_cols], diag [n_rows]   (LSE = m + log l, kept as pairs).
         ``scale_dev``: optional 1-element f32 CUDA tensor holding s; the kernels then read s on the device and the float
@@ -116,6 +141,7 @@ class CudaEngine:
                                             _p(col_l), _p(diag), _p(ws), ws.numel(), _stream()), "forward")
         return row_m, row_l, col_m, col_l, diag
 
+    @_guard
     def backward(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, grad_out,
                  flags=0, want_dscale=True, scale_dev=None):
         """-> dx_hat [n_rows,d] f32, d_scale_sum [1] f32 (or None)"""
@@ -132,6 +158,7 @@ class CudaEngine:
                                              _p(ws), ws.numel(), _stream()), "backward")
         return dx, ds
 
+    @_guard
     def backward_dx(self, x, y, y_t, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, x_orig,
                     out_dtype, grad_scale=None, flags=0, want_dscale=True, scale_dev=None):
         """One backward side including the normalise backward -> dx [n_rows,d] in ``out_dtype`` (gradient of the caller's
@@ -152,16 +179,19 @@ class CudaEngine:
                                                 ws.numel(), _stream()), "backward_dx")
         return dx, ds
 
+    @_guard
     def softmax_weights(self, l, coef):
         out = torch.empty_like(l)
         _lib.check(self.lib.clipnce_softmax_weights(_p(l), l.numel(), float(coef), _p(out), _stream()), "softmax_weights")
         return out
 
+    @_guard
     def combine_lse(self, m, l):
         out = torch.empty_like(m)
         _lib.check(self.lib.clipnce_combine_lse(_p(m), _p(l), m.numel(), _p(out), _stream()), "combine_lse")
         return out
 
+    @_guard
     def normalize_backward(self, x, rinv, dx_hat, out_dtype, grad_scale=None):
         n, d = x.shape
         dx = torch.empty((n, d), dtype=out_dtype, device=x.device)
@@ -169,6 +199,7 @@ class CudaEngine:
                                                        _p(dx), _DT[out_dtype], _stream()), "normalize_backward")
         return dx
 
+    @_guard
     def topk(self, q, lib, rinv_q, rinv_lib, k, col_offset=0):
         """-> scores [n_q,k] f32 (descending), indices [n_q,k] i64 of the k most similar library rows per query
         (cosine similarity; run1/full.py:152,157).  bf16, d in {128,...,512}, k <= 16; raises otherwise."""
@@ -196,12 +227,14 @@ class CudaEngine:
     def link_barrier(self, peers, world, rank, phase):
         _lib.check(self.lib.clipnce_link_barrier(peers, world, rank, phase, _stream()), "link_barrier")
 
+    @_guard
     def link_push_rows(self, x, c_dtype, peers, world, rank, rows_off, rinv_off, row0, max_blocks=0):
         self._chk(x, (torch.bfloat16, torch.float32), "embedding")
         n, d = x.shape
         _lib.check(self.lib.clipnce_link_push_rows(_p(x), _DT[x.dtype], n, d, _DT[c_dtype], peers, world, rank, rows_off,
                                                    rinv_off, row0, max_blocks, _stream()), "link_push_rows")
 
+    @_guard
     def link_copy(self, src, peers, world, rank, dst_off):
         """Copy-engine broadcast of a contiguous local tensor to byte offset ``dst_off`` of every rank's buffer."""
         self._chk(src, (torch.bfloat16, torch.float32), "rows")
@@ -217,6 +250,7 @@ class CudaEngine:
         off = (ctypes.c_int64 * k)(*dst_offs)
         _lib.check(self.lib.clipnce_link_push_f32(src, n, off, k, peers, world, rank, _stream()), "link_push_f32")
 
+    @_guard
     def link_sum_scalars(self, vals, peers, world, rank, phase):
         self._chk(vals, (torch.float32,), "scalars")
         out = torch.empty_like(vals)
@@ -224,6 +258,7 @@ class CudaEngine:
                    "link_sum_scalars")
         return out
 
+    @_guard
     def combine_partials(self, part_m, part_l, n_part, ld, n):
         out_m = torch.empty(n, dtype=torch.float32, device=part_m.device)
         out_l = torch.empty(n, dtype=torch.float32, device=part_m.device)
@@ -231,6 +266,7 @@ class CudaEngine:
                    "combine_partials")
         return out_m, out_l
 
+    @_guard
     def loss(self, row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric):
         out = torch.empty(1, dtype=torch.float32, device=row_m.device)
         _lib.check(self.lib.clipnce_loss(_p(row_m), _p(row_l), _p(col_m), _p(col_l), _p(diag), row_m.numel(),

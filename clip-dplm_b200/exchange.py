@@ -76,15 +76,14 @@ class CollectiveExchange:
 
     def exchange_stats(self, row_m, row_l, col_m, col_l, fixed_shift, need_rows):
         g = self.group
-        if fixed_shift:   # every partial sum already shares the shift col_m == s on every rank
-            col_l = col_l.clone()
-            dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=g)
-        else:
-            m_max = col_m.clone()
-            dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=g)
-            col_l = col_l * torch.exp(col_m - m_max)
-            dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=g)
-            col_m = m_max
+        # Always the general (shift, sum) combine: `fixed_shift` is derived from a host-side, possibly stale copy of the
+        # logit scale (functional._ScaleHint), so ranks may briefly disagree on it while s crosses the kernel-family
+        # threshold -- and ranks that disagree must still issue the SAME collectives.
+        m_max = col_m.clone()
+        dist.all_reduce(m_max, op=dist.ReduceOp.MAX, group=g)
+        col_l = col_l * torch.exp(col_m - m_max)
+        dist.all_reduce(col_l, op=dist.ReduceOp.SUM, group=g)
+        col_m = m_max
         if not need_rows:
             return col_m, col_l, None, None
         return col_m, col_l, _all_gather(row_m, g), _all_gather(row_l, g)
@@ -210,7 +209,8 @@ class PeerExchange:
         return self.engine.link_sum_scalars(vals, self.peers, self.world, self.rank, phase)
 
     def check(self):
-        """Host check of the status word (synchronises): raises if a barrier timed out."""
+        """Host check of the status word (synchronises): raises if a barrier timed out.  A timeout also traps on the
+        device (kernels_link.cuh), so in practice the synchronisation inside this read raises first."""
         code = int(self.status[0])
         if code != 0:
             raise RuntimeError(f"clip_dplm_b200: peer exchange barrier phase {code - 1} timed out (a rank did not arrive)")

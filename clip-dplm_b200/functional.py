@@ -70,7 +70,7 @@ class _ScaleHint:
 class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, logit_scale, extra, symmetric, scale_is_log, clamp_max, group, compute_dtype, flags, engine,
-                want_stats=True, grad_mode=True):
+                want_stats=True, grad_mode=True, ddp=False):
         # grad_mode: autograd's mode at the call (always off inside forward()).  Without a backward to come the step
         # neither gathers the rows side B would stream nor keeps its exchange buffers (step.py)
         need_grad = grad_mode and (a.requires_grad or b.requires_grad or
@@ -94,6 +94,11 @@ class _FusedClipLoss(torch.autograd.Function):
                                              compute_dtype=compute_dtype, flags=flags, need_grad=need_grad,
                                              scale_dev=s_dev)
         ctx.st, ctx.engine = st, engine
+        # DistributedDataParallel AVERAGES parameter gradients over the ranks.  dA / dB are the exact gradient of the GLOBAL
+        # mean loss with respect to the LOCAL rows (their sum over ranks is the parameter gradient), d logit_scale is the
+        # full sum on every rank (its average is itself): under DDP the row gradients are therefore scaled by the world
+        # size, so that every parameter comes out of DDP's mean with the gradient of the global loss.
+        ctx.row_grad_mult = float(torch.distributed.get_world_size(group)) if (ddp and group is not None) else 1.0
         if s_dev is None:
             _, s, clamped = info["v"]
             ctx.scale_info = (s, clamped, scale_is_log, None, None, None)
@@ -119,9 +124,10 @@ class _FusedClipLoss(torch.autograd.Function):
                 st.xchg.release()
                 st.xchg = None
             ctx.st = None
-            return (None,) * 13
+            return (None,) * 14
         g = g_loss.reshape(1).to(torch.float32).contiguous()
-        da, db, ds = _step.contrastive_backward(engine, st, grad_scale=g)
+        g_rows = g * ctx.row_grad_mult if ctx.row_grad_mult != 1.0 else g
+        da, db, ds = _step.contrastive_backward(engine, st, grad_scale=g_rows)
         d_ls = None
         if ctx.ls_meta is not None and ctx.needs_input_grad[2]:
             # sum G.S = dL/dt for s = exp(t);  dL/ds = sum G.S / s for a raw scale;  0 where the clamp is active
@@ -136,13 +142,13 @@ class _FusedClipLoss(torch.autograd.Function):
                 coef = 1.0 if scale_is_log else 1.0 / s
                 d_ls = (ds * g * coef).reshape(()).to(device=ctx.ls_meta[1], dtype=ctx.ls_meta[0])
         ctx.st = None
-        return da, db, d_ls, None, None, None, None, None, None, None, None, None, None
+        return da, db, d_ls, None, None, None, None, None, None, None, None, None, None, None
 
 
 def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: bool = True,
                     clamp_max: Optional[float] = None, extra_cols=None, extra_normalized: bool = True,
                     group=None, compute_dtype: Optional[torch.dtype] = None, return_stats: bool = False,
-                    engine=None):
+                    ddp: bool = False, engine=None):
     """Fused CLIP / InfoNCE loss of two [N,d] embedding batches (un-normalised projection-head outputs).
 
     logit_scale   0-d tensor (learnable parameter) or float; ``s = exp(logit_scale)`` (scale_is_log) or
@@ -153,6 +159,11 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
                   (rows of arbitrary norm) routes to the exact kernels.
     group         torch.distributed process group: rows are this rank's shard of a global batch; negatives
                   are global, gradients are exact (both sides complete on their owner), the returned loss is the global mean.
+    ddp           with ``group``: the model producing ``a``/``b`` is wrapped in DistributedDataParallel (how the reference
+                  runs old/clip_opt.py), which AVERAGES parameter gradients over ranks.  The row gradients are then scaled
+                  by the world size, so that after DDP's mean every parameter -- encoders, heads and logit_scale alike --
+                  holds the gradient of the global mean loss.  Default (False): dA/dB are the plain partial derivatives
+                  of the global loss with respect to the local rows (sum them over ranks yourself).
     compute_dtype torch.bfloat16 (tcgen05 tensor-core kernels) or torch.float32 (exact check mode).
                   Default: bf16 for bf16/fp16 inputs or under autocast, else fp32 (the reference's numerics).
     """
@@ -169,7 +180,7 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
         flags |= _step.FLAG_FORCE_EXACT
     loss, row_lse, col_lse, diag = _FusedClipLoss.apply(a, b, logit_scale, extra_cols, symmetric, scale_is_log,
                                                         clamp_max, group, compute_dtype, flags, engine, bool(return_stats),
-                                                        torch.is_grad_enabled())
+                                                        torch.is_grad_enabled(), bool(ddp))
     if return_stats:
         return loss, {"row_lse": row_lse, "col_lse": col_lse, "diag": diag}
     return loss

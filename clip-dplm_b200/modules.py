@@ -162,9 +162,13 @@ class _PairCLIP(nn.Module):
     symmetric = True
     clamp_max: Optional[float] = None
 
+    # with a process group: the module is assumed to be wrapped in DistributedDataParallel, as the reference does
+    # (old/clip_opt.py:154, run1/full.py:172) -- row gradients follow DDP's averaging convention (fused_clip_loss `ddp`)
+    ddp_gradients = True
+
     def _tail(self, emb_a, emb_b, extra_cols=None, group=None):
         loss = fused_clip_loss(emb_a, emb_b, self.logit_scale, symmetric=self.symmetric, clamp_max=self.clamp_max,
-                               extra_cols=extra_cols, group=group)
+                               extra_cols=extra_cols, group=group, ddp=self.ddp_gradients and group is not None)
         a_hat, b_hat = fused_normalize(emb_a), fused_normalize(emb_b)
         s = self.logit_scale.detach().exp()
         if self.clamp_max is not None:

@@ -215,8 +215,10 @@ int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const floa
  * and leave it alone.  Everything else is laid out by the caller and addressed by BYTE OFFSETS from the base.
  * All calls enqueue on `stream`, never synchronise the host, and keep their epochs on the device, so a step that
  * contains them can be captured once in a CUDA graph and replayed.  Ranks must issue the same sequence of calls.
- * A peer that does not arrive within CLIPNCE_LINK_TIMEOUT_MS (default 10000) sets the status word
- * (u32 at status_offset of the own buffer: 1 + phase) instead of hanging the GPU; later barriers then return at once.
+ * A peer that does not arrive within CLIPNCE_LINK_TIMEOUT_MS (default 600000 = 10 minutes, the order of NCCL's
+ * watchdog) is FATAL: the waiting kernel records 1 + phase in the status word (u32 at status_offset of the own buffer,
+ * for the post-mortem) and traps, so the CUDA error surfaces at the caller's next synchronisation -- a step never
+ * continues on peer buffers that were not synchronised.
  */
 int clipnce_link_control_bytes(int64_t* control_bytes, int64_t* status_offset);
 

@@ -266,3 +266,84 @@ def test_module_parameter_names_match_reference():
         a = {k: tuple(v.shape) for k, v in getattr(ref, name)(cfg).state_dict().items()}
         b = {k: tuple(v.shape) for k, v in getattr(M, name)(cfg).state_dict().items()}
         assert a == b, name
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_sampled_oracle_matches_closed_form(symmetric):
+    """oracle/sampled.py (blockwise statistics + float64 gradient rows of a sample; what bench.py's `parity` key and the
+    large-shape GPU tests compare with) against the dense closed form on a size where both fit."""
+    from oracle import sampled as SO
+    n, d, s = 300, 64, 14.2857
+    a, b = O.make_inputs(n, d, seed=5)
+    cf = O.closed_form(a.numpy(), b.numpy(), s, symmetric=symmetric)
+    rows_a, rows_b = np.array([0, 7, 150, 299]), np.array([3, 299, 42])
+    ref = SO.sampled_reference(a, b, s, rows_a, rows_b, chunk=128, symmetric=symmetric)
+    assert abs(ref["loss"] - cf["loss"]) <= 1e-6 * abs(cf["loss"])
+    assert np.allclose(ref["row_lse"], cf["row_lse"], atol=2e-5)
+    assert np.allclose(ref["col_lse"], cf["col_lse"], atol=2e-5)
+    assert np.allclose(ref["diag"], cf["diag"], atol=1e-9)
+    assert abs(ref["d_scale_sum"] - cf["d_scale_sum"]) <= 1e-4 * abs(cf["d_scale_sum"])
+    assert rel(ref["d_a"], cf["d_a"][rows_a]) <= 1e-4   # the blockwise LSEs come from an fp32 GEMM
+    assert rel(ref["d_b"], cf["d_b"][rows_b]) <= 1e-4
+    cmp = SO.compare(ref, cf["loss"], cf["d_a"][rows_a], cf["d_b"][rows_b], cf["d_scale_sum"])
+    assert cmp["ok"] and cmp["rows"] == 4
+
+
+# ------------------------------------------------------------------------------------------------ DDP convention
+class _TinyTwoTower(torch.nn.Module):
+    def __init__(self, d_in, d):
+        super().__init__()
+        g = torch.Generator().manual_seed(4)
+        self.wa = torch.nn.Parameter(torch.randn(d_in, d, generator=g, dtype=torch.float64) * 0.3)
+        self.wb = torch.nn.Parameter(torch.randn(d_in, d, generator=g, dtype=torch.float64) * 0.3)
+        self.logit_scale = torch.nn.Parameter(torch.tensor(O.LOGIT_SCALE_INIT, dtype=torch.float64))
+
+    def forward(self, xa, xb, group=None, ddp=False):
+        from clip_dplm_b200 import fused_clip_loss
+        return fused_clip_loss(xa @ self.wa, xb @ self.wb, self.logit_scale, engine=TorchCpuEngine(),
+                               compute_dtype=torch.float64, group=group, ddp=ddp)
+
+
+def _ddp_worker(rank, world, port, n, d_in, d, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        torch.set_num_threads(1)
+        g = torch.Generator().manual_seed(8)
+        xa, xb = torch.randn(n, d_in, generator=g, dtype=torch.float64), torch.randn(n, d_in, generator=g, dtype=torch.float64)
+        nl = n // world
+        model = DDP(_TinyTwoTower(d_in, d))
+        loss = model(xa[rank * nl:(rank + 1) * nl], xb[rank * nl:(rank + 1) * nl], group=dist.group.WORLD, ddp=True)
+        loss.backward()                                   # DDP averages every parameter gradient over the ranks
+        m = model.module
+        q.put((rank, float(loss.detach()), m.wa.grad.numpy(), m.wb.grad.numpy(), float(m.logit_scale.grad)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_parameter_gradients_match_single_process():
+    """Under DistributedDataParallel (how the reference runs old/clip_opt.py:154, run1/full.py:172) EVERY parameter --
+    tower weights and logit_scale alike -- must come out of DDP's gradient averaging with the gradient of the global
+    mean loss of a single-process run on the whole batch (`fused_clip_loss(..., ddp=True)`)."""
+    world, n, d_in, d = 2, 64, 12, 16
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 25500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, n, d_in, d, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(8)
+    xa, xb = torch.randn(n, d_in, generator=g, dtype=torch.float64), torch.randn(n, d_in, generator=g, dtype=torch.float64)
+    ref = _TinyTwoTower(d_in, d)
+    loss = O.ref_loss(xa @ ref.wa, xb @ ref.wb, ref.logit_scale)
+    loss.backward()
+    for rank, l, gwa, gwb, gt in out:
+        assert abs(l - float(loss.detach())) < 1e-12
+        assert rel(gwa, ref.wa.grad) < 1e-9 and rel(gwb, ref.wb.grad) < 1e-9
+        assert abs(gt - float(ref.logit_scale.grad)) < 1e-9 * max(1.0, abs(float(ref.logit_scale.grad)))

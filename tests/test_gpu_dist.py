@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 def _worker(rank, world, port, n, d, comm, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("CLIPNCE_LINK_TIMEOUT_MS", "30000")   # a lost rank fails the test in 30 s, not in 10 min
     os.environ["CLIPNCE_COMM"] = comm
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -86,6 +87,7 @@ def test_row_sharded_matches_single_process(comm):
 def _worker_topk_and_graph(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("CLIPNCE_LINK_TIMEOUT_MS", "30000")   # a lost rank fails the test in 30 s, not in 10 min
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -138,6 +140,7 @@ def _worker_sequence(rank, world, port, q):
     exchanged), hard-negative cache columns.  Every result is checked on the parent against the oracle."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("CLIPNCE_LINK_TIMEOUT_MS", "30000")   # a lost rank fails the test in 30 s, not in 10 min
     os.environ["CLIPNCE_COMM"] = "link"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -226,6 +229,7 @@ def test_peer_exchange_step_sequence():
 def _worker_single(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("CLIPNCE_LINK_TIMEOUT_MS", "30000")   # a lost rank fails the test in 30 s, not in 10 min
     torch.cuda.set_device(0)
     dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
     try:
