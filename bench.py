@@ -221,7 +221,7 @@ def run_ours(args, rank, local_rank, world):
 
         def __init__(self):
             super().__init__()
-            self.ev, self.launches, self.on = {"fwd": [], "bwd": []}, 0, False
+            self.ev, self.launches, self.on = {"fwd": [], "bwd": [], "bwd2": []}, 0, False
 
         def _timed(self, key, fn, *a, **k):
             if not self.on:
@@ -245,6 +245,11 @@ def run_ours(args, rank, local_rank, world):
             # contraction kernel + finish_rows (split sum, row dots, normalise backward) [+ the scalar reduction]
             self.launches += 3 if k.get("want_dscale", True) else 2
             return self._timed("bwd", super().backward_dx, *a, **k)
+
+        def backward_both(self, *a, **k):
+            # 2 x normalise-to-bf16, the two-sided contraction kernel, 2 x finish_rows, the scalar reduction
+            self.launches += 6
+            return self._timed("bwd2", super().backward_both, *a, **k)
 
         def normalize(self, *a, **k):
             self.launches += 1
@@ -394,6 +399,9 @@ def run_ours(args, rank, local_rank, world):
     eng.on = False
     t_fwd = sum(e0.elapsed_time(e1) for e0, e1 in eng.ev["fwd"]) / max(1, len(eng.ev["fwd"]))
     t_bwd = sum(e0.elapsed_time(e1) for e0, e1 in eng.ev["bwd"]) / max(1, len(eng.ev["bwd"]))
+    two_sided = len(eng.ev["bwd2"]) > 0
+    if two_sided:
+        t_bwd = sum(e0.elapsed_time(e1) for e0, e1 in eng.ev["bwd2"]) / len(eng.ev["bwd2"])
 
     # the step as the library runs it in production: forward + backward (collectives included) replayed as ONE CUDA
     # graph (clip_dplm_b200.graph.GraphedClipStep); the logit scale is read on the device, nothing needs the host
@@ -485,7 +493,7 @@ def run_ours(args, rank, local_rank, world):
     flops_step = 6.0 * n_global * n_global * d
     # dominant kernel: one backward side = recompute S tile + gradient GEMM; algorithmic work of the launch is
     # its gradient GEMM, 2 * rows * cols * d (the three launches of a step add up to 6 N^2 d)
-    flops_bwd_launch = 2.0 * n_local * n_global * d
+    flops_bwd_launch = (4.0 if two_sided else 2.0) * n_local * n_global * d
     achieved = flops_bwd_launch / (t_bwd * 1e-3) / 1e12
     peak = peaks["sustained"]           # the kernel is timed inside a long, power-capped step
     cpu = None
@@ -508,7 +516,11 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_local * d * 2, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "launch_mode": graph_note, "eager_ms_per_step": ms_eager / args.steps,
-        "roofline": {"bound": "tensor", "kernel": "pair::bwd_kernel (one backward side: logits recompute + gradient GEMM, cta_group::2)", "achieved": achieved,
+        "roofline": {"bound": "tensor",
+                     "kernel": ("pair2::bwd2_kernel (both backward sides in one sweep: logits recompute + dA and dB gradient GEMMs, "
+                                "algorithmic 4 N^2 d of 6 N^2 d executed, cta_group::2)" if two_sided else
+                                "pair::bwd_kernel (one backward side: logits recompute + gradient GEMM, cta_group::2)"),
+                     "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": measured_traffic(n_global, d, world),
                      "peak_kind": f"{peaks['src']} sustained bf16 cuBLAS", "frac_of_burst": achieved / peaks["burst"],
                      "ms_per_launch": t_bwd, "fwd_ms_per_launch": t_fwd,

@@ -16,6 +16,7 @@
 #include "kernels_aux.cuh"
 #include "kernels_link.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_pair2.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 
@@ -624,6 +625,189 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
 #undef FINISH
   CUDA_TRY(cudaGetLastError());
   if (df.ds_pending) {
+    aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)n_blk, 1.f, d_scale_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- two-sided backward (kernels_pair2.cuh) ----------------------------------------------------------------------------
+namespace {
+struct Bwd2Plan {
+  int P, Q, n_rb, n_waves, n_steps, n_half, depth, stages_a, stages_b, stages_c, smem;
+  size_t off_flags, off_xh, off_yh, off_ring, off_dxh, off_dyh, off_part, bytes;
+};
+
+bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resident at once
+  {   // read per call: tests switch between the two-sided kernel and the two-sweep path inside one process
+    const char* e = getenv("CLIPNCE_NO_BWD2");
+    if (e && atoi(e) != 0) return false;
+  }
+  static const bool ok = [] {
+    if (cudaFuncSetAttribute(pair2::bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(2 * pair_slots());
+    cfg.blockDim = dim3(pair2::THREADS);
+    cfg.dynamicSmemBytes = pair::SMEM_LIMIT;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, pair2::bwd2_kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return n >= pair_slots();
+  }();
+  return ok;
+}
+
+bool bwd2_plan(int64_t n, int64_t d, int dtype, float scale, int flags, Bwd2Plan* pl) {
+  if (!tc_eligible(dtype, d, scale, flags) || !pair_eligible(d) || d > 512) return false;
+  int64_t min_n = 16384;   // below this the row blocks do not fill the producer pairs (CLIPNCE_BWD2_MIN_N: test hook)
+  if (const char* e = getenv("CLIPNCE_BWD2_MIN_N")) min_n = atoll(e);
+  if (n % 256 != 0 || n < min_n || n < 256 || n > (1ll << 22)) return false;
+  const int slots = pair_slots();
+  if (slots < 8) return false;
+  pl->n_rb = (int)(n / 128);
+  pl->n_steps = (int)(n / 256);
+  pl->n_half = (int)ceil_div(d, 256);
+  // producers : consumers.  A producer pair spends two tile units per step (logits + dX), the consumers one per producer
+  // tile (dY) at a rate `r` times a producer's (plain GEMM, 256 x 256 instructions): pick the split with the shortest
+  // modelled time, row-block waves included.  CLIPNCE_BWD2_P forces the number of producer pairs.
+  const char* ef = getenv("CLIPNCE_BWD2_P");
+  const int forced = ef ? atoi(ef) : 0;
+  const char* er = getenv("CLIPNCE_BWD2_RATIO");
+  const double r = (er && atof(er) > 0.1) ? atof(er) : 1.15;
+  int best_p = 0;
+  double best_t = 1e300;
+  for (int P = slots / 2; P <= slots - 2; ++P) {
+    const int Q = slots - P;
+    const double tp = 2.0 * (double)ceil_div(pl->n_rb, P);
+    const double tc_ = (double)pl->n_rb / ((double)Q * r);
+    const double t = tp > tc_ ? tp : tc_;
+    if (t < best_t - 1e-9) { best_t = t; best_p = P; }
+  }
+  if (forced >= 1 && forced <= slots - 1) best_p = forced;
+  pl->P = best_p;
+  pl->Q = slots - best_p;
+  pl->n_waves = (int)ceil_div(pl->n_rb, pl->P);
+  pl->depth = pair2::RING_DEPTH;
+  if (const char* e = getenv("CLIPNCE_BWD2_DEPTH")) { const int v = atoi(e); if (v >= 2 && v <= 64) pl->depth = v; }
+  const int nkc = (int)(d / 64);
+  const int total = (pair::SMEM_LIMIT - pair2::producer_smem(nkc, 0)) / pair::STAGE_BYTES;
+  if (total < 4) return false;
+  auto cap = [](int v) { return v > pair2::MAXS ? pair2::MAXS : v; };
+  pl->stages_b = cap(total / 2);
+  pl->stages_a = cap(total - total / 2);
+  pl->stages_c = cap((pair::SMEM_LIMIT - pair2::SMALL) / pair2::C_STAGE);
+  const int ps = pair2::producer_smem(nkc, pl->stages_a + pl->stages_b), cs = pair2::consumer_smem(pl->stages_c);
+  pl->smem = ps > cs ? ps : cs;
+  size_t off = 0;
+  auto region = [&](size_t bytes) { const size_t o = off; off = (size_t)round_up((int64_t)(off + bytes), 256); return o; };
+  pl->off_flags = region(sizeof(uint32_t) * 2 * (size_t)pl->n_waves * (size_t)pl->n_steps);
+  pl->off_xh = region(2 * (size_t)n * (size_t)d);
+  pl->off_yh = region(2 * (size_t)n * (size_t)d);
+  pl->off_ring = region((size_t)pl->depth * (size_t)pl->P * 128 * 256 * 2);
+  pl->off_dxh = region(sizeof(float) * (size_t)n * (size_t)d);
+  pl->off_dyh = region(sizeof(float) * (size_t)n * (size_t)d);
+  pl->off_part = region(sizeof(float) * ((size_t)ceil_div(n, 8) + (size_t)n));
+  pl->bytes = off;
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+int clipnce_backward_both_workspace_bytes(int64_t n, int64_t d, int dtype, float scale, int flags, size_t* out) {
+  if (!out) return fail(CLIPNCE_EINVAL, "backward_both_workspace_bytes: null pointer");
+  Bwd2Plan pl;
+  *out = (n >= 1 && d >= 1 && bwd2_plan(n, d, dtype, scale, flags, &pl) && check_device_sm100() == 0 && bwd2_device_ok()) ? pl.bytes : 0;
+  return 0;
+}
+
+int clipnce_backward_both_dx(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n,
+                             int64_t d, float scale, const float* scale_dev, const float* row_m, const float* row_w,
+                             const float* col_m, const float* col_w, float diag_w, int dtype, int flags,
+                             const void* x_orig, const void* y_orig, int in_dtype, const float* grad_scale, void* dx,
+                             void* dy, int out_dtype, float* d_scale_sum, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !col_m || !col_w || !x_orig || !y_orig || !dx || !dy || !workspace)
+    return fail(CLIPNCE_EINVAL, "backward_both_dx: null pointer");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "backward_both_dx: bad dtype");
+  if (in_dtype == dtype && (x_orig != x || y_orig != y))
+    return fail(CLIPNCE_EINVAL, "backward_both_dx: x_orig / y_orig of the compute type must be x / y themselves");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(workspace)) return fail(CLIPNCE_EINVAL, "backward_both_dx: operands must be 16-byte aligned");
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  Bwd2Plan pl;
+  if (!bwd2_plan(n, d, dtype, scale, flags, &pl) || !bwd2_device_ok())
+    return fail(CLIPNCE_EUNSUPPORTED, "backward_both_dx: shape not served (see clipnce_backward_both_workspace_bytes)");
+  if (workspace_bytes < pl.bytes) return fail(CLIPNCE_EWORKSPACE, "backward_both_dx: workspace %zu < %zu", workspace_bytes, pl.bytes);
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  uint32_t* flags_dev = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_xh);
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_yh);
+  void* ring = ws + pl.off_ring;
+  float* dxh = reinterpret_cast<float*>(ws + pl.off_dxh);
+  float* dyh = reinterpret_cast<float*>(ws + pl.off_dyh);
+  float* ds_part = reinterpret_cast<float*>(ws + pl.off_part);
+  float* rinv_scratch = ds_part + ceil_div(n, 8);
+  const int di = (int)d;
+
+  // normalised rows rounded to bf16: the operands both gradient GEMMs contract the shared G tile against
+  {
+    const int wpb = 8;
+    dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
+    aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, xh, rinv_scratch);
+    aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)y, n, di, yh, rinv_scratch);
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * 2 * (size_t)pl.n_waves * (size_t)pl.n_steps, st));
+
+  pair2::Params p;
+  memset(&p, 0, sizeof p);
+  p.n = (int)n; p.d = di; p.nkc = (int)(d / 64); p.nq2 = (int)ceil_div(d, 256); p.n_steps = pl.n_steps; p.n_half = pl.n_half;
+  p.P = pl.P; p.Q = pl.Q; p.n_rb = pl.n_rb; p.n_waves = pl.n_waves; p.depth = pl.depth;
+  p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c;
+  p.scale = scale; p.scale_dev = scale_dev; p.diag_w = diag_w;
+  p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_w = row_w; p.col_m = col_m; p.col_w = col_w;
+  p.dx = dxh; p.dy = dyh;
+  p.ready = flags_dev; p.done = flags_dev + (size_t)pl.n_waves * (size_t)pl.n_steps;
+  CUtensorMap tx, ty, tyh, txh, tg;
+  if ((rc = make_tmap(&tx, x, d, n, d, pair2::ROWS))) return rc;
+  if ((rc = make_tmap(&ty, y, d, n, d, 128))) return rc;
+  if ((rc = make_tmap(&tyh, yh, d, n, d, 64))) return rc;
+  if ((rc = make_tmap(&txh, xh, d, n, d, 64))) return rc;
+  if ((rc = make_tmap(&tg, ring, 256, (int64_t)pl.depth * pl.P * 128, 256, 64))) return rc;
+  pair2::bwd2_kernel<<<2 * (pl.P + pl.Q), pair2::THREADS, pl.smem, st>>>(tx, ty, tyh, txh, tg, p);
+  CUDA_TRY(cudaGetLastError());
+
+  // tails: row dots (sum G.S, side A only) + normalise backward, one pass per side
+  const int64_t n_blk = ceil_div(n, 8);
+  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  const unsigned grid = (unsigned)n_blk;
+  const int64_t slab = n * d;
+#define FINISH2(TI, TO)                                                                                                      \
+  do {                                                                                                                       \
+    aux::finish_rows_v4<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(dxh, 1, slab, (const __nv_bfloat16*)x, (const TI*)x_orig, \
+                                                                        rinv_x, grad_scale, n, di, (TO*)dx,                 \
+                                                                        d_scale_sum ? ds_part : nullptr);                   \
+    aux::finish_rows_v4<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(dyh, 1, slab, (const __nv_bfloat16*)y, (const TI*)y_orig, \
+                                                                        rinv_y, grad_scale, n, di, (TO*)dy, nullptr);       \
+  } while (0)
+  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH2(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == CLIPNCE_BF16) FINISH2(__nv_bfloat16, float);
+  else if (out_dtype == CLIPNCE_BF16) FINISH2(float, __nv_bfloat16);
+  else FINISH2(float, float);
+#undef FINISH2
+  CUDA_TRY(cudaGetLastError());
+  if (d_scale_sum) {
     aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)n_blk, 1.f, d_scale_sum);
     CUDA_TRY(cudaGetLastError());
   }

@@ -1,0 +1,572 @@
+// Two-sided backward: ONE sweep over the logits tiles emits both dA_hat and dB_hat (8 N^2 d executed per step instead of
+// the 10 N^2 d of two pair::bwd_kernel launches) -- loss.backward() of current/rna_clip_codes.ipynb:2074,
+// run1/full.py:134, old/clip_opt.py:167 for the single-GPU symmetric loss.
+//
+// Why it is not "one CTA pair keeps two accumulators".  A pair's TMEM holds 128 K floats.  With d = 512 the stationary
+// gradient of 128 resident rows already takes half of it and two logits buffers the other half; a second, per-column-block
+// accumulator [256 x 512] does not fit, and flushing one per step would cost 1/(1.5 R) B per FLOP of fp32 reduction
+// traffic (R = 128 rows: ~7 TB/s).  So the second gradient is formed by OTHER SMs, and what travels between them is the
+// bf16 gradient tile G the producer has in shared memory anyway:
+//
+//   producer pairs (P of the 74)   exactly pair::bwd_kernel's sweep -- 128 resident rows of X, S = X Y^T per 256-column
+//                                  step, G = exp(S - s)(u_i + v_j) - diag, dXhat += G Yhat stationary in TMEM -- plus a TMA
+//                                  store of every G tile [128 x 256] bf16 into a ring in global memory (L2-resident)
+//   consumer pairs (Q = 74 - P)    dYhat[J_t, d half] += sum over the wave's producers G_p^T Xhat_p : a plain GEMM,
+//                                  M = 256 columns j, N = 256 (d half), K = all rows of the wave (P x 128), both operands
+//                                  MN-major straight from TMA boxes; flushed once per task (K = 6656 rows: the fp32
+//                                  read-modify-write traffic is 2 % of what a per-pair flush would cost)
+//
+// All producers sweep the column steps in lock step (they run the same code on the same data volume), so at any time
+// the tiles in flight belong to a window of ~Q/2 + 2 steps: the ring holds D = 16 steps x P tiles x 64 KiB.
+// Producers : consumers = 2 : 1 in work (S + dX against dY), P is chosen so that the waves of row blocks are full.
+//
+// Both gradient GEMMs contract G against the NORMALISED rows rounded to bf16 (Xhat, Yhat: one extra elementwise pass)
+// because one tile has to serve both sides: the per-row / per-column 1/norm factors can no longer be folded into G.  The
+// logits themselves still come from the raw rows scaled in fp32, exactly as in the forward.
+//
+// Flags (global memory, zeroed per launch): ready[g] counts the G boxes stored for global step g = wave * n_steps + t
+// (2 per producer pair: one per CTA, after its four boxes), done[g] the consumer tasks that finished reading them (one per d half).  A
+// producer stores step g only after done[g - D] is complete.  TMA stores are published by
+// cp.async.bulk.wait_group 0 -> fence.proxy.async -> red.release.gpu; consumers ld.acquire.gpu -> fence.proxy.async ->
+// TMA loads.  Liveness: the smallest incomplete step's consumers never wait on anything but producers, and producers only
+// wait on steps D behind them.  All 74 pairs must be co-resident (persistent grid of 148 CTAs, checked by the host).
+#pragma once
+#include "kernels_pair.cuh"
+
+namespace pair2 {
+
+using pair::LOG2E;
+using pair::STAGE_BYTES;
+using pair::STEP_J;
+using pair::TMEM_COLS;
+
+constexpr int THREADS = 416;                 // 4 service warps + 8 epilogue warps + the ring-store warp
+constexpr int STORE_WARP = 12;
+constexpr int EPI_WARPS = 8;
+constexpr int ROWS = 64;                     // resident rows per producer CTA (128 per pair)
+constexpr int X_CHUNK = ROWS * 128;          // [64 rows][64 k] bf16
+constexpr int G_BYTES = 4 * 8192;            // [64 i][256 j] bf16 = four K-major boxes
+constexpr int SMALL = 8192;                  // barriers (512) | tmem ptr | column vectors 2 x 2 x 256 f32 at +1024
+constexpr int C_STAGE = 32768;               // consumer stage: A = 2 boxes G^T [64 i][64 j], B = 2 boxes Xhat [64 i][64 d]
+constexpr int MAXS = 6;
+constexpr int RING_DEPTH = 16;               // steps of G tiles the ring holds
+
+constexpr int B_FULL_A = 0, B_EMPTY_A = MAXS, B_FULL_B = 2 * MAXS, B_EMPTY_B = 3 * MAXS, B_XFULL = 4 * MAXS,
+              B_XEMPTY = B_XFULL + 1, B_SFULL = B_XEMPTY + 1, B_SEMPTY = B_SFULL + 2, B_GFULL = B_SEMPTY + 2,
+              B_GEMPTY = B_GFULL + 4, B_ACCFULL = B_GEMPTY + 4, B_ACCEMPTY = B_ACCFULL + 2, B_GSFULL = B_ACCEMPTY + 2,
+              B_GSTORED = B_GSFULL + 4, B_COUNT = B_GSTORED + 4;
+static_assert(B_COUNT * 8 <= 512, "barrier block");
+
+struct Params {
+  int n, d;             // n_rows == n_cols == n, n % 256 == 0, d % 128 == 0, d <= 512
+  int nkc, nq2, n_steps, n_half;
+  int P, Q, n_rb, n_waves, depth;
+  int stages_a, stages_b, stages_c;
+  float scale, diag_w;
+  const float* scale_dev;
+  const float* rinv_x;
+  const float* rinv_y;
+  const float* row_m;
+  const float* row_w;
+  const float* col_m;
+  const float* col_w;
+  float* dx;            // [n, d] f32: s * sum_j G_ij yhat_j
+  float* dy;            // [n, d] f32: s * sum_i G_ij xhat_i
+  uint32_t* ready;      // [n_waves * n_steps]
+  uint32_t* done;       // [n_waves * n_steps]
+};
+
+__host__ __device__ constexpr int producer_smem(int nkc, int stages) { return nkc * X_CHUNK + G_BYTES + stages * STAGE_BYTES + SMALL; }
+__host__ __device__ constexpr int consumer_smem(int stages) { return stages * C_STAGE + SMALL; }
+
+__device__ __forceinline__ void publish(uint32_t* flag) {   // TMA stores of this thread (already waited for) -> visible, then count
+  ptx::fence_proxy_async_all();
+  ptx::red_release_gpu_add(flag, 1u);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k, 64 rows}      resident rows (logits A operand)
+            const __grid_constant__ CUtensorMap tmap_y,    // Y raw   box {64 k, 128 rows}     logits B operand, K-major
+            const __grid_constant__ CUtensorMap tmap_yh,   // Yhat    box {64 d, 64 rows}      dX gradient B operand, MN-major
+            const __grid_constant__ CUtensorMap tmap_xh,   // Xhat    box {64 d, 64 rows}      dY gradient B operand, MN-major
+            const __grid_constant__ CUtensorMap tmap_g,    // G ring  [depth * P * 128, 256]   box {64 j, 64 i}
+            const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = ptx::smem_u32(smem);
+  if ((base & 1023u) != 0) __trap();
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pair_id = blockIdx.x >> 1;
+  const bool is_producer = pair_id < p.P;
+
+  // the small block sits at the same offset for both roles: behind the larger of the two layouts
+  const int body = max(producer_smem(p.nkc, p.stages_a + p.stages_b), consumer_smem(p.stages_c)) - SMALL;
+  const uint32_t bars = base + body;
+  auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + body + 512);
+  float* const colv = reinterpret_cast<float*>(smem + body + 1024);   // [2][2][256]
+
+  const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;
+  const float k2 = sc * LOG2E;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_y);
+    ptx::prefetch_tmap(&tmap_yh);
+    ptx::prefetch_tmap(&tmap_xh);
+    ptx::prefetch_tmap(&tmap_g);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAXS; ++s) {
+      ptx::mbar_init(bar(B_FULL_A + s), 1);
+      ptx::mbar_init(bar(B_EMPTY_A + s), 1);
+      ptx::mbar_init(bar(B_FULL_B + s), 1);
+      ptx::mbar_init(bar(B_EMPTY_B + s), 1);
+    }
+    ptx::mbar_init(bar(B_XFULL), 1);
+    ptx::mbar_init(bar(B_XEMPTY), 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar(B_SFULL + b), 1);
+      ptx::mbar_init(bar(B_SEMPTY + b), 2 * EPI_WARPS);
+      ptx::mbar_init(bar(B_ACCFULL + b), 1);
+      ptx::mbar_init(bar(B_ACCEMPTY + b), 2 * EPI_WARPS);
+    }
+    for (int k = 0; k < 4; ++k) {
+      ptx::mbar_init(bar(B_GFULL + k), 4);
+      ptx::mbar_init(bar(B_GEMPTY + k), 1);
+      ptx::mbar_init(bar(B_GSFULL + k), 2);     // the two epilogue warps of THIS CTA that wrote box k
+      ptx::mbar_init(bar(B_GSTORED + k), 1);    // the ring store has read box k out of shared memory
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_pair(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const uint32_t desc_hi_k = static_cast<uint32_t>(ptx::smem_desc_k_sw128(0) >> 32);
+  const uint32_t desc_hi_mn = static_cast<uint32_t>(ptx::smem_desc_mn_sw128(0, 8192) >> 32);
+  auto desc_lo = [&](uint32_t addr, uint32_t lbo16) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (lbo16 << 16); };
+  auto mk = [&](uint32_t hi, uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(hi) << 32) | lo; };
+
+  if (is_producer) {
+    // =========================================================================================== PRODUCER PAIR
+    const uint32_t x_smem = base;
+    const uint32_t g_smem = x_smem + p.nkc * X_CHUNK;
+    const uint32_t ring_a = g_smem + G_BYTES;
+    const uint32_t ring_b = ring_a + p.stages_a * STAGE_BYTES;
+    constexpr int S_COL0 = TMEM_COLS - 256;   // two logits buffers of 128 columns behind the accumulators
+
+    if (warp == 0) {
+      // ------------------------------------------------------------- TMA: resident X per wave, then Y rows (K-major)
+      if (ptx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          const int rb = w * p.P + pair_id;
+          if (rb >= p.n_rb) break;
+          const int i0 = rb * (2 * ROWS) + (int)rank * ROWS;
+          ptx::mbar_wait(bar(B_XEMPTY), (w & 1) ^ 1u);   // the previous wave's logits MMAs have read X
+          if (leader) ptx::mbar_arrive_expect_tx(bar(B_XFULL), 2 * p.nkc * X_CHUNK);
+          for (int kc = 0; kc < p.nkc; ++kc)
+            ptx::tma_load_2d_pair(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0);
+          for (int t = 0; t < p.n_steps; ++t) {
+            for (int g = 0; g < p.nkc; ++g) {
+              ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
+              if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
+              ptx::tma_load_2d_pair(ring_a + stage * STAGE_BYTES, &tmap_y, bar(B_FULL_A + stage), g * 64,
+                                    t * STEP_J + (int)rank * 128);
+              if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 2) {
+      // ------------------------------------------------------------- TMA: Yhat[j, d slice] boxes (MN-major)
+      if (ptx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          if (w * p.P + pair_id >= p.n_rb) break;
+          for (int t = 0; t < p.n_steps; ++t) {
+            for (int kc = 0; kc < 4; ++kc) {
+              for (int q = 0; q < p.nq2; ++q) {
+                const int wq = min(256, p.d - 256 * q);
+                const int half = wq >> 1;
+                const int ngr = half >> 6;
+                ptx::mbar_wait(bar(B_EMPTY_B + stage), phase ^ 1u);
+                if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), 2 * ngr * 8192);
+                for (int gi = 0; gi < ngr; ++gi)
+                  ptx::tma_load_2d_pair(ring_b + stage * STAGE_BYTES + gi * 8192, &tmap_yh, bar(B_FULL_B + stage),
+                                        256 * q + half * (int)rank + 64 * gi, t * STEP_J + 64 * kc);
+                if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ------------------------------------------------------------- logits MMA issuer (leader)
+      if (leader && ptx::elect_one()) {
+        constexpr uint32_t idesc_s = ptx::idesc_bf16_f32_major(2 * ROWS, STEP_J, 0, 0);
+        const uint32_t x_lo0 = desc_lo(x_smem, 1), a_lo0 = desc_lo(ring_a, 1);
+        int stage = 0;
+        uint32_t phase = 0, ready = 0, gs = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          if (w * p.P + pair_id >= p.n_rb) break;
+          ptx::mbar_wait(bar(B_XFULL), w & 1);
+          for (int t = 0; t < p.n_steps; ++t, ++gs) {
+            const int sb = gs & 1;
+            ptx::mbar_wait(bar(B_SEMPTY + sb), ((gs >> 1) & 1) ^ 1u);
+            const uint32_t d_tmem = tmem_base + S_COL0 + sb * 128;
+            for (int g = 0; g < p.nkc; ++g) {
+              if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
+              ptx::tc_fence_after();
+              int ns = stage + 1;
+              uint32_t np = phase;
+              if (ns == p.stages_a) { ns = 0; np ^= 1u; }
+              ready = ptx::mma_box_pair(d_tmem, mk(desc_hi_k, x_lo0 + g * (X_CHUNK >> 4)),
+                                        mk(desc_hi_k, a_lo0 + stage * (STAGE_BYTES >> 4)), 2, 2, idesc_s, g != 0,
+                                        bar(B_FULL_A + ns), np);
+              ptx::mma_commit_pair(bar(B_EMPTY_A + stage));
+              if (g == p.nkc - 1) ptx::mma_commit_pair(bar(B_SFULL + sb));
+              stage = ns;
+              phase = np;
+            }
+          }
+          ptx::mma_commit_pair(bar(B_XEMPTY));   // every logits MMA of this wave has read X
+        }
+      }
+      __syncwarp();
+    } else if (warp == 3) {
+      // ------------------------------------------------------------- dX gradient MMA issuer (leader)
+      if (leader && ptx::elect_one()) {
+        const uint32_t g_lo0 = desc_lo(g_smem, 1), b_lo0 = desc_lo(ring_b, 8192 >> 4);
+        int stage = 0;
+        uint32_t phase = 0, ready = 0, gs = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          if (w * p.P + pair_id >= p.n_rb) break;
+          ptx::mbar_wait(bar(B_ACCEMPTY), (w & 1) ^ 1u);   // the previous wave's accumulators have been drained
+          ptx::tc_fence_after();
+          for (int t = 0; t < p.n_steps; ++t, ++gs) {
+            for (int kc = 0; kc < 4; ++kc) {
+              ptx::mbar_wait(bar(B_GFULL + kc), gs & 1);
+              for (int q = 0; q < p.nq2; ++q) {
+                const int wq = min(256, p.d - 256 * q);
+                const uint32_t idesc_g = ptx::idesc_bf16_f32_major(2 * ROWS, wq, 0, 1);
+                if (!ready) ptx::mbar_wait(bar(B_FULL_B + stage), phase);
+                ptx::tc_fence_after();
+                int ns = stage + 1;
+                uint32_t np = phase;
+                if (ns == p.stages_b) { ns = 0; np ^= 1u; }
+                ready = ptx::mma_box_pair(tmem_base + 128 * q, mk(desc_hi_k, g_lo0 + kc * (8192 >> 4)),
+                                          mk(desc_hi_mn, b_lo0 + stage * (STAGE_BYTES >> 4)), 2, 2048 >> 4, idesc_g,
+                                          (t | kc) != 0, bar(B_FULL_B + ns), np);
+                ptx::mma_commit_pair(bar(B_EMPTY_B + stage));
+                stage = ns;
+                phase = np;
+              }
+              ptx::mma_commit_pair(bar(B_GEMPTY + kc));
+            }
+          }
+          ptx::mma_commit_pair(bar(B_ACCFULL));
+        }
+      }
+      __syncwarp();
+    } else if (warp == STORE_WARP) {
+      // ------------------------------------------------------------- ring store: G boxes of this CTA -> global ring
+      // A thread of its own, so that nothing on the epilogue's critical path touches global memory: the back-pressure
+      // spin (done[g - depth]), the bulk-group waits and the release that publishes a step all live here.
+      if (ptx::elect_one()) {
+        uint32_t gs = 0;
+        bool pending = false;
+        uint32_t g_prev = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          if (w * p.P + pair_id >= p.n_rb) break;
+          for (int t = 0; t < p.n_steps; ++t, ++gs) {
+            const uint32_t g = (uint32_t)w * (uint32_t)p.n_steps + (uint32_t)t;
+            const int row0 = ((int)(g % (uint32_t)p.depth) * p.P + pair_id) * 128 + (int)rank * ROWS;
+            // latency-critical part: the epilogue of the NEXT step waits for these boxes to be released
+            for (int kc = 0; kc < 4; ++kc) {
+              ptx::mbar_wait(bar(B_GSFULL + kc), gs & 1);
+              ptx::tma_store_2d(&tmap_g, g_smem + kc * 8192, 64 * kc, row0);
+              ptx::bulk_commit_group();
+            }
+            ptx::bulk_wait_group_read0();               // shared memory of the four boxes has been read
+            for (int kc = 0; kc < 4; ++kc) ptx::mbar_arrive(bar(B_GSTORED + kc));
+            // off the critical path: publish the PREVIOUS step (its four groups are older than the four just committed,
+            // so this does not wait for an L2 round trip), then the back-pressure check for the next step
+            if (pending) {
+              ptx::bulk_wait_group_le<4>();
+              publish(p.ready + g_prev);
+            }
+            pending = true;
+            g_prev = g;
+            if (g + 1 >= (uint32_t)p.depth && (t + 1 < p.n_steps || (w + 1) * p.P + pair_id < p.n_rb))
+              ptx::spin_until_ge(p.done + (g + 1 - p.depth), (uint32_t)p.n_half);
+          }
+        }
+        if (pending) {
+          ptx::bulk_wait_group0();
+          publish(p.ready + g_prev);
+        }
+      }
+      __syncwarp();
+    } else {
+      // ------------------------------------------------------------- epilogue: S tile -> bf16 G tile (MMA operand + ring)
+      const int e = warp - 4;
+      const int q = warp & 3;
+      const int h = e >> 2;
+      const int jh = q >> 1;
+      const int i_local = 32 * (q & 1) + lane;
+      const int te = threadIdx.x - 128;
+      const int jl0 = 128 * jh + 64 * h;
+      const int kc = 2 * jh + h;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t g_row = g_smem + kc * 8192 + (i_local >> 3) * 1024 + (i_local & 7) * 128;
+      const uint32_t sw = i_local & 7;
+      const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
+      const uint32_t gfull_leader = ptx::mapa(bar(B_GFULL + kc), 0);
+      const uint32_t accempty_leader = ptx::mapa(bar(B_ACCEMPTY), 0);
+      uint32_t gs = 0;
+
+      for (int w = 0; w < p.n_waves; ++w) {
+        const int rb = w * p.P + pair_id;
+        if (rb >= p.n_rb) break;
+        const int i_glob = rb * (2 * ROWS) + (int)rank * ROWS + i_local;
+        const float rx = p.rinv_x[i_glob];
+        const float u = p.row_w[i_glob] * pair::ex2((sc - p.row_m[i_glob]) * LOG2E);
+        float cw_n = p.col_w[te], cm_n = p.col_m[te], ry_n = p.rinv_y[te];
+
+        for (int t = 0; t < p.n_steps; ++t, ++gs) {
+          const int sb = gs & 1;
+          float* const cv = colv + (gs & 1) * 512;
+          cv[te] = ry_n * k2;                                          // S_ij log2(e) = acc * rinv_x[i] * cj
+          cv[256 + te] = cw_n * pair::ex2((sc - cm_n) * LOG2E);       // v_j
+          if (t + 1 < p.n_steps) {
+            const int jn = (t + 1) * STEP_J + te;
+            cw_n = p.col_w[jn]; cm_n = p.col_m[jn]; ry_n = p.rinv_y[jn];
+          }
+          pair::named_bar_sync(1, EPI_WARPS * 32);
+          const int dl = i_glob - (t * STEP_J + jl0);   // step-local index of the positive, if in [0, 64)
+          const bool has_diag = dl >= 0 && dl < 64;
+
+          ptx::mbar_wait(bar(B_SFULL + sb), (gs >> 1) & 1);
+          ptx::tc_fence_after();
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + sb * 128 + 64 * h + 32 * c, r);
+            ptx::tmem_ld_wait();
+            if (c == 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(sempty_leader + 8u * sb);
+            }
+            const float* const cjp = cv + jl0 + 32 * c;
+#pragma unroll
+            for (int x4 = 0; x4 < 8; ++x4) {
+              const float4 cj4 = *reinterpret_cast<const float4*>(cjp + 4 * x4);
+              const float4 vj4 = *reinterpret_cast<const float4*>(cjp + 256 + 4 * x4);
+              const float cjv[4] = {cj4.x, cj4.y, cj4.z, cj4.w};
+              const float vjv[4] = {vj4.x, vj4.y, vj4.z, vj4.w};
+              float g[4];
+#pragma unroll
+              for (int xx = 0; xx < 4; ++xx) {
+                const float y = __uint_as_float(r[4 * x4 + xx]) * rx;
+                g[xx] = pair::ex2(fmaf(y, cjv[xx], -k2)) * (u + vjv[xx]);   // exp(S_ij - s)(u_i + v_j)
+              }
+              if (has_diag) {
+#pragma unroll
+                for (int xx = 0; xx < 4; ++xx)
+                  if (dl == 32 * c + 4 * x4 + xx) g[xx] -= p.diag_w;
+              }
+              const __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]);
+              const __nv_bfloat162 p1 = __floats2bfloat162_rn(g[2], g[3]);
+              pk[16 * c + 2 * x4] = *reinterpret_cast<const uint32_t*>(&p0);
+              pk[16 * c + 2 * x4 + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+            }
+          }
+          ptx::mbar_wait(bar(B_GEMPTY + kc), (gs & 1) ^ 1u);    // the gradient MMAs of the previous step have read this box
+          ptx::mbar_wait(bar(B_GSTORED + kc), (gs & 1) ^ 1u);   // ... and so has its ring store
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            pair::st_shared_v4(g_row + ((static_cast<uint32_t>(ch) ^ sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2],
+                               pk[4 * ch + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive_cluster(gfull_leader);
+            ptx::mbar_arrive(bar(B_GSFULL + kc));
+          }
+        }
+
+        // the wave's accumulators: slot q2 holds dXhat[i, 256 q2 + ...] in the 2x2 layout
+        ptx::mbar_wait(bar(B_ACCFULL), w & 1);
+        ptx::tc_fence_after();
+        for (int q2 = 0; q2 < p.nq2; ++q2) {
+          const int halfw = min(256, p.d - 256 * q2) >> 1;
+          if (64 * h < halfw) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(t_lane + 128 * q2 + 64 * h + 32 * c, r);
+              ptx::tmem_ld_wait();
+              float* const dst = p.dx + (long long)i_glob * p.d + 256 * q2 + halfw * jh + 64 * h + 32 * c;
+#pragma unroll
+              for (int x4 = 0; x4 < 8; ++x4)
+                *reinterpret_cast<float4*>(dst + 4 * x4) =
+                    make_float4(__uint_as_float(r[4 * x4]) * sc, __uint_as_float(r[4 * x4 + 1]) * sc,
+                                __uint_as_float(r[4 * x4 + 2]) * sc, __uint_as_float(r[4 * x4 + 3]) * sc);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(accempty_leader);
+      }
+    }
+  } else {
+    // =========================================================================================== CONSUMER PAIR
+    const int cidx = pair_id - p.P;
+    const uint32_t ring_c = base;
+
+    if (warp == 0) {
+      // ------------------------------------------------------------- TMA: G^T boxes from the ring + Xhat boxes
+      if (ptx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          const int pw = min(p.P, p.n_rb - w * p.P);
+          for (int t = 0; t < p.n_steps; ++t) {
+            for (int hh = 0; hh < p.n_half; ++hh) {
+              if ((t * p.n_half + hh) % p.Q != cidx) continue;
+              const uint32_t g = (uint32_t)w * (uint32_t)p.n_steps + (uint32_t)t;
+              ptx::spin_until_ge(p.ready + g, 2u * (uint32_t)pw);
+              ptx::fence_proxy_async_all();
+              const int slot = (int)(g % (uint32_t)p.depth);
+              const int wq = min(256, p.d - 256 * hh);
+              const int ngr = wq >> 7;                   // 64-wide d groups this CTA supplies (N split over the pair)
+              for (int pp = 0; pp < pw; ++pp) {
+                for (int kb = 0; kb < 2; ++kb) {
+                  ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
+                  if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * (2 + ngr) * 8192);
+                  const uint32_t st = ring_c + stage * C_STAGE;
+                  const int grow = (slot * p.P + pp) * 128 + 64 * kb;
+                  const int xrow = (w * p.P + pp) * 128 + 64 * kb;
+                  for (int gi = 0; gi < 2; ++gi)
+                    ptx::tma_load_2d_pair(st + gi * 8192, &tmap_g, bar(B_FULL_A + stage), 128 * (int)rank + 64 * gi, grow);
+                  for (int gi = 0; gi < ngr; ++gi)
+                    ptx::tma_load_2d_pair(st + 16384 + gi * 8192, &tmap_xh, bar(B_FULL_A + stage),
+                                          256 * hh + (wq >> 1) * (int)rank + 64 * gi, xrow);
+                  if (++stage == p.stages_c) { stage = 0; phase ^= 1u; }
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ------------------------------------------------------------- dY gradient MMA issuer (leader)
+      if (leader && ptx::elect_one()) {
+        const uint32_t a_lo0 = desc_lo(ring_c, 8192 >> 4), b_lo0 = desc_lo(ring_c + 16384, 8192 >> 4);
+        int stage = 0;
+        uint32_t phase = 0, ready = 0, nt = 0;
+        for (int w = 0; w < p.n_waves; ++w) {
+          const int pw = min(p.P, p.n_rb - w * p.P);
+          for (int t = 0; t < p.n_steps; ++t) {
+            for (int hh = 0; hh < p.n_half; ++hh) {
+              if ((t * p.n_half + hh) % p.Q != cidx) continue;
+              const int buf = nt & 1;
+              ptx::mbar_wait(bar(B_ACCEMPTY + buf), ((nt >> 1) & 1) ^ 1u);
+              ptx::tc_fence_after();
+              const int wq = min(256, p.d - 256 * hh);
+              const uint32_t idesc = ptx::idesc_bf16_f32_major(256, wq, 1, 1);
+              const uint32_t d_tmem = tmem_base + buf * 256;
+              for (int k = 0; k < 2 * pw; ++k) {
+                if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
+                ptx::tc_fence_after();
+                int ns = stage + 1;
+                uint32_t np = phase;
+                if (ns == p.stages_c) { ns = 0; np ^= 1u; }
+                ready = ptx::mma_box_pair(d_tmem, mk(desc_hi_mn, a_lo0 + stage * (C_STAGE >> 4)),
+                                          mk(desc_hi_mn, b_lo0 + stage * (C_STAGE >> 4)), 2048 >> 4, 2048 >> 4, idesc,
+                                          k != 0, bar(B_FULL_A + ns), np);
+                ptx::mma_commit_pair(bar(B_EMPTY_A + stage));
+                stage = ns;
+                phase = np;
+              }
+              ptx::mma_commit_pair(bar(B_ACCFULL + buf));
+              ++nt;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
+      // ------------------------------------------------------------- epilogue: accumulator -> dYhat (read-modify-write)
+      const int q = warp & 3;
+      const int hcol = (warp - 4) >> 2;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t accempty_leader = ptx::mapa(bar(B_ACCEMPTY), 0);
+      uint32_t nt = 0;
+      for (int w = 0; w < p.n_waves; ++w) {
+        for (int t = 0; t < p.n_steps; ++t) {
+          for (int hh = 0; hh < p.n_half; ++hh) {
+            if ((t * p.n_half + hh) % p.Q != cidx) continue;
+            const int buf = nt & 1;
+            ptx::mbar_wait(bar(B_ACCFULL + buf), (nt >> 1) & 1);
+            ptx::tc_fence_after();
+            if (leader && warp == 4 && lane == 0)   // every MMA of the task is complete: its ring tiles have been read
+              ptx::red_release_gpu_add(p.done + ((uint32_t)w * (uint32_t)p.n_steps + (uint32_t)t), 1u);
+            const int wq = min(256, p.d - 256 * hh);
+            const int wh = wq >> 1;                  // columns per epilogue-warp half
+            const long long j = (long long)t * STEP_J + (int)rank * 128 + 32 * q + lane;
+            float* const drow = p.dy + j * p.d + 256 * hh + hcol * wh;
+            for (int c = 0; c < (wh >> 5); ++c) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(t_lane + buf * 256 + hcol * wh + 32 * c, r);
+              ptx::tmem_ld_wait();
+              float4* const dst = reinterpret_cast<float4*>(drow + 32 * c);
+              if (w == 0) {
+#pragma unroll
+                for (int x4 = 0; x4 < 8; ++x4)
+                  dst[x4] = make_float4(__uint_as_float(r[4 * x4]) * sc, __uint_as_float(r[4 * x4 + 1]) * sc,
+                                        __uint_as_float(r[4 * x4 + 2]) * sc, __uint_as_float(r[4 * x4 + 3]) * sc);
+              } else {
+                float4 old[8];
+#pragma unroll
+                for (int x4 = 0; x4 < 8; ++x4) old[x4] = dst[x4];
+#pragma unroll
+                for (int x4 = 0; x4 < 8; ++x4)
+                  dst[x4] = make_float4(fmaf(__uint_as_float(r[4 * x4]), sc, old[x4].x),
+                                        fmaf(__uint_as_float(r[4 * x4 + 1]), sc, old[x4].y),
+                                        fmaf(__uint_as_float(r[4 * x4 + 2]), sc, old[x4].z),
+                                        fmaf(__uint_as_float(r[4 * x4 + 3]), sc, old[x4].w));
+              }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(accempty_leader + 8u * buf);
+            ++nt;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
+}  // namespace pair2

@@ -80,6 +80,41 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst_smem, const CUtensor
       : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async-group completion).  The box is read from shared memory through the async
+// proxy: generic-proxy writes to it need fence.proxy.async first; the source may be reused after wait_group.read.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// at most N of this thread's most recent bulk groups still pending (older ones complete, writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_le() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// full cross-proxy fence (generic <-> async, every state space): orders TMA traffic to GLOBAL memory against flags that
+// are written / read with ordinary loads and stores
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ------------------------------------------------------------------ inter-CTA flags in global memory (gpu scope)
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin until *p >= want: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t want) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(p) < want) {
+    __nanosleep(64);
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // ------------------------------------------------------------------ clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

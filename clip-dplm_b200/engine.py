@@ -179,6 +179,41 @@ class CudaEngine:
                                                 ws.numel(), _stream()), "backward_dx")
         return dx, ds
 
+    def backward_both_bytes(self, n, d, dtype, scale, flags=0):
+        """Workspace of the two-sided backward (one sweep emits dA and dB) for an [n,d] x [n,d] step; 0 = not served."""
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.clipnce_backward_both_workspace_bytes(n, d, _DT[dtype], float(scale), flags, ctypes.byref(nbytes)),
+                   "backward_both_workspace_bytes")
+        return nbytes.value
+
+    @_guard
+    def backward_both(self, x, y, rinv_x, rinv_y, scale, row_m, row_w, col_m, col_w, diag_w, x_orig, y_orig, out_dtype,
+                      grad_scale=None, flags=0, want_dscale=True, scale_dev=None):
+        """Both backward sides of the single-GPU symmetric step in one sweep over the logits tiles (clipnce_backward_both_dx)
+        -> dx, dy [n,d] in ``out_dtype`` (gradients of the caller's rows), d_scale_sum [1] f32 (or None)."""
+        n, d = x.shape
+        dev = x.device
+        self._chk(x_orig, (torch.bfloat16, torch.float32), "x_orig")
+        self._chk(y_orig, (x_orig.dtype,), "y_orig")
+        key = ("both", n, d, x.dtype, flags, dev, torch.cuda.current_stream(dev).cuda_stream)
+        nbytes = self.backward_both_bytes(n, d, x.dtype, scale, flags)   # host-only call; depends on the producer split too
+        if nbytes == 0:
+            raise RuntimeError("clip_dplm_b200: the two-sided backward does not serve this shape")
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
+        dx = torch.empty((n, d), dtype=out_dtype, device=dev)
+        dy = torch.empty((n, d), dtype=out_dtype, device=dev)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+        xo = x if x_orig.dtype == x.dtype else x_orig
+        yo = y if y_orig.dtype == y.dtype else y_orig
+        _lib.check(self.lib.clipnce_backward_both_dx(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n, d, float(scale), _p(scale_dev),
+                                                     _p(row_m), _p(row_w), _p(col_m), _p(col_w), float(diag_w), _DT[x.dtype],
+                                                     flags, _p(xo), _p(yo), _DT[xo.dtype], _p(grad_scale), _p(dx), _p(dy),
+                                                     _DT[out_dtype], _p(ds), _p(ws), ws.numel(), _stream()), "backward_both_dx")
+        return dx, dy, ds
+
     @_guard
     def softmax_weights(self, l, coef):
         out = torch.empty_like(l)

@@ -147,6 +147,17 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     diag_w = 1.0 / n_glob
     kw = {"scale_dev": st.scale_dev} if st.scale_dev is not None else {}
 
+    # one GPU, plain symmetric loss: both sides from ONE sweep over the logits tiles where the engine serves the shape
+    # (8 N^2 d executed per step instead of 10; csrc/kernels_pair2.cuh)
+    both = getattr(engine, "backward_both", None)
+    if (both is not None and st.xchg is None and st.symmetric and st.y is st.b_c and st.xa is st.a_c and not st.want_t
+            and st.a.dtype == st.b.dtype and (grad_dtype_a or st.a.dtype) == (grad_dtype_b or st.b.dtype)
+            and st.compute_dtype == torch.bfloat16 and engine.backward_both_bytes(n, st.a_c.shape[1], st.compute_dtype,
+                                                                                  st.scale, st.flags) > 0):
+        da, db, ds = both(st.a_c, st.b_c, st.rinv_a, st.rinv_b, st.scale, st.row_m, row_w, col_m, col_w, diag_w, st.a, st.b,
+                          grad_dtype_a or st.a.dtype, grad_scale, st.flags, want_dscale=True, **kw)
+        return da, db, ds
+
     # side A: local rows of A x all columns -> dA (normalise backward fused into the tail) and sum G.S over the local
     # row block
     da, ds = engine.backward_dx(st.a_c, st.y, st.y_t, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w, col_m, col_w,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 102
+#define CLIPNCE_VERSION 103
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -160,6 +160,29 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
                         float diag_w, int dtype, int flags,
                         const void* x_orig, int in_dtype, const float* grad_scale, void* dx, int out_dtype,
                         float* d_scale_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * BOTH backward sides of the single-GPU symmetric step in ONE sweep over the logits tiles (8 N^2 d executed per step
+ * instead of the 10 N^2 d of two clipnce_backward_dx calls): `loss.backward()` of current/rna_clip_codes.ipynb:2074,
+ * run1/full.py:134, old/clip_opt.py:167.  A persistent role-specialised kernel (csrc/kernels_pair2.cuh): producer CTA
+ * pairs recompute S, form the bf16 gradient tile G once, accumulate dA_hat and hand G through an L2-resident ring to
+ * consumer pairs that accumulate dB_hat = G^T A_hat.
+ * x = A rows, y = B rows [n,d] bf16 (n_rows == n_cols == n, positives on the diagonal), statistics as for
+ * clipnce_backward_dx (row_* of the rows of x, col_* of the rows of y).  dx / dy [n,d] out_dtype: gradients of the
+ * caller's rows x_orig / y_orig (the normalise backward and grad_scale are applied as in clipnce_backward_dx);
+ * d_scale_sum [1] += sum_ij G_ij S_ij (or NULL).
+ * clipnce_backward_both_workspace_bytes() returns 0 bytes in *out when the shape is not served (then use two
+ * clipnce_backward_dx calls): bf16, fixed-shift regime (2 s <= 86), d in {128,...,512}, n % 256 == 0, n >= 16384, and a
+ * device on which all CTA pairs of the persistent grid are co-resident.  CLIPNCE_NO_BWD2=1 disables it.
+ */
+int clipnce_backward_both_workspace_bytes(int64_t n, int64_t d, int dtype, float scale, int flags, size_t* out);
+int clipnce_backward_both_dx(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n,
+                             int64_t d, float scale, const float* scale_dev,
+                             const float* row_m, const float* row_w, const float* col_m, const float* col_w,
+                             float diag_w, int dtype, int flags,
+                             const void* x_orig, const void* y_orig, int in_dtype, const float* grad_scale,
+                             void* dx, void* dy, int out_dtype, float* d_scale_sum,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* w_i = coef / l_i  (l = +inf -> 0).  Builds row_w / col_w from the forward's sums. */
 int clipnce_softmax_weights(const float* l, int64_t n, float coef, float* w, void* stream);

@@ -433,3 +433,32 @@ def test_benchmarked_shapes_against_sampled_oracle(n, d, ls):
     ref = SO.sampled_reference(a, b, math.exp(ls), rows_a, rows_b)
     cmp = SO.compare(ref, loss, da[rows_a].numpy(), db[rows_b].numpy(), dt, loss_tol=LOSS_RTOL_BF16, grad_tol=GRAD_RTOL_BF16)
     assert cmp["ok"], cmp
+
+
+# ------------------------------------------------------------------------------------------------
+# two-sided backward (csrc/kernels_pair2.cuh): one sweep over the logits tiles emits dA and dB
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,forced_p", [(4096, 512, 0), (4096, 512, 5), (2048, 256, 3), (2048, 128, 0), (3072, 384, 7)])
+def test_two_sided_backward(monkeypatch, n, d, forced_p):
+    """clipnce_backward_both_dx against the dense float64 closed form AND against the two-sweep path on the same inputs.
+    `forced_p` producer pairs force several row-block waves (the last one partly filled), ring wrap-around and the
+    read-modify-write of dB across waves at a size the dense oracle still reaches."""
+    from clip_dplm_b200.engine import CudaEngine
+    monkeypatch.setenv("CLIPNCE_BWD2_MIN_N", "256")
+    if forced_p:
+        monkeypatch.setenv("CLIPNCE_BWD2_P", str(forced_p))
+    assert CudaEngine().backward_both_bytes(n, d, torch.bfloat16, 1 / 0.07) > 0, "two-sided backward not served on this device"
+    a, b = O.make_inputs(n, d, seed=91)
+    loss2, da2, db2, dt2 = run_fused(a, b, O.LOGIT_SCALE_INIT, torch.bfloat16)
+    monkeypatch.setenv("CLIPNCE_NO_BWD2", "1")
+    loss1, da1, db1, dt1 = run_fused(a, b, O.LOGIT_SCALE_INIT, torch.bfloat16)
+    monkeypatch.delenv("CLIPNCE_NO_BWD2")
+    cf = O.closed_form(a.numpy(), b.numpy(), math.exp(O.LOGIT_SCALE_INIT))
+    assert loss1 == loss2
+    assert rel(da2, cf["d_a"]) <= GRAD_RTOL_BF16 and rel(db2, cf["d_b"]) <= GRAD_RTOL_BF16
+    assert abs(dt2 - cf["d_scale_sum"]) <= GRAD_RTOL_BF16 * abs(cf["d_scale_sum"])
+    # the two paths round G the same way; only the 1/norm factors move between G and the bf16 operands
+    assert rel(da2, da1) <= 5e-3 and rel(db2, db1) <= 5e-3
+    # rerun: bit-identical (fixed-order accumulation, no atomics on data)
+    _, da3, db3, _ = run_fused(a, b, O.LOGIT_SCALE_INIT, torch.bfloat16)
+    assert torch.equal(da2, da3) and torch.equal(db2, db3)
