@@ -247,9 +247,18 @@ def run_ours(args, rank, local_rank, world):
             return self._timed("bwd", super().backward_dx, *a, **k)
 
         def backward_both(self, *a, **k):
-            # 2 x normalise-to-bf16, the two-sided contraction kernel, 2 x finish_rows, the scalar reduction
-            self.launches += 6
+            # the two-sided contraction kernel, 2 x finish_rows, the scalar reduction
+            self.launches += 4
             return self._timed("bwd2", super().backward_both, *a, **k)
+
+        def backward_both_sharded(self, *a, **k):
+            # the two-sided contraction + reduce-scatter kernel, finish_rows of side A, the scalar reduction
+            self.launches += 3
+            return self._timed("bwd2", super().backward_both_sharded, *a, **k)
+
+        def finish_slots(self, *a, **k):
+            self.launches += 1
+            return super().finish_slots(*a, **k)
 
         def normalize(self, *a, **k):
             self.launches += 1

@@ -636,8 +636,8 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
 // ---- two-sided backward (kernels_pair2.cuh) ----------------------------------------------------------------------------
 namespace {
 struct Bwd2Plan {
-  int P, Q, n_rb, n_waves, n_steps, n_half, depth, stages_a, stages_b, stages_c, smem;
-  size_t off_flags, off_xh, off_yh, off_ring, off_dxh, off_dyh, off_part, bytes;
+  int P, Q, n_rb, n_seg, seg_steps, n_items, n_rounds, n_steps, n_half, depth, stages_a, stages_b, stages_c, smem;
+  size_t off_flags, off_ring, off_dxh, off_dyh, off_part, bytes;
 };
 
 bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resident at once
@@ -665,36 +665,60 @@ bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resid
   return ok;
 }
 
-bool bwd2_plan(int64_t n, int64_t d, int dtype, float scale, int flags, Bwd2Plan* pl) {
+// world == 0: one GPU (n_rows == n_cols, every column segment stays local); world >= 2: row-sharded step, the rank's
+// n_rows = n_cols / world rows against all columns, one segment per owner rank.
+bool bwd2_plan(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale, int flags, int world, Bwd2Plan* pl) {
   if (!tc_eligible(dtype, d, scale, flags) || !pair_eligible(d) || d > 512) return false;
-  int64_t min_n = 16384;   // below this the row blocks do not fill the producer pairs (CLIPNCE_BWD2_MIN_N: test hook)
-  if (const char* e = getenv("CLIPNCE_BWD2_MIN_N")) min_n = atoll(e);
-  if (n % 256 != 0 || n < min_n || n < 256 || n > (1ll << 22)) return false;
+  if (world == 1 || world < 0 || world > pair2::MAX_WORLD) return false;
+  if (world == 0 ? n_rows != n_cols : n_rows * world != n_cols) return false;
+  int64_t min_pairs = 16384ll * 16384ll;   // below this the items do not fill the producer pairs (CLIPNCE_BWD2_MIN_N: test hook)
+  if (const char* e = getenv("CLIPNCE_BWD2_MIN_N")) min_pairs = atoll(e) * atoll(e);
+  if (n_rows % 128 != 0 || n_cols % 256 != 0 || n_rows * n_cols < min_pairs || n_cols > (1ll << 22)) return false;
+  if (world >= 2 && (n_cols / world) % 256 != 0) return false;
   const int slots = pair_slots();
   if (slots < 8) return false;
-  pl->n_rb = (int)(n / 128);
-  pl->n_steps = (int)(n / 256);
+  pl->n_rb = (int)(n_rows / 128);
+  pl->n_steps = (int)(n_cols / 256);
   pl->n_half = (int)ceil_div(d, 256);
-  // producers : consumers.  A producer pair spends two tile units per step (logits + dX), the consumers one per producer
-  // tile (dY) at a rate `r` times a producer's (plain GEMM, 256 x 256 instructions): pick the split with the shortest
-  // modelled time, row-block waves included.  CLIPNCE_BWD2_P forces the number of producer pairs.
+  // Split of the CTA pairs into producers and consumers, and (one GPU) the number of column segments.  Model, in units of
+  // one producer step: a producer item costs seg_steps + 1 (accumulator drain, reload of the resident rows, pipeline
+  // refill), the consumers work through one tile unit per producer tile at `r` times a producer's rate (measured on B200,
+  // N = 65536, d = 512: P = 48..52 within 1 %), every segment beyond the first costs a pass over an [n_rows, d] fp32 slab.
   const char* ef = getenv("CLIPNCE_BWD2_P");
-  const int forced = ef ? atoi(ef) : 0;
+  const int forced_p = ef ? atoi(ef) : 0;
+  const char* es = getenv("CLIPNCE_BWD2_SEG");
+  const int forced_seg = es ? atoi(es) : 0;
   const char* er = getenv("CLIPNCE_BWD2_RATIO");
-  const double r = (er && atof(er) > 0.1) ? atof(er) : 1.0;   // measured on B200 (N = 65536, d = 512): P = 48..52 within 1 %, 44 and 54 5 % slower
-  int best_p = 0;
+  const double r = (er && atof(er) > 0.1) ? atof(er) : 1.0;
   double best_t = 1e300;
-  for (int P = slots / 2; P <= slots - 2; ++P) {
-    const int Q = slots - P;
-    const double tp = 2.0 * (double)ceil_div(pl->n_rb, P);
-    const double tc_ = (double)pl->n_rb / ((double)Q * r);
-    const double t = tp > tc_ ? tp : tc_;
-    if (t < best_t - 1e-9) { best_t = t; best_p = P; }
+  int best_p = 0, best_seg = 0;
+  for (int n_seg = 1; n_seg <= 8; n_seg *= 2) {
+    int ns = world >= 2 ? world : n_seg;
+    if (world == 0 && forced_seg >= 1) ns = forced_seg;
+    if (pl->n_steps % ns != 0) continue;
+    const int seg_steps = pl->n_steps / ns;
+    if (seg_steps < 8 && ns > 1 && world == 0 && forced_seg < 1) continue;
+    const int64_t n_items = (int64_t)pl->n_rb * ns;
+    const double slab_steps = (double)(ns - 1) * (double)n_rows * (double)d * 8.0 / 3e12 / 3.9e-6;
+    const bool force = forced_p >= 1 && forced_p <= slots - 1;
+    for (int Pe = force ? forced_p : slots / 2; Pe <= (force ? forced_p : slots - 2); ++Pe) {
+      const int Q = slots - Pe;
+      const double tp = (double)ceil_div(n_items, Pe) * ((double)seg_steps + 1.0);
+      const double tc_ = (double)n_items * (double)seg_steps / ((double)Q * 2.0 * r);
+      // measured (one GPU, N = 65536, d = 512): 1 segment 11.9 ms, 2 (auto) 12.1, 4 12.5 -- the extra slabs and item
+      // prologues cost more than the fuller rounds return, so more segments must win by a clear margin
+      const double t = ((tp > tc_ ? tp : tc_) + slab_steps) * (world == 0 && ns > 1 ? 1.08 : 1.0);
+      if (t < best_t - 1e-9) { best_t = t; best_p = Pe; best_seg = ns; }
+    }
+    if (world >= 2 || forced_seg >= 1) break;
   }
-  if (forced >= 1 && forced <= slots - 1) best_p = forced;
+  if (best_p == 0) return false;
   pl->P = best_p;
   pl->Q = slots - best_p;
-  pl->n_waves = (int)ceil_div(pl->n_rb, pl->P);
+  pl->n_seg = best_seg;
+  pl->seg_steps = pl->n_steps / best_seg;
+  pl->n_items = pl->n_rb * best_seg;
+  pl->n_rounds = (int)ceil_div(pl->n_items, pl->P);
   pl->depth = pair2::RING_DEPTH;
   if (const char* e = getenv("CLIPNCE_BWD2_DEPTH")) { const int v = atoi(e); if (v >= 2 && v <= 64) pl->depth = v; }
   const int nkc = (int)(d / 64);
@@ -708,24 +732,75 @@ bool bwd2_plan(int64_t n, int64_t d, int dtype, float scale, int flags, Bwd2Plan
   pl->smem = ps > cs ? ps : cs;
   size_t off = 0;
   auto region = [&](size_t bytes) { const size_t o = off; off = (size_t)round_up((int64_t)(off + bytes), 256); return o; };
-  pl->off_flags = region(sizeof(uint32_t) * 2 * (size_t)pl->n_waves * (size_t)pl->n_steps);
-  pl->off_xh = region(2 * (size_t)n * (size_t)d);
-  pl->off_yh = region(2 * (size_t)n * (size_t)d);
+  pl->off_flags = region(sizeof(uint32_t) * 2 * (size_t)pl->n_rounds * (size_t)pl->seg_steps);
   pl->off_ring = region((size_t)pl->depth * (size_t)pl->P * 128 * 256 * 2);
-  pl->off_dxh = region(sizeof(float) * (size_t)n * (size_t)d);
-  pl->off_dyh = region(sizeof(float) * (size_t)n * (size_t)d);
-  pl->off_part = region(sizeof(float) * ((size_t)ceil_div(n, 8) + (size_t)n));
+  pl->off_dxh = region(sizeof(float) * (size_t)pl->n_seg * (size_t)n_rows * (size_t)d);
+  pl->off_dyh = region(sizeof(float) * (size_t)n_cols * (size_t)d);
+  pl->off_part = region(sizeof(float) * (size_t)ceil_div(n_rows > n_cols ? n_rows : n_cols, 8));
   pl->bytes = off;
   return true;
+}
+
+// One pass over the fp32 gradient of normalised rows: sum of n_split slabs + row dots (sum G.S) + normalise backward.
+int launch_finish(const float* parts, int n_split, int64_t slab_elems, const void* xc, const void* xo, int in_dtype,
+                  const float* rinv, const float* grad_scale, int64_t n, int64_t d, void* dx, int out_dtype, float* ds_part,
+                  cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(n, 8);
+  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  const int di = (int)d;
+#define FINISH3(TI, TO)                                                                                                \
+  aux::finish_rows_v4<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(parts, n_split, slab_elems, (const __nv_bfloat16*)xc, \
+                                                                      (const TI*)xo, rinv, grad_scale, n, di, (TO*)dx, ds_part)
+  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH3(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == CLIPNCE_BF16) FINISH3(__nv_bfloat16, float);
+  else if (out_dtype == CLIPNCE_BF16) FINISH3(float, __nv_bfloat16);
+  else FINISH3(float, float);
+#undef FINISH3
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bwd2_launch(const Bwd2Plan& pl, const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* scale_dev, const float* row_m,
+                const float* row_w, const float* col_m, const float* col_w, float diag_w, char* ws, float* const* dy_peer,
+                int world, cudaStream_t st) {
+  uint32_t* flags_dev = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
+  const size_t n_flags = (size_t)pl.n_rounds * (size_t)pl.seg_steps;
+  CUDA_TRY(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * 2 * n_flags, st));
+  pair2::Params p;
+  memset(&p, 0, sizeof p);
+  p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
+  p.nkc = (int)(d / 64); p.nq2 = (int)ceil_div(d, 256); p.n_half = pl.n_half;
+  p.n_rb = pl.n_rb; p.n_seg = pl.n_seg; p.seg_steps = pl.seg_steps; p.n_items = pl.n_items; p.n_rounds = pl.n_rounds;
+  p.P = pl.P; p.Q = pl.Q; p.depth = pl.depth;
+  p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c;
+  p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev; p.diag_w = diag_w;
+  p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_w = row_w; p.col_m = col_m; p.col_w = col_w;
+  p.dx = reinterpret_cast<float*>(ws + pl.off_dxh);
+  p.dy = reinterpret_cast<float*>(ws + pl.off_dyh);
+  p.world = world;
+  for (int s = 0; s < world; ++s) p.dy_peer[s] = dy_peer[s];
+  p.ready = flags_dev; p.done = flags_dev + n_flags;
+  CUtensorMap tx, ty, tyg, tg;
+  int rc;
+  if ((rc = make_tmap(&tx, x, d, n_rows, d, pair2::ROWS))) return rc;
+  if ((rc = make_tmap(&ty, y, d, n_cols, d, 128))) return rc;
+  if ((rc = make_tmap(&tyg, y, d, n_cols, d, 64))) return rc;
+  if ((rc = make_tmap(&tg, ws + pl.off_ring, 256, (int64_t)pl.depth * pl.P * 128, 256, 64))) return rc;
+  pair2::bwd2_kernel<<<2 * (pl.P + pl.Q), pair2::THREADS, pl.smem, st>>>(tx, ty, tyg, tg, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 }  // namespace
 
 extern "C" {
 
-int clipnce_backward_both_workspace_bytes(int64_t n, int64_t d, int dtype, float scale, int flags, size_t* out) {
+int clipnce_backward_both_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale, int flags,
+                                          int world, size_t* out) {
   if (!out) return fail(CLIPNCE_EINVAL, "backward_both_workspace_bytes: null pointer");
   Bwd2Plan pl;
-  *out = (n >= 1 && d >= 1 && bwd2_plan(n, d, dtype, scale, flags, &pl) && check_device_sm100() == 0 && bwd2_device_ok()) ? pl.bytes : 0;
+  *out = (n_rows >= 1 && n_cols >= 1 && d >= 1 && bwd2_plan(n_rows, n_cols, d, dtype, scale, flags, world, &pl) &&
+          check_device_sm100() == 0 && bwd2_device_ok()) ? pl.bytes : 0;
   return 0;
 }
 
@@ -745,73 +820,81 @@ int clipnce_backward_both_dx(const void* x, const void* y, const float* rinv_x, 
   int rc = check_device_sm100();
   if (rc) return rc;
   Bwd2Plan pl;
-  if (!bwd2_plan(n, d, dtype, scale, flags, &pl) || !bwd2_device_ok())
+  if (!bwd2_plan(n, n, d, dtype, scale, flags, 0, &pl) || !bwd2_device_ok())
     return fail(CLIPNCE_EUNSUPPORTED, "backward_both_dx: shape not served (see clipnce_backward_both_workspace_bytes)");
   if (workspace_bytes < pl.bytes) return fail(CLIPNCE_EWORKSPACE, "backward_both_dx: workspace %zu < %zu", workspace_bytes, pl.bytes);
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(workspace);
-  uint32_t* flags_dev = reinterpret_cast<uint32_t*>(ws + pl.off_flags);
-  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_xh);
-  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_yh);
-  void* ring = ws + pl.off_ring;
-  float* dxh = reinterpret_cast<float*>(ws + pl.off_dxh);
-  float* dyh = reinterpret_cast<float*>(ws + pl.off_dyh);
+  if ((rc = bwd2_launch(pl, x, y, rinv_x, rinv_y, n, n, d, 0, scale, scale_dev, row_m, row_w, col_m, col_w, diag_w, ws, nullptr,
+                        0, st)))
+    return rc;
+  // tails: segment sum + row dots (sum G.S, side A only) + normalise backward, one pass per side
   float* ds_part = reinterpret_cast<float*>(ws + pl.off_part);
-  float* rinv_scratch = ds_part + ceil_div(n, 8);
-  const int di = (int)d;
-
-  // normalised rows rounded to bf16: the operands both gradient GEMMs contract the shared G tile against
-  {
-    const int wpb = 8;
-    dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
-    aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)x, n, di, xh, rinv_scratch);
-    aux::normalize_rows<<<grid, block, 0, st>>>((const __nv_bfloat16*)y, n, di, yh, rinv_scratch);
-    CUDA_TRY(cudaGetLastError());
-  }
-  CUDA_TRY(cudaMemsetAsync(flags_dev, 0, sizeof(uint32_t) * 2 * (size_t)pl.n_waves * (size_t)pl.n_steps, st));
-
-  pair2::Params p;
-  memset(&p, 0, sizeof p);
-  p.n = (int)n; p.d = di; p.nkc = (int)(d / 64); p.nq2 = (int)ceil_div(d, 256); p.n_steps = pl.n_steps; p.n_half = pl.n_half;
-  p.P = pl.P; p.Q = pl.Q; p.n_rb = pl.n_rb; p.n_waves = pl.n_waves; p.depth = pl.depth;
-  p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c;
-  p.scale = scale; p.scale_dev = scale_dev; p.diag_w = diag_w;
-  p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_w = row_w; p.col_m = col_m; p.col_w = col_w;
-  p.dx = dxh; p.dy = dyh;
-  p.ready = flags_dev; p.done = flags_dev + (size_t)pl.n_waves * (size_t)pl.n_steps;
-  CUtensorMap tx, ty, tyh, txh, tg;
-  if ((rc = make_tmap(&tx, x, d, n, d, pair2::ROWS))) return rc;
-  if ((rc = make_tmap(&ty, y, d, n, d, 128))) return rc;
-  if ((rc = make_tmap(&tyh, yh, d, n, d, 64))) return rc;
-  if ((rc = make_tmap(&txh, xh, d, n, d, 64))) return rc;
-  if ((rc = make_tmap(&tg, ring, 256, (int64_t)pl.depth * pl.P * 128, 256, 64))) return rc;
-  pair2::bwd2_kernel<<<2 * (pl.P + pl.Q), pair2::THREADS, pl.smem, st>>>(tx, ty, tyh, txh, tg, p);
-  CUDA_TRY(cudaGetLastError());
-
-  // tails: row dots (sum G.S, side A only) + normalise backward, one pass per side
-  const int64_t n_blk = ceil_div(n, 8);
-  const size_t smem = sizeof(float) * 8 * (size_t)d;
-  const unsigned grid = (unsigned)n_blk;
-  const int64_t slab = n * d;
-#define FINISH2(TI, TO)                                                                                                      \
-  do {                                                                                                                       \
-    aux::finish_rows_v4<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(dxh, 1, slab, (const __nv_bfloat16*)x, (const TI*)x_orig, \
-                                                                        rinv_x, grad_scale, n, di, (TO*)dx,                 \
-                                                                        d_scale_sum ? ds_part : nullptr);                   \
-    aux::finish_rows_v4<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(dyh, 1, slab, (const __nv_bfloat16*)y, (const TI*)y_orig, \
-                                                                        rinv_y, grad_scale, n, di, (TO*)dy, nullptr);       \
-  } while (0)
-  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH2(__nv_bfloat16, __nv_bfloat16);
-  else if (in_dtype == CLIPNCE_BF16) FINISH2(__nv_bfloat16, float);
-  else if (out_dtype == CLIPNCE_BF16) FINISH2(float, __nv_bfloat16);
-  else FINISH2(float, float);
-#undef FINISH2
-  CUDA_TRY(cudaGetLastError());
+  if ((rc = launch_finish(reinterpret_cast<float*>(ws + pl.off_dxh), pl.n_seg, n * d, x, x_orig, in_dtype, rinv_x, grad_scale, n, d,
+                          dx, out_dtype, d_scale_sum ? ds_part : nullptr, st)))
+    return rc;
+  if ((rc = launch_finish(reinterpret_cast<float*>(ws + pl.off_dyh), 1, n * d, y, y_orig, in_dtype, rinv_y, grad_scale, n, d, dy,
+                          out_dtype, nullptr, st)))
+    return rc;
   if (d_scale_sum) {
-    aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)n_blk, 1.f, d_scale_sum);
+    aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)ceil_div(n, 8), 1.f, d_scale_sum);
     CUDA_TRY(cudaGetLastError());
   }
   return 0;
+}
+
+int clipnce_backward_both_sharded(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                                  int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* scale_dev,
+                                  const float* row_m, const float* row_w, const float* col_m, const float* col_w,
+                                  float diag_w, int dtype, int flags, const void* x_orig, int in_dtype,
+                                  const float* grad_scale, void* dx, int out_dtype, float* d_scale_sum,
+                                  void* const* peer_base, int world, int rank, int64_t slots_offset, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !col_m || !col_w || !x_orig || !dx || !workspace || !peer_base)
+    return fail(CLIPNCE_EINVAL, "backward_both_sharded: null pointer");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "backward_both_sharded: bad dtype");
+  if (in_dtype == dtype && x_orig != x) return fail(CLIPNCE_EINVAL, "backward_both_sharded: x_orig of the compute type must be x itself");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(workspace)) return fail(CLIPNCE_EINVAL, "backward_both_sharded: operands must be 16-byte aligned");
+  if (world < 2 || world > pair2::MAX_WORLD || rank < 0 || rank >= world || slots_offset < 0 || slots_offset % 16 != 0)
+    return fail(CLIPNCE_EINVAL, "backward_both_sharded: bad world / rank / slots_offset");
+  if (diag_offset != (int64_t)rank * n_rows) return fail(CLIPNCE_EINVAL, "backward_both_sharded: diag_offset must be rank * n_rows");
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  Bwd2Plan pl;
+  if (!bwd2_plan(n_rows, n_cols, d, dtype, scale, flags, world, &pl) || !bwd2_device_ok())
+    return fail(CLIPNCE_EUNSUPPORTED, "backward_both_sharded: shape not served (see clipnce_backward_both_workspace_bytes)");
+  if (workspace_bytes < pl.bytes) return fail(CLIPNCE_EWORKSPACE, "backward_both_sharded: workspace %zu < %zu", workspace_bytes, pl.bytes);
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* dy_peer[pair2::MAX_WORLD];
+  for (int s = 0; s < world; ++s) {   // this rank's slot in rank s's buffer: [n_rows, d] f32 (n_rows == columns per owner)
+    if (!peer_base[s] || !aligned16(peer_base[s])) return fail(CLIPNCE_EINVAL, "backward_both_sharded: peer buffer %d is null or unaligned", s);
+    dy_peer[s] = reinterpret_cast<float*>(reinterpret_cast<char*>(peer_base[s]) + slots_offset) + (size_t)rank * (size_t)n_rows * (size_t)d;
+  }
+  if ((rc = bwd2_launch(pl, x, y, rinv_x, rinv_y, n_rows, n_cols, d, diag_offset, scale, scale_dev, row_m, row_w, col_m, col_w,
+                        diag_w, ws, dy_peer, world, st)))
+    return rc;
+  float* ds_part = reinterpret_cast<float*>(ws + pl.off_part);
+  if ((rc = launch_finish(reinterpret_cast<float*>(ws + pl.off_dxh), pl.n_seg, n_rows * d, x, x_orig, in_dtype, rinv_x, grad_scale,
+                          n_rows, d, dx, out_dtype, d_scale_sum ? ds_part : nullptr, st)))
+    return rc;
+  if (d_scale_sum) {
+    aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)ceil_div(n_rows, 8), 1.f, d_scale_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int clipnce_finish_slots(const float* slots, int n_slots, const void* x, int dtype, const void* x_orig, int in_dtype,
+                         const float* rinv, const float* grad_scale, int64_t n, int64_t d, void* dx, int out_dtype,
+                         void* stream) {
+  if (!slots || !x || !x_orig || !rinv || !dx || n < 1 || d < 1 || n_slots < 1) return fail(CLIPNCE_EINVAL, "finish_slots: bad argument");
+  if (dtype != CLIPNCE_BF16 || d % 4 != 0 || sizeof(float) * 8 * (size_t)d > 48 * 1024)
+    return fail(CLIPNCE_EUNSUPPORTED, "finish_slots: bf16 compute rows, d %% 4 == 0, d <= 1536");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "finish_slots: bad dtype");
+  return launch_finish(slots, n_slots, n * d, x, x_orig, in_dtype, rinv, grad_scale, n, d, dx, out_dtype, nullptr, as_stream(stream));
 }
 
 }  // extern "C"

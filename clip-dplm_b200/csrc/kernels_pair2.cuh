@@ -1,35 +1,46 @@
 // Two-sided backward: ONE sweep over the logits tiles emits both dA_hat and dB_hat (8 N^2 d executed per step instead of
 // the 10 N^2 d of two pair::bwd_kernel launches) -- loss.backward() of current/rna_clip_codes.ipynb:2074,
-// run1/full.py:134, old/clip_opt.py:167 for the single-GPU symmetric loss.
+// run1/full.py:134, old/clip_opt.py:167.
 //
 // Why it is not "one CTA pair keeps two accumulators".  A pair's TMEM holds 128 K floats.  With d = 512 the stationary
 // gradient of 128 resident rows already takes half of it and two logits buffers the other half; a second, per-column-block
 // accumulator [256 x 512] does not fit, and flushing one per step would cost 1/(1.5 R) B per FLOP of fp32 reduction
 // traffic (R = 128 rows: ~7 TB/s).  So the second gradient is formed by OTHER SMs, and what travels between them is the
-// bf16 gradient tile G the producer has in shared memory anyway:
+// bf16 gradient tile the producer has in shared memory anyway:
 //
 //   producer pairs (P of the 74)   exactly pair::bwd_kernel's sweep -- 128 resident rows of X, S = X Y^T per 256-column
-//                                  step, G = exp(S - s)(u_i + v_j) - diag, dXhat += G Yhat stationary in TMEM -- plus a TMA
-//                                  store of every G tile [128 x 256] bf16 into a ring in global memory (L2-resident)
-//   consumer pairs (Q = 74 - P)    dYhat[J_t, d half] += sum over the wave's producers G_p^T Xhat_p : a plain GEMM,
-//                                  M = 256 columns j, N = 256 (d half), K = all rows of the wave (P x 128), both operands
-//                                  MN-major straight from TMA boxes; flushed once per task (K = 6656 rows: the fp32
-//                                  read-modify-write traffic is 2 % of what a per-pair flush would cost)
+//                                  step, G'' = (exp(S - s)(u_i + v_j) - diag) / (|x_i| |y_j|), dX += G'' Y stationary in
+//                                  TMEM -- plus a TMA store of every G'' tile [128 x 256] bf16 into a ring in global
+//                                  memory (L2-resident)
+//   consumer pairs (Q = 74 - P)    dY[J_t, d half] += sum over the round's producers G''_p^T X_p : a plain GEMM,
+//                                  M = 256 columns j, N = 256 (d half), K = the rows of the round (<= P x 128), both
+//                                  operands MN-major straight from TMA boxes; flushed once per task
 //
-// All producers sweep the column steps in lock step (they run the same code on the same data volume), so at any time
-// the tiles in flight belong to a window of ~Q/2 + 2 steps: the ring holds D = 16 steps x P tiles x 64 KiB.
-// Producers : consumers = 2 : 1 in work (S + dX against dY), P is chosen so that the waves of row blocks are full.
+// ONE tile serves both sides because it carries BOTH 1/norm factors: dXhat_i = (s |x_i|) sum_j G''_ij y_j and
+// dYhat_j = (s |y_j|) sum_i G''_ij x_i contract it against the RAW rows; the per-row factor is applied when an accumulator
+// is drained.  The logits come from the raw rows scaled in fp32, exactly as in the forward.
 //
-// Both gradient GEMMs contract G against the NORMALISED rows rounded to bf16 (Xhat, Yhat: one extra elementwise pass)
-// because one tile has to serve both sides: the per-row / per-column 1/norm factors can no longer be folded into G.  The
-// logits themselves still come from the raw rows scaled in fp32, exactly as in the forward.
+// Work items.  A producer's unit of work is (row block, column segment): the column sweep is cut into n_seg segments of
+// seg_steps steps, items are numbered segment-major and dealt out in rounds of P (item r P + p goes to producer p in
+// round r), so P need not divide the number of row blocks and the rounds stay full; an item's gradient goes to slab `seg`
+// of dX (summed by aux::finish_rows).  All producers of a round advance in lock step, so the tiles in flight belong to a
+// window of ~Q/2 + 2 steps: the ring holds `depth` steps x P tiles x 64 KiB.  A round may straddle segment boundaries:
+// its producers then split into runs of equal segment ("subs"), and every (sub, step, d half) is one consumer task.
+// Consumer tasks are assigned by (column step, d half) only, so every contribution to one block of dY is accumulated by
+// the same threads in program order: no atomics, bit-reproducible.
 //
-// Flags (global memory, zeroed per launch): ready[g] counts the G boxes stored for global step g = wave * n_steps + t
-// (2 per producer pair: one per CTA, after its four boxes), done[g] the consumer tasks that finished reading them (one per d half).  A
-// producer stores step g only after done[g - D] is complete.  TMA stores are published by
-// cp.async.bulk.wait_group 0 -> fence.proxy.async -> red.release.gpu; consumers ld.acquire.gpu -> fence.proxy.async ->
-// TMA loads.  Liveness: the smallest incomplete step's consumers never wait on anything but producers, and producers only
-// wait on steps D behind them.  All 74 pairs must be co-resident (persistent grid of 148 CTAs, checked by the host).
+// Row-sharded global batch: X = the rank's A rows, Y = all ranks' B rows, segment s = the columns
+// owned by rank s.  The LAST contribution to a block of segment s is not written locally but stored straight into rank
+// s's slot for this rank in NVLink peer memory: the kernel is the contraction AND the reduce-scatter of the partial dB
+// (what the reference's all_gather formulation leaves to autograd + DDP, old/clip_opt.py:102-112); the owner sums the
+// world slots in fixed order (aux::finish_rows).
+//
+// Flags (global memory, zeroed per launch): ready[g] counts the CTAs whose four G boxes of global step
+// g = round * seg_steps + tau have landed (2 per producer pair), done[g] the consumer tasks that finished reading them.  A
+// producer stores step g only after done[g - depth] is complete.  TMA stores are published by
+// cp.async.bulk.wait_group -> fence.proxy.async -> red.release.gpu; consumers ld.acquire.gpu -> fence.proxy.async -> TMA
+// loads.  Liveness: the smallest incomplete step's consumers never wait on anything but producers, and producers only
+// wait on steps `depth` behind them.  All pairs must be co-resident (persistent grid, checked by the host).
 #pragma once
 #include "kernels_pair.cuh"
 
@@ -46,10 +57,11 @@ constexpr int EPI_WARPS = 8;
 constexpr int ROWS = 64;                     // resident rows per producer CTA (128 per pair)
 constexpr int X_CHUNK = ROWS * 128;          // [64 rows][64 k] bf16
 constexpr int G_BYTES = 4 * 8192;            // [64 i][256 j] bf16 = four K-major boxes
-constexpr int SMALL = 8192;                  // barriers (512) | tmem ptr | column vectors 2 x 2 x 256 f32 at +1024
-constexpr int C_STAGE = 32768;               // consumer stage: A = 2 boxes G^T [64 i][64 j], B = 2 boxes Xhat [64 i][64 d]
+constexpr int SMALL = 8192;                  // barriers (512) | tmem ptr | column vectors 2 x 3 x 256 f32 at +1024
+constexpr int C_STAGE = 32768;               // consumer stage: A = 2 boxes G^T [64 i][64 j], B = 2 boxes X [64 i][64 d]
 constexpr int MAXS = 6;
 constexpr int RING_DEPTH = 16;               // steps of G tiles the ring holds
+constexpr int MAX_WORLD = 16;
 
 constexpr int B_FULL_A = 0, B_EMPTY_A = MAXS, B_FULL_B = 2 * MAXS, B_EMPTY_B = 3 * MAXS, B_XFULL = 4 * MAXS,
               B_XEMPTY = B_XFULL + 1, B_SFULL = B_XEMPTY + 1, B_SEMPTY = B_SFULL + 2, B_GFULL = B_SEMPTY + 2,
@@ -58,10 +70,12 @@ constexpr int B_FULL_A = 0, B_EMPTY_A = MAXS, B_FULL_B = 2 * MAXS, B_EMPTY_B = 3
 static_assert(B_COUNT * 8 <= 512, "barrier block");
 
 struct Params {
-  int n, d;             // n_rows == n_cols == n, n % 256 == 0, d % 128 == 0, d <= 512
-  int nkc, nq2, n_steps, n_half;
-  int P, Q, n_rb, n_waves, depth;
+  int n_rows, n_cols, d;      // n_rows % 128 == 0, n_cols % (256 n_seg) == 0, d % 128 == 0, d <= 512
+  int nkc, nq2, n_half;
+  int n_rb, n_seg, seg_steps, n_items, n_rounds;
+  int P, Q, depth;
   int stages_a, stages_b, stages_c;
+  long long diag_offset;      // column of row i's positive = i + diag_offset
   float scale, diag_w;
   const float* scale_dev;
   const float* rinv_x;
@@ -70,10 +84,14 @@ struct Params {
   const float* row_w;
   const float* col_m;
   const float* col_w;
-  float* dx;            // [n, d] f32: s * sum_j G_ij yhat_j
-  float* dy;            // [n, d] f32: s * sum_i G_ij xhat_i
-  uint32_t* ready;      // [n_waves * n_steps]
-  uint32_t* done;       // [n_waves * n_steps]
+  float* dx;                  // [n_seg][n_rows, d] f32: per-segment partials of s sum_j G_ij yhat_j
+  float* dy;                  // [n_cols, d] f32: s sum_i G_ij xhat_i over the LOCAL rows (partial / result)
+  // row-sharded step: the last contribution to segment s is stored at dy_peer[s] (this rank's slot in rank s's peer
+  // memory, [seg_steps * 256, d] f32) instead of dy; world == 0: everything stays in dy
+  float* dy_peer[MAX_WORLD];
+  int world;
+  uint32_t* ready;            // [n_rounds * seg_steps]
+  uint32_t* done;             // [n_rounds * seg_steps]
 };
 
 __host__ __device__ constexpr int producer_smem(int nkc, int stages) { return nkc * X_CHUNK + G_BYTES + stages * STAGE_BYTES + SMALL; }
@@ -84,12 +102,34 @@ __device__ __forceinline__ void publish(uint32_t* flag) {   // TMA stores of thi
   ptx::red_release_gpu_add(flag, 1u);
 }
 
+// The runs of equal segment ("subs") among the items of round r.
+struct Sub {
+  int seg, p_lo, p_hi, rb_lo;   // producers [p_lo, p_hi) of the round work on segment seg, row blocks rb_lo + (p - p_lo)
+  bool first, last;             // the run holds the segment's first / last row block
+};
+__device__ __forceinline__ int round_items(const Params& p, int r) { return min(p.P, p.n_items - r * p.P); }
+__device__ __forceinline__ int round_subs(const Params& p, int r) {
+  const int lo = r * p.P, hi = lo + round_items(p, r);
+  return (hi - 1) / p.n_rb - lo / p.n_rb + 1;
+}
+__device__ __forceinline__ Sub round_sub(const Params& p, int r, int k) {
+  const int lo = r * p.P, hi = lo + round_items(p, r);
+  Sub s;
+  s.seg = lo / p.n_rb + k;
+  const int a = max(lo, s.seg * p.n_rb), b = min(hi, (s.seg + 1) * p.n_rb);
+  s.p_lo = a - lo;
+  s.p_hi = b - lo;
+  s.rb_lo = a - s.seg * p.n_rb;
+  s.first = a == s.seg * p.n_rb;
+  s.last = b == (s.seg + 1) * p.n_rb;
+  return s;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k, 64 rows}      resident rows (logits A operand)
-            const __grid_constant__ CUtensorMap tmap_y,    // Y raw   box {64 k, 128 rows}     logits B operand, K-major
-            const __grid_constant__ CUtensorMap tmap_yh,   // Yhat    box {64 d, 64 rows}      dX gradient B operand, MN-major
-            const __grid_constant__ CUtensorMap tmap_xh,   // Xhat    box {64 d, 64 rows}      dY gradient B operand, MN-major
-            const __grid_constant__ CUtensorMap tmap_g,    // G ring  [depth * P * 128, 256]   box {64 j, 64 i}
+bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 rows}     resident rows (K-major) / dY operand (MN-major)
+            const __grid_constant__ CUtensorMap tmap_y,    // Y  box {64 k, 128 rows}  logits B operand, K-major
+            const __grid_constant__ CUtensorMap tmap_yg,   // Y  box {64 d, 64 rows}   dX gradient B operand, MN-major
+            const __grid_constant__ CUtensorMap tmap_g,    // G ring [depth * P * 128, 256] bf16, box {64 j, 64 i}
             const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ptx::smem_u32(smem);
@@ -106,7 +146,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
   const uint32_t bars = base + body;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + body + 512);
-  float* const colv = reinterpret_cast<float*>(smem + body + 1024);   // [2][2][256]
+  float* const colv = reinterpret_cast<float*>(smem + body + 1024);   // [2][3][256]
 
   const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;
   const float k2 = sc * LOG2E;
@@ -114,8 +154,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_y);
-    ptx::prefetch_tmap(&tmap_yh);
-    ptx::prefetch_tmap(&tmap_xh);
+    ptx::prefetch_tmap(&tmap_yg);
     ptx::prefetch_tmap(&tmap_g);
   }
   if (warp == 1 && lane == 0) {
@@ -155,6 +194,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
 
   if (is_producer) {
     // =========================================================================================== PRODUCER PAIR
+    // item of round r: i = r P + pair_id  ->  segment i / n_rb, row block i % n_rb, column steps seg * seg_steps + tau
     const uint32_t x_smem = base;
     const uint32_t g_smem = x_smem + p.nkc * X_CHUNK;
     const uint32_t ring_a = g_smem + G_BYTES;
@@ -162,19 +202,20 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
     constexpr int S_COL0 = TMEM_COLS - 256;   // two logits buffers of 128 columns behind the accumulators
 
     if (warp == 0) {
-      // ------------------------------------------------------------- TMA: resident X per wave, then Y rows (K-major)
+      // ------------------------------------------------------------- TMA: resident X per item, then Y rows (K-major)
       if (ptx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          const int rb = w * p.P + pair_id;
-          if (rb >= p.n_rb) break;
-          const int i0 = rb * (2 * ROWS) + (int)rank * ROWS;
-          ptx::mbar_wait(bar(B_XEMPTY), (w & 1) ^ 1u);   // the previous wave's logits MMAs have read X
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int item = r * p.P + pair_id;
+          if (item >= p.n_items) break;
+          const int i0 = (item % p.n_rb) * (2 * ROWS) + (int)rank * ROWS;
+          const int t0 = (item / p.n_rb) * p.seg_steps;
+          ptx::mbar_wait(bar(B_XEMPTY), (r & 1) ^ 1u);   // the previous item's logits MMAs have read X
           if (leader) ptx::mbar_arrive_expect_tx(bar(B_XFULL), 2 * p.nkc * X_CHUNK);
           for (int kc = 0; kc < p.nkc; ++kc)
             ptx::tma_load_2d_pair(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0);
-          for (int t = 0; t < p.n_steps; ++t) {
+          for (int t = t0; t < t0 + p.seg_steps; ++t) {
             for (int g = 0; g < p.nkc; ++g) {
               ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
               if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
@@ -187,13 +228,15 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
       }
       __syncwarp();
     } else if (warp == 2) {
-      // ------------------------------------------------------------- TMA: Yhat[j, d slice] boxes (MN-major)
+      // ------------------------------------------------------------- TMA: Y[j, d slice] boxes (MN-major)
       if (ptx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          if (w * p.P + pair_id >= p.n_rb) break;
-          for (int t = 0; t < p.n_steps; ++t) {
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int item = r * p.P + pair_id;
+          if (item >= p.n_items) break;
+          const int t0 = (item / p.n_rb) * p.seg_steps;
+          for (int t = t0; t < t0 + p.seg_steps; ++t) {
             for (int kc = 0; kc < 4; ++kc) {
               for (int q = 0; q < p.nq2; ++q) {
                 const int wq = min(256, p.d - 256 * q);
@@ -202,7 +245,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
                 ptx::mbar_wait(bar(B_EMPTY_B + stage), phase ^ 1u);
                 if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), 2 * ngr * 8192);
                 for (int gi = 0; gi < ngr; ++gi)
-                  ptx::tma_load_2d_pair(ring_b + stage * STAGE_BYTES + gi * 8192, &tmap_yh, bar(B_FULL_B + stage),
+                  ptx::tma_load_2d_pair(ring_b + stage * STAGE_BYTES + gi * 8192, &tmap_yg, bar(B_FULL_B + stage),
                                         256 * q + half * (int)rank + 64 * gi, t * STEP_J + 64 * kc);
                 if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
               }
@@ -218,10 +261,10 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
         const uint32_t x_lo0 = desc_lo(x_smem, 1), a_lo0 = desc_lo(ring_a, 1);
         int stage = 0;
         uint32_t phase = 0, ready = 0, gs = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          if (w * p.P + pair_id >= p.n_rb) break;
-          ptx::mbar_wait(bar(B_XFULL), w & 1);
-          for (int t = 0; t < p.n_steps; ++t, ++gs) {
+        for (int r = 0; r < p.n_rounds; ++r) {
+          if (r * p.P + pair_id >= p.n_items) break;
+          ptx::mbar_wait(bar(B_XFULL), r & 1);
+          for (int t = 0; t < p.seg_steps; ++t, ++gs) {
             const int sb = gs & 1;
             ptx::mbar_wait(bar(B_SEMPTY + sb), ((gs >> 1) & 1) ^ 1u);
             const uint32_t d_tmem = tmem_base + S_COL0 + sb * 128;
@@ -240,7 +283,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
               phase = np;
             }
           }
-          ptx::mma_commit_pair(bar(B_XEMPTY));   // every logits MMA of this wave has read X
+          ptx::mma_commit_pair(bar(B_XEMPTY));   // every logits MMA of this item has read X
         }
       }
       __syncwarp();
@@ -250,11 +293,11 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
         const uint32_t g_lo0 = desc_lo(g_smem, 1), b_lo0 = desc_lo(ring_b, 8192 >> 4);
         int stage = 0;
         uint32_t phase = 0, ready = 0, gs = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          if (w * p.P + pair_id >= p.n_rb) break;
-          ptx::mbar_wait(bar(B_ACCEMPTY), (w & 1) ^ 1u);   // the previous wave's accumulators have been drained
+        for (int r = 0; r < p.n_rounds; ++r) {
+          if (r * p.P + pair_id >= p.n_items) break;
+          ptx::mbar_wait(bar(B_ACCEMPTY), (r & 1) ^ 1u);   // the previous item's accumulators have been drained
           ptx::tc_fence_after();
-          for (int t = 0; t < p.n_steps; ++t, ++gs) {
+          for (int t = 0; t < p.seg_steps; ++t, ++gs) {
             for (int kc = 0; kc < 4; ++kc) {
               ptx::mbar_wait(bar(B_GFULL + kc), gs & 1);
               for (int q = 0; q < p.nq2; ++q) {
@@ -287,10 +330,11 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
         uint32_t gs = 0;
         bool pending = false;
         uint32_t g_prev = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          if (w * p.P + pair_id >= p.n_rb) break;
-          for (int t = 0; t < p.n_steps; ++t, ++gs) {
-            const uint32_t g = (uint32_t)w * (uint32_t)p.n_steps + (uint32_t)t;
+        for (int r = 0; r < p.n_rounds; ++r) {
+          if (r * p.P + pair_id >= p.n_items) break;
+          const bool more_rounds = (r + 1) * p.P + pair_id < p.n_items;
+          for (int t = 0; t < p.seg_steps; ++t, ++gs) {
+            const uint32_t g = (uint32_t)r * (uint32_t)p.seg_steps + (uint32_t)t;
             const int row0 = ((int)(g % (uint32_t)p.depth) * p.P + pair_id) * 128 + (int)rank * ROWS;
             // latency-critical part: the epilogue of the NEXT step waits for these boxes to be released
             for (int kc = 0; kc < 4; ++kc) {
@@ -308,8 +352,10 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
             }
             pending = true;
             g_prev = g;
-            if (g + 1 >= (uint32_t)p.depth && (t + 1 < p.n_steps || (w + 1) * p.P + pair_id < p.n_rb))
-              ptx::spin_until_ge(p.done + (g + 1 - p.depth), (uint32_t)p.n_half);
+            if (g + 1 >= (uint32_t)p.depth && (t + 1 < p.seg_steps || more_rounds)) {
+              const uint32_t go = g + 1 - (uint32_t)p.depth;
+              ptx::spin_until_ge(p.done + go, (uint32_t)(round_subs(p, (int)(go / (uint32_t)p.seg_steps)) * p.n_half));
+            }
           }
         }
         if (pending) {
@@ -319,7 +365,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
       }
       __syncwarp();
     } else {
-      // ------------------------------------------------------------- epilogue: S tile -> bf16 G tile (MMA operand + ring)
+      // ------------------------------------------------------------- epilogue: S tile -> bf16 G'' tile (MMA operand + ring)
       const int e = warp - 4;
       const int q = warp & 3;
       const int h = e >> 2;
@@ -336,25 +382,33 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
       const uint32_t accempty_leader = ptx::mapa(bar(B_ACCEMPTY), 0);
       uint32_t gs = 0;
 
-      for (int w = 0; w < p.n_waves; ++w) {
-        const int rb = w * p.P + pair_id;
-        if (rb >= p.n_rb) break;
-        const int i_glob = rb * (2 * ROWS) + (int)rank * ROWS + i_local;
+      for (int r = 0; r < p.n_rounds; ++r) {
+        const int item = r * p.P + pair_id;
+        if (item >= p.n_items) break;
+        const int seg = item / p.n_rb;
+        const int t0 = seg * p.seg_steps;
+        const int i_glob = (item % p.n_rb) * (2 * ROWS) + (int)rank * ROWS + i_local;
         const float rx = p.rinv_x[i_glob];
         const float u = p.row_w[i_glob] * pair::ex2((sc - p.row_m[i_glob]) * LOG2E);
-        float cw_n = p.col_w[te], cm_n = p.col_m[te], ry_n = p.rinv_y[te];
+        const long long dcol = (long long)i_glob + p.diag_offset;   // column of this row's positive
+        float cw_n, cm_n, ry_n;
+        {
+          const long long jn = (long long)t0 * STEP_J + te;
+          cw_n = p.col_w[jn]; cm_n = p.col_m[jn]; ry_n = p.rinv_y[jn];
+        }
 
-        for (int t = 0; t < p.n_steps; ++t, ++gs) {
+        for (int t = t0; t < t0 + p.seg_steps; ++t, ++gs) {
           const int sb = gs & 1;
-          float* const cv = colv + (gs & 1) * 512;
-          cv[te] = ry_n * k2;                                          // S_ij log2(e) = acc * rinv_x[i] * cj
-          cv[256 + te] = cw_n * pair::ex2((sc - cm_n) * LOG2E);       // v_j
-          if (t + 1 < p.n_steps) {
-            const int jn = (t + 1) * STEP_J + te;
+          float* const cv = colv + (gs & 1) * 768;
+          cv[te] = ry_n * k2;                                                   // S_ij log2(e) = acc * rinv_x[i] * cj
+          cv[256 + te] = cw_n * pair::ex2((sc - cm_n) * LOG2E) * ry_n;          // v_j / |y_j|
+          cv[512 + te] = ry_n;
+          if (t + 1 < t0 + p.seg_steps) {
+            const long long jn = (long long)(t + 1) * STEP_J + te;
             cw_n = p.col_w[jn]; cm_n = p.col_m[jn]; ry_n = p.rinv_y[jn];
           }
           pair::named_bar_sync(1, EPI_WARPS * 32);
-          const int dl = i_glob - (t * STEP_J + jl0);   // step-local index of the positive, if in [0, 64)
+          const long long dl = dcol - ((long long)t * STEP_J + jl0);   // step-local index of the positive, if in [0, 64)
           const bool has_diag = dl >= 0 && dl < 64;
 
           ptx::mbar_wait(bar(B_SFULL + sb), (gs >> 1) & 1);
@@ -362,8 +416,8 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
           uint32_t pk[32];
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + sb * 128 + 64 * h + 32 * c, r);
+            uint32_t rr[32];
+            ptx::tmem_ld_32x32b_x32(t_lane + S_COL0 + sb * 128 + 64 * h + 32 * c, rr);
             ptx::tmem_ld_wait();
             if (c == 1) {
               ptx::tc_fence_before();
@@ -374,19 +428,22 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
 #pragma unroll
             for (int x4 = 0; x4 < 8; ++x4) {
               const float4 cj4 = *reinterpret_cast<const float4*>(cjp + 4 * x4);
-              const float4 vj4 = *reinterpret_cast<const float4*>(cjp + 256 + 4 * x4);
+              const float4 vr4 = *reinterpret_cast<const float4*>(cjp + 256 + 4 * x4);
+              const float4 ry4 = *reinterpret_cast<const float4*>(cjp + 512 + 4 * x4);
               const float cjv[4] = {cj4.x, cj4.y, cj4.z, cj4.w};
-              const float vjv[4] = {vj4.x, vj4.y, vj4.z, vj4.w};
+              const float vrv[4] = {vr4.x, vr4.y, vr4.z, vr4.w};
+              const float ryv[4] = {ry4.x, ry4.y, ry4.z, ry4.w};
               float g[4];
 #pragma unroll
               for (int xx = 0; xx < 4; ++xx) {
-                const float y = __uint_as_float(r[4 * x4 + xx]) * rx;
-                g[xx] = pair::ex2(fmaf(y, cjv[xx], -k2)) * (u + vjv[xx]);   // exp(S_ij - s)(u_i + v_j)
+                const float y = __uint_as_float(rr[4 * x4 + xx]) * rx;
+                const float ev = pair::ex2(fmaf(y, cjv[xx], -k2)) * rx;     // exp(S_ij - s) / |x_i|
+                g[xx] = ev * fmaf(u, ryv[xx], vrv[xx]);                       // (u_i + v_j) / |y_j|
               }
               if (has_diag) {
 #pragma unroll
                 for (int xx = 0; xx < 4; ++xx)
-                  if (dl == 32 * c + 4 * x4 + xx) g[xx] -= p.diag_w;
+                  if (dl == 32 * c + 4 * x4 + xx) g[xx] -= p.diag_w * rx * ryv[xx];
               }
               const __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]);
               const __nv_bfloat162 p1 = __floats2bfloat162_rn(g[2], g[3]);
@@ -408,23 +465,25 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
           }
         }
 
-        // the wave's accumulators: slot q2 holds dXhat[i, 256 q2 + ...] in the 2x2 layout
-        ptx::mbar_wait(bar(B_ACCFULL), w & 1);
+        // the item's accumulators: slot q2 holds sum_j G''_ij y_j [i, 256 q2 + ...] in the 2x2 layout; dXhat = s |x_i| (...)
+        ptx::mbar_wait(bar(B_ACCFULL), r & 1);
         ptx::tc_fence_after();
+        const float osc = sc / rx;
+        float* const slab = p.dx + (long long)seg * p.n_rows * p.d;
         for (int q2 = 0; q2 < p.nq2; ++q2) {
           const int halfw = min(256, p.d - 256 * q2) >> 1;
           if (64 * h < halfw) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              ptx::tmem_ld_32x32b_x32(t_lane + 128 * q2 + 64 * h + 32 * c, r);
+              uint32_t rr[32];
+              ptx::tmem_ld_32x32b_x32(t_lane + 128 * q2 + 64 * h + 32 * c, rr);
               ptx::tmem_ld_wait();
-              float* const dst = p.dx + (long long)i_glob * p.d + 256 * q2 + halfw * jh + 64 * h + 32 * c;
+              float* const dst = slab + (long long)i_glob * p.d + 256 * q2 + halfw * jh + 64 * h + 32 * c;
 #pragma unroll
               for (int x4 = 0; x4 < 8; ++x4)
                 *reinterpret_cast<float4*>(dst + 4 * x4) =
-                    make_float4(__uint_as_float(r[4 * x4]) * sc, __uint_as_float(r[4 * x4 + 1]) * sc,
-                                __uint_as_float(r[4 * x4 + 2]) * sc, __uint_as_float(r[4 * x4 + 3]) * sc);
+                    make_float4(__uint_as_float(rr[4 * x4]) * osc, __uint_as_float(rr[4 * x4 + 1]) * osc,
+                                __uint_as_float(rr[4 * x4 + 2]) * osc, __uint_as_float(rr[4 * x4 + 3]) * osc);
             }
           }
         }
@@ -435,38 +494,48 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
     }
   } else {
     // =========================================================================================== CONSUMER PAIR
+    // task = (round, sub, tau, d half); it belongs to the consumer with index (t n_half + hh) % Q, t = the column step
     const int cidx = pair_id - p.P;
     const uint32_t ring_c = base;
 
     if (warp == 0) {
-      // ------------------------------------------------------------- TMA: G^T boxes from the ring + Xhat boxes
+      // ------------------------------------------------------------- TMA: G^T boxes from the ring + X boxes
       if (ptx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          const int pw = min(p.P, p.n_rb - w * p.P);
-          for (int t = 0; t < p.n_steps; ++t) {
-            for (int hh = 0; hh < p.n_half; ++hh) {
-              if ((t * p.n_half + hh) % p.Q != cidx) continue;
-              const uint32_t g = (uint32_t)w * (uint32_t)p.n_steps + (uint32_t)t;
-              ptx::spin_until_ge(p.ready + g, 2u * (uint32_t)pw);
-              ptx::fence_proxy_async_all();
-              const int slot = (int)(g % (uint32_t)p.depth);
-              const int wq = min(256, p.d - 256 * hh);
-              const int ngr = wq >> 7;                   // 64-wide d groups this CTA supplies (N split over the pair)
-              for (int pp = 0; pp < pw; ++pp) {
-                for (int kb = 0; kb < 2; ++kb) {
-                  ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
-                  if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * (2 + ngr) * 8192);
-                  const uint32_t st = ring_c + stage * C_STAGE;
-                  const int grow = (slot * p.P + pp) * 128 + 64 * kb;
-                  const int xrow = (w * p.P + pp) * 128 + 64 * kb;
-                  for (int gi = 0; gi < 2; ++gi)
-                    ptx::tma_load_2d_pair(st + gi * 8192, &tmap_g, bar(B_FULL_A + stage), 128 * (int)rank + 64 * gi, grow);
-                  for (int gi = 0; gi < ngr; ++gi)
-                    ptx::tma_load_2d_pair(st + 16384 + gi * 8192, &tmap_xh, bar(B_FULL_A + stage),
-                                          256 * hh + (wq >> 1) * (int)rank + 64 * gi, xrow);
-                  if (++stage == p.stages_c) { stage = 0; phase ^= 1u; }
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int pw = round_items(p, r);
+          const int nsub = round_subs(p, r);
+          for (int tau = 0; tau < p.seg_steps; ++tau) {
+            const uint32_t g = (uint32_t)r * (uint32_t)p.seg_steps + (uint32_t)tau;
+            const int slot = (int)(g % (uint32_t)p.depth);
+            bool step_ready = false;
+            for (int k = 0; k < nsub; ++k) {
+              const Sub sub = round_sub(p, r, k);
+              const int t = sub.seg * p.seg_steps + tau;
+              for (int hh = 0; hh < p.n_half; ++hh) {
+                if ((t * p.n_half + hh) % p.Q != cidx) continue;
+                if (!step_ready) {
+                  ptx::spin_until_ge(p.ready + g, 2u * (uint32_t)pw);
+                  ptx::fence_proxy_async_all();
+                  step_ready = true;
+                }
+                const int wq = min(256, p.d - 256 * hh);
+                const int ngr = wq >> 7;                   // 64-wide d groups this CTA supplies (N split over the pair)
+                for (int pp = sub.p_lo; pp < sub.p_hi; ++pp) {
+                  for (int kb = 0; kb < 2; ++kb) {
+                    ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
+                    if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * (2 + ngr) * 8192);
+                    const uint32_t st = ring_c + stage * C_STAGE;
+                    const int grow = (slot * p.P + pp) * 128 + 64 * kb;
+                    const int xrow = (sub.rb_lo + pp - sub.p_lo) * 128 + 64 * kb;
+                    for (int gi = 0; gi < 2; ++gi)
+                      ptx::tma_load_2d_pair(st + gi * 8192, &tmap_g, bar(B_FULL_A + stage), 128 * (int)rank + 64 * gi, grow);
+                    for (int gi = 0; gi < ngr; ++gi)
+                      ptx::tma_load_2d_pair(st + 16384 + gi * 8192, &tmap_x, bar(B_FULL_A + stage),
+                                            256 * hh + (wq >> 1) * (int)rank + 64 * gi, xrow);
+                    if (++stage == p.stages_c) { stage = 0; phase ^= 1u; }
+                  }
                 }
               }
             }
@@ -480,83 +549,100 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X raw   box {64 k,
         const uint32_t a_lo0 = desc_lo(ring_c, 8192 >> 4), b_lo0 = desc_lo(ring_c + 16384, 8192 >> 4);
         int stage = 0;
         uint32_t phase = 0, ready = 0, nt = 0;
-        for (int w = 0; w < p.n_waves; ++w) {
-          const int pw = min(p.P, p.n_rb - w * p.P);
-          for (int t = 0; t < p.n_steps; ++t) {
-            for (int hh = 0; hh < p.n_half; ++hh) {
-              if ((t * p.n_half + hh) % p.Q != cidx) continue;
-              const int buf = nt & 1;
-              ptx::mbar_wait(bar(B_ACCEMPTY + buf), ((nt >> 1) & 1) ^ 1u);
-              ptx::tc_fence_after();
-              const int wq = min(256, p.d - 256 * hh);
-              const uint32_t idesc = ptx::idesc_bf16_f32_major(256, wq, 1, 1);
-              const uint32_t d_tmem = tmem_base + buf * 256;
-              for (int k = 0; k < 2 * pw; ++k) {
-                if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
+        for (int r = 0; r < p.n_rounds; ++r) {
+          const int nsub = round_subs(p, r);
+          for (int tau = 0; tau < p.seg_steps; ++tau) {
+            for (int k = 0; k < nsub; ++k) {
+              const Sub sub = round_sub(p, r, k);
+              const int t = sub.seg * p.seg_steps + tau;
+              for (int hh = 0; hh < p.n_half; ++hh) {
+                if ((t * p.n_half + hh) % p.Q != cidx) continue;
+                const int buf = nt & 1;
+                ptx::mbar_wait(bar(B_ACCEMPTY + buf), ((nt >> 1) & 1) ^ 1u);
                 ptx::tc_fence_after();
-                int ns = stage + 1;
-                uint32_t np = phase;
-                if (ns == p.stages_c) { ns = 0; np ^= 1u; }
-                ready = ptx::mma_box_pair(d_tmem, mk(desc_hi_mn, a_lo0 + stage * (C_STAGE >> 4)),
-                                          mk(desc_hi_mn, b_lo0 + stage * (C_STAGE >> 4)), 2048 >> 4, 2048 >> 4, idesc,
-                                          k != 0, bar(B_FULL_A + ns), np);
-                ptx::mma_commit_pair(bar(B_EMPTY_A + stage));
-                stage = ns;
-                phase = np;
+                const int wq = min(256, p.d - 256 * hh);
+                const uint32_t idesc = ptx::idesc_bf16_f32_major(256, wq, 1, 1);
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                const int nk = 2 * (sub.p_hi - sub.p_lo);
+                for (int kk = 0; kk < nk; ++kk) {
+                  if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
+                  ptx::tc_fence_after();
+                  int ns = stage + 1;
+                  uint32_t np = phase;
+                  if (ns == p.stages_c) { ns = 0; np ^= 1u; }
+                  ready = ptx::mma_box_pair(d_tmem, mk(desc_hi_mn, a_lo0 + stage * (C_STAGE >> 4)),
+                                            mk(desc_hi_mn, b_lo0 + stage * (C_STAGE >> 4)), 2048 >> 4, 2048 >> 4, idesc,
+                                            kk != 0, bar(B_FULL_A + ns), np);
+                  ptx::mma_commit_pair(bar(B_EMPTY_A + stage));
+                  stage = ns;
+                  phase = np;
+                }
+                ptx::mma_commit_pair(bar(B_ACCFULL + buf));
+                ++nt;
               }
-              ptx::mma_commit_pair(bar(B_ACCFULL + buf));
-              ++nt;
             }
           }
         }
       }
       __syncwarp();
     } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
-      // ------------------------------------------------------------- epilogue: accumulator -> dYhat (read-modify-write)
+      // ------------------------------------------------------------- epilogue: accumulator -> dY (store / read-modify-write / peer)
       const int q = warp & 3;
       const int hcol = (warp - 4) >> 2;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       const uint32_t accempty_leader = ptx::mapa(bar(B_ACCEMPTY), 0);
       uint32_t nt = 0;
-      for (int w = 0; w < p.n_waves; ++w) {
-        for (int t = 0; t < p.n_steps; ++t) {
-          for (int hh = 0; hh < p.n_half; ++hh) {
-            if ((t * p.n_half + hh) % p.Q != cidx) continue;
-            const int buf = nt & 1;
-            ptx::mbar_wait(bar(B_ACCFULL + buf), (nt >> 1) & 1);
-            ptx::tc_fence_after();
-            if (leader && warp == 4 && lane == 0)   // every MMA of the task is complete: its ring tiles have been read
-              ptx::red_release_gpu_add(p.done + ((uint32_t)w * (uint32_t)p.n_steps + (uint32_t)t), 1u);
-            const int wq = min(256, p.d - 256 * hh);
-            const int wh = wq >> 1;                  // columns per epilogue-warp half
-            const long long j = (long long)t * STEP_J + (int)rank * 128 + 32 * q + lane;
-            float* const drow = p.dy + j * p.d + 256 * hh + hcol * wh;
-            for (int c = 0; c < (wh >> 5); ++c) {
-              uint32_t r[32];
-              ptx::tmem_ld_32x32b_x32(t_lane + buf * 256 + hcol * wh + 32 * c, r);
-              ptx::tmem_ld_wait();
-              float4* const dst = reinterpret_cast<float4*>(drow + 32 * c);
-              if (w == 0) {
+      for (int r = 0; r < p.n_rounds; ++r) {
+        const int nsub = round_subs(p, r);
+        for (int tau = 0; tau < p.seg_steps; ++tau) {
+          for (int k = 0; k < nsub; ++k) {
+            const Sub sub = round_sub(p, r, k);
+            const int t = sub.seg * p.seg_steps + tau;
+            for (int hh = 0; hh < p.n_half; ++hh) {
+              if ((t * p.n_half + hh) % p.Q != cidx) continue;
+              const int buf = nt & 1;
+              const long long j = (long long)t * STEP_J + (int)rank * 128 + 32 * q + lane;
+              const float osc = sc / p.rinv_y[j];              // dYhat_j = s |y_j| sum_i G''_ij x_i
+              ptx::mbar_wait(bar(B_ACCFULL + buf), (nt >> 1) & 1);
+              ptx::tc_fence_after();
+              if (leader && warp == 4 && lane == 0)   // every MMA of the task is complete: its ring tiles have been read
+                ptx::red_release_gpu_add(p.done + ((uint32_t)r * (uint32_t)p.seg_steps + (uint32_t)tau), 1u);
+              const int wq = min(256, p.d - 256 * hh);
+              const int wh = wq >> 1;                  // columns per epilogue-warp half
+              const long long col0 = 256 * hh + hcol * wh;
+              float* const lrow = p.dy + j * p.d + col0;
+              // the segment's last contribution of a row-sharded step goes to the owner's slot in peer memory
+              float* const orow = (sub.last && p.world > 0)
+                                      ? p.dy_peer[sub.seg] + (j - (long long)sub.seg * p.seg_steps * STEP_J) * p.d + col0
+                                      : lrow;
+              for (int c = 0; c < (wh >> 5); ++c) {
+                uint32_t rr[32];
+                ptx::tmem_ld_32x32b_x32(t_lane + buf * 256 + hcol * wh + 32 * c, rr);
+                ptx::tmem_ld_wait();
+                float4* const dst = reinterpret_cast<float4*>(orow + 32 * c);
+                if (sub.first) {
 #pragma unroll
-                for (int x4 = 0; x4 < 8; ++x4)
-                  dst[x4] = make_float4(__uint_as_float(r[4 * x4]) * sc, __uint_as_float(r[4 * x4 + 1]) * sc,
-                                        __uint_as_float(r[4 * x4 + 2]) * sc, __uint_as_float(r[4 * x4 + 3]) * sc);
-              } else {
-                float4 old[8];
+                  for (int x4 = 0; x4 < 8; ++x4)
+                    dst[x4] = make_float4(__uint_as_float(rr[4 * x4]) * osc, __uint_as_float(rr[4 * x4 + 1]) * osc,
+                                          __uint_as_float(rr[4 * x4 + 2]) * osc, __uint_as_float(rr[4 * x4 + 3]) * osc);
+                } else {
+                  const float4* const src = reinterpret_cast<const float4*>(lrow + 32 * c);
+                  float4 old[8];
 #pragma unroll
-                for (int x4 = 0; x4 < 8; ++x4) old[x4] = dst[x4];
+                  for (int x4 = 0; x4 < 8; ++x4) old[x4] = src[x4];
 #pragma unroll
-                for (int x4 = 0; x4 < 8; ++x4)
-                  dst[x4] = make_float4(fmaf(__uint_as_float(r[4 * x4]), sc, old[x4].x),
-                                        fmaf(__uint_as_float(r[4 * x4 + 1]), sc, old[x4].y),
-                                        fmaf(__uint_as_float(r[4 * x4 + 2]), sc, old[x4].z),
-                                        fmaf(__uint_as_float(r[4 * x4 + 3]), sc, old[x4].w));
+                  for (int x4 = 0; x4 < 8; ++x4)
+                    dst[x4] = make_float4(fmaf(__uint_as_float(rr[4 * x4]), osc, old[x4].x),
+                                          fmaf(__uint_as_float(rr[4 * x4 + 1]), osc, old[x4].y),
+                                          fmaf(__uint_as_float(rr[4 * x4 + 2]), osc, old[x4].z),
+                                          fmaf(__uint_as_float(rr[4 * x4 + 3]), osc, old[x4].w));
+                }
               }
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(accempty_leader + 8u * buf);
+              ++nt;
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(accempty_leader + 8u * buf);
-            ++nt;
           }
         }
       }

@@ -179,12 +179,24 @@ class CudaEngine:
                                                 ws.numel(), _stream()), "backward_dx")
         return dx, ds
 
-    def backward_both_bytes(self, n, d, dtype, scale, flags=0):
-        """Workspace of the two-sided backward (one sweep emits dA and dB) for an [n,d] x [n,d] step; 0 = not served."""
+    def backward_both_bytes(self, n_rows, n_cols, d, dtype, scale, flags=0, world=0):
+        """Workspace of the two-sided backward (one sweep over the logits tiles emits dA and dB) for [n_rows,d] x [n_cols,d];
+        world = 0: one GPU, world >= 2: the row-sharded step.  0 = the shape is not served."""
         nbytes = ctypes.c_size_t(0)
-        _lib.check(self.lib.clipnce_backward_both_workspace_bytes(n, d, _DT[dtype], float(scale), flags, ctypes.byref(nbytes)),
-                   "backward_both_workspace_bytes")
+        _lib.check(self.lib.clipnce_backward_both_workspace_bytes(n_rows, n_cols, d, _DT[dtype], float(scale), flags, world,
+                                                                  ctypes.byref(nbytes)), "backward_both_workspace_bytes")
         return nbytes.value
+
+    def _both_ws(self, n_rows, n_cols, d, dtype, scale, flags, world, dev):
+        nbytes = self.backward_both_bytes(n_rows, n_cols, d, dtype, scale, flags, world)   # host-only; depends on the producer split
+        if nbytes == 0:
+            raise RuntimeError("clip_dplm_b200: the two-sided backward does not serve this shape")
+        key = ("both", n_rows, n_cols, d, dtype, flags, world, dev, torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
+        return ws
 
     @_guard
     def backward_both(self, x, y, rinv_x, rinv_y, scale, row_m, row_w, col_m, col_w, diag_w, x_orig, y_orig, out_dtype,
@@ -195,14 +207,7 @@ class CudaEngine:
         dev = x.device
         self._chk(x_orig, (torch.bfloat16, torch.float32), "x_orig")
         self._chk(y_orig, (x_orig.dtype,), "y_orig")
-        key = ("both", n, d, x.dtype, flags, dev, torch.cuda.current_stream(dev).cuda_stream)
-        nbytes = self.backward_both_bytes(n, d, x.dtype, scale, flags)   # host-only call; depends on the producer split too
-        if nbytes == 0:
-            raise RuntimeError("clip_dplm_b200: the two-sided backward does not serve this shape")
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._ws[key] = ws
+        ws = self._both_ws(n, n, d, x.dtype, scale, flags, 0, dev)
         dx = torch.empty((n, d), dtype=out_dtype, device=dev)
         dy = torch.empty((n, d), dtype=out_dtype, device=dev)
         ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
@@ -213,6 +218,38 @@ class CudaEngine:
                                                      flags, _p(xo), _p(yo), _DT[xo.dtype], _p(grad_scale), _p(dx), _p(dy),
                                                      _DT[out_dtype], _p(ds), _p(ws), ws.numel(), _stream()), "backward_both_dx")
         return dx, dy, ds
+
+    @_guard
+    def backward_both_sharded(self, x, y, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, x_orig,
+                              out_dtype, peers, world, rank, slots_off, grad_scale=None, flags=0, want_dscale=True,
+                              scale_dev=None):
+        """Row-sharded two-sided backward (clipnce_backward_both_sharded): -> dx [n,d] (finished), d_scale_sum [1] or None;
+        the partial dB of every owner rank is stored into its slot over NVLink peer memory (publish with a barrier, then
+        `finish_slots`)."""
+        n, d = x.shape
+        n_cols = y.shape[0]
+        dev = x.device
+        self._chk(x_orig, (torch.bfloat16, torch.float32), "x_orig")
+        ws = self._both_ws(n, n_cols, d, x.dtype, scale, flags, world, dev)
+        dx = torch.empty((n, d), dtype=out_dtype, device=dev)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+        xo = x if x_orig.dtype == x.dtype else x_orig
+        _lib.check(self.lib.clipnce_backward_both_sharded(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n, n_cols, d, int(diag_offset),
+                                                          float(scale), _p(scale_dev), _p(row_m), _p(row_w), _p(col_m), _p(col_w),
+                                                          float(diag_w), _DT[x.dtype], flags, _p(xo), _DT[xo.dtype],
+                                                          _p(grad_scale), _p(dx), _DT[out_dtype], _p(ds), peers, world, rank,
+                                                          int(slots_off), _p(ws), ws.numel(), _stream()), "backward_both_sharded")
+        return dx, ds
+
+    @_guard
+    def finish_slots(self, slots, n_slots, x, x_orig, rinv, out_dtype, grad_scale=None):
+        """dx = normalise-backward(sum of the n_slots partial gradients [n_slots][n,d] f32), fixed order."""
+        n, d = x.shape
+        dx = torch.empty((n, d), dtype=out_dtype, device=x.device)
+        xo = x if x_orig.dtype == x.dtype else x_orig
+        _lib.check(self.lib.clipnce_finish_slots(_p(slots), n_slots, _p(x), _DT[x.dtype], _p(xo), _DT[xo.dtype], _p(rinv),
+                                                 _p(grad_scale), n, d, _p(dx), _DT[out_dtype], _stream()), "finish_slots")
+        return dx
 
     @_guard
     def softmax_weights(self, l, coef):

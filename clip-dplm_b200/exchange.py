@@ -26,7 +26,7 @@ import warnings
 import torch
 import torch.distributed as dist
 
-PHASE_COLS, PHASE_STATS, PHASE_LOSS, PHASE_CLOSE = 0, 1, 2, 3
+PHASE_COLS, PHASE_STATS, PHASE_LOSS, PHASE_CLOSE, PHASE_GRADS = 0, 1, 2, 3, 4
 # The A rows travel beside the forward sweep.  Every SM a push kernel takes costs the sweep a CTA-pair slot and -- its grid
 # being sized in whole waves of slots -- part of an extra wave (a full-grid push: 365 -> 435 us on 8 GPUs; 8 fat blocks:
 # +20 us on 8 GPUs, +80 us on 2 and 4), so by default the copy engines move them (CLIPNCE_LINK_BG=kernel for the push kernel
@@ -135,6 +135,8 @@ class PeerExchange:
         self.o_coll = region(self.world * n_cols * 4)
         self.o_rowm = region(self.N * 4)
         self.o_rowl = region(self.N * 4)
+        # partial dB_hat slots of the two-sided backward: rank q stores its contribution to MY columns into slot q
+        self.o_slots = region(self.world * n_local * d * 4)
         self.nbytes = off
         self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
         self.buf.zero_()
@@ -162,6 +164,7 @@ class PeerExchange:
         self.coll = view(self.o_coll, self.world * n_cols, torch.float32)
         self.rowm = view(self.o_rowm, self.N, torch.float32)
         self.rowl = view(self.o_rowl, self.N, torch.float32)
+        self.slots = view(self.o_slots, self.world * n_local * d, torch.float32)
         self.status = self.buf[self.status_off:self.status_off + 4].view(torch.int32)
 
     # ---------------------------------------------------------------- the exchange steps
@@ -207,6 +210,9 @@ class PeerExchange:
 
     def sum_scalars(self, vals, phase):
         return self.engine.link_sum_scalars(vals, self.peers, self.world, self.rank, phase)
+
+    def barrier(self, phase):
+        self.engine.link_barrier(self.peers, self.world, self.rank, phase)
 
     def check(self):
         """Host check of the status word (synchronises): raises if a barrier timed out.  A timeout also traps on the

@@ -60,6 +60,7 @@ class StepState:
     want_t: bool
     compute_dtype: torch.dtype
     xchg: object = None             # the exchange of this step (exchange.py); None on one GPU
+    both_sharded: bool = False      # the backward will run the row-sharded two-sided kernel (no gathered A rows needed)
 
 
 def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, group=None,
@@ -79,6 +80,7 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
     n_extra = extra.shape[0] if extra is not None else 0
 
     xchg = None
+    both_sharded = False
     rinv_a, _ = engine.normalize(a)
     a_c, _ = engine.stage(a, compute_dtype)
     if world > 1:
@@ -86,8 +88,15 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
         # to step would otherwise need a new set -- a host-side rendezvous -- for every length)
         xchg = _exchange.open_exchange(engine, group, n_local, d, n_global, compute_dtype, a.device)
         b_c, rinv_b, y, rinv_y = xchg.gather_cols(b, compute_dtype)
-        if need_grad:   # side B of the backward streams every rank's A rows; they travel behind the forward sweep
-            xchg.gather_rows_begin(a, a_c, rinv_a, compute_dtype)
+        if need_grad:
+            if callable(scale):
+                scale = scale()
+            # two-sided backward over peer memory (one sweep emits dA and the reduce-scattered dB): nothing to gather
+            both_sharded = bool(symmetric and extra is None and compute_dtype == torch.bfloat16 and
+                                getattr(xchg, "kind", "") == "nvlink-peer" and hasattr(engine, "backward_both_sharded") and
+                                engine.backward_both_bytes(n_local, n_global, d, compute_dtype, scale, flags, world) > 0)
+            if not both_sharded:   # side B of the backward streams every rank's A rows; they travel behind the forward sweep
+                xchg.gather_rows_begin(a, a_c, rinv_a, compute_dtype)
     else:
         rinv_b, _ = engine.normalize(b)
         b_c, _ = engine.stage(b, compute_dtype)
@@ -111,10 +120,13 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
         fixed = bool(fixed is not None and fixed(compute_dtype, d, scale, flags))
         # only the batch's own columns are exchanged: extra negatives carry no positives, so their column statistics are
         # never used (no column loss, no column soft-max: the sum is set to +inf below)
-        gm, gl, row_m_all, row_l_all = xchg.exchange_stats(row_m, row_l, col_m[:n_global], col_l[:n_global], fixed, need_grad)
+        gm, gl, row_m_all, row_l_all = xchg.exchange_stats(row_m, row_l, col_m[:n_global], col_l[:n_global], fixed,
+                                                           need_grad and not both_sharded)
+        if both_sharded:
+            row_m_all, row_l_all = row_m, row_l
         col_m = torch.cat([gm, col_m[n_global:]]) if n_extra else gm
         col_l = torch.cat([gl, col_l[n_global:]]) if n_extra else gl
-        xa, rinv_xa = xchg.gather_rows_end() if need_grad else (None, None)
+        xa, rinv_xa = xchg.gather_rows_end() if (need_grad and not both_sharded) else ((a_c, rinv_a) if both_sharded else (None, None))
     if n_extra:
         col_l[n_global:] = float("inf")
     loss = engine.loss(row_m, row_l, col_m, col_l, diag, diag_offset, n_global, symmetric)
@@ -125,7 +137,7 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
             xchg = None
     st = StepState(a, b, a_c, b_c, y, y_t, xa, None, rinv_a, rinv_b, rinv_y, rinv_xa, row_m, row_l, row_m_all, row_l_all,
                    col_m, col_l, diag, scale, scale_dev, symmetric, n_local, n_global, diag_offset, flags, group, want_t,
-                   compute_dtype, xchg)
+                   compute_dtype, xchg, both_sharded)
     return loss, st
 
 
@@ -152,10 +164,24 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     both = getattr(engine, "backward_both", None)
     if (both is not None and st.xchg is None and st.symmetric and st.y is st.b_c and st.xa is st.a_c and not st.want_t
             and st.a.dtype == st.b.dtype and (grad_dtype_a or st.a.dtype) == (grad_dtype_b or st.b.dtype)
-            and st.compute_dtype == torch.bfloat16 and engine.backward_both_bytes(n, st.a_c.shape[1], st.compute_dtype,
+            and st.compute_dtype == torch.bfloat16 and engine.backward_both_bytes(n, n, st.a_c.shape[1], st.compute_dtype,
                                                                                   st.scale, st.flags) > 0):
         da, db, ds = both(st.a_c, st.b_c, st.rinv_a, st.rinv_b, st.scale, st.row_m, row_w, col_m, col_w, diag_w, st.a, st.b,
                           grad_dtype_a or st.a.dtype, grad_scale, st.flags, want_dscale=True, **kw)
+        return da, db, ds
+
+    if st.both_sharded:
+        # row-sharded: ONE kernel sweeps local A rows x all columns, emits dA and stores every owner's partial dB straight
+        # into its slot over NVLink peer memory (contraction + reduce-scatter); after the barrier the owner sums its slots
+        x = st.xchg
+        da, ds = engine.backward_both_sharded(st.a_c, st.y, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w, col_m, col_w,
+                                              diag_w, st.a, grad_dtype_a or st.a.dtype, x.peers, x.world, x.rank, x.o_slots,
+                                              grad_scale, st.flags, want_dscale=True, **kw)
+        x.barrier(_exchange.PHASE_GRADS)
+        db = engine.finish_slots(x.slots, x.world, st.b_c, st.b, st.rinv_b, grad_dtype_b or st.b.dtype, grad_scale)
+        ds = x.sum_scalars(ds, _exchange.PHASE_CLOSE)
+        x.release()
+        st.xchg = None
         return da, db, ds
 
     # side A: local rows of A x all columns -> dA (normalise backward fused into the tail) and sum G.S over the local

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 103
+#define CLIPNCE_VERSION 104
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -172,10 +172,13 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
  * caller's rows x_orig / y_orig (the normalise backward and grad_scale are applied as in clipnce_backward_dx);
  * d_scale_sum [1] += sum_ij G_ij S_ij (or NULL).
  * clipnce_backward_both_workspace_bytes() returns 0 bytes in *out when the shape is not served (then use two
- * clipnce_backward_dx calls): bf16, fixed-shift regime (2 s <= 86), d in {128,...,512}, n % 256 == 0, n >= 16384, and a
- * device on which all CTA pairs of the persistent grid are co-resident.  CLIPNCE_NO_BWD2=1 disables it.
+ * clipnce_backward_dx calls): bf16, fixed-shift regime (2 s <= 86), d in {128,...,512}, n_rows % 128 == 0,
+ * n_cols % 256 == 0, n_rows * n_cols >= 16384^2, and a device on which all CTA pairs of the persistent grid are
+ * co-resident.  world = 0: one GPU (n_rows == n_cols); world >= 2: the row-sharded step below.  CLIPNCE_NO_BWD2=1
+ * disables the path.
  */
-int clipnce_backward_both_workspace_bytes(int64_t n, int64_t d, int dtype, float scale, int flags, size_t* out);
+int clipnce_backward_both_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale, int flags,
+                                          int world, size_t* out);
 int clipnce_backward_both_dx(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n,
                              int64_t d, float scale, const float* scale_dev,
                              const float* row_m, const float* row_w, const float* col_m, const float* col_w,
@@ -183,6 +186,33 @@ int clipnce_backward_both_dx(const void* x, const void* y, const float* rinv_x, 
                              const void* x_orig, const void* y_orig, int in_dtype, const float* grad_scale,
                              void* dx, void* dy, int out_dtype, float* d_scale_sum,
                              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The same sweep for the ROW-SHARDED global batch (replaces what autograd + DDP do behind the
+ * reference's all_gather formulation, old/clip_opt.py:102-112, run1/full.py:77-84): x = this rank's A rows [n_rows,d],
+ * y = ALL ranks' B rows [n_cols,d] (n_cols = world * n_rows, rank r owns columns [r n_rows, (r+1) n_rows)),
+ * diag_offset = rank * n_rows, row_* for the local rows, col_* for all columns.  One kernel is the contraction AND the
+ * reduce-scatter of the partial dB: dx [n_rows,d] comes out finished; the partial dB_hat of the columns owned by rank s
+ * is stored, as it completes, straight into rank s's buffer over NVLink peer memory at
+ *   peer_base[s] + slots_offset + rank * n_rows * d * 4        ([world][n_rows, d] f32 slots per rank).
+ * After a barrier (clipnce_link_barrier) every rank sums its world slots and applies the normalise backward with
+ * clipnce_finish_slots.  peer_base: see the exchange section below.
+ */
+int clipnce_backward_both_sharded(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
+                                  int64_t n_rows, int64_t n_cols, int64_t d, int64_t diag_offset, float scale,
+                                  const float* scale_dev,
+                                  const float* row_m, const float* row_w, const float* col_m, const float* col_w,
+                                  float diag_w, int dtype, int flags,
+                                  const void* x_orig, int in_dtype, const float* grad_scale, void* dx, int out_dtype,
+                                  float* d_scale_sum,
+                                  void* const* peer_base, int world, int rank, int64_t slots_offset,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* dx_i = normalise-backward( sum_k slots[k][i, :] ), k < n_slots in fixed order: the tail of the row-sharded two-sided
+ * backward (slots [n_slots][n, d] f32 = the ranks' partial gradients of the normalised rows x_hat). */
+int clipnce_finish_slots(const float* slots, int n_slots, const void* x, int dtype, const void* x_orig, int in_dtype,
+                         const float* rinv, const float* grad_scale, int64_t n, int64_t d, void* dx, int out_dtype,
+                         void* stream);
 
 /* w_i = coef / l_i  (l = +inf -> 0).  Builds row_w / col_w from the forward's sums. */
 int clipnce_softmax_weights(const float* l, int64_t n, float coef, float* w, void* stream);

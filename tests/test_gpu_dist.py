@@ -2,6 +2,7 @@
 the single-process reference on the concatenated batch -- through the NVLink peer-memory exchange
 kernels (the product path, "link") and through the NCCL collectives (the baseline it is measured against, "nccl").
 The exchange kernels themselves also run on ONE GPU (a one-rank group): test_peer_exchange_kernels_single_rank."""
+import math
 import os
 
 import pytest
@@ -14,9 +15,13 @@ from oracle import ref_step as O
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, d, comm, q):
+def _worker(rank, world, port, n, d, comm, q, both=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if both:
+        os.environ["CLIPNCE_BWD2_MIN_N"] = "256"    # serve the small test shape with the two-sided kernel
+    else:
+        os.environ["CLIPNCE_NO_BWD2"] = "1"
     os.environ.setdefault("CLIPNCE_LINK_TIMEOUT_MS", "30000")   # a lost rank fails the test in 30 s, not in 10 min
     os.environ["CLIPNCE_COMM"] = comm
     torch.cuda.set_device(rank)
@@ -33,16 +38,19 @@ def _worker(rank, world, port, n, d, comm, q):
         torch.cuda.synchronize()
         from clip_dplm_b200 import exchange
         assert exchange.comm_kind(dist.group.WORLD) == comm
+        if both:
+            from clip_dplm_b200.engine import default_engine
+            assert default_engine().backward_both_bytes(nl, n, d, torch.bfloat16, 14.3, 0, world) > 0, "two-sided path not served"
         q.put((rank, float(loss.detach()), ac.grad.float().cpu().numpy(), bc.grad.float().cpu().numpy(), float(t.grad)))
         exchange.reset()
     finally:
         dist.destroy_process_group()
 
 
-def _run(target, args, world, timeout=300):
+def _run(target, args, world, timeout=300, extra=()):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=target, args=(r, world) + tuple(args) + (q,)) for r in range(world)]
+    procs = [ctx.Process(target=target, args=(r, world) + tuple(args) + (q,) + tuple(extra)) for r in range(world)]
     for p in procs:
         p.start()
     import queue as _queue
@@ -114,6 +122,27 @@ def _worker_topk_and_graph(rank, world, port, q):
         exchange.reset()
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("n,d", [(1024, 256), (8192, 512)])
+def test_row_sharded_two_sided_backward(n, d):
+    """The row-sharded step through the two-sided kernel: local A rows x all columns in one sweep, dA finished locally,
+    every owner's partial dB stored into its slot over NVLink peer memory (contraction + reduce-scatter), summed in fixed
+    order -- against the sampled-row CPU oracle on the concatenated batch."""
+    import numpy as np
+    from oracle import sampled as SO
+    world = 2
+    out = _run(_worker, (21700 + (os.getpid() % 2000), n, d, "link"), world, extra=(True,))
+    a, b = O.make_inputs(n, d, seed=33)
+    rng = np.random.default_rng(n)
+    rows = np.sort(rng.choice(n, 128, replace=False))
+    ref = SO.sampled_reference(a, b, math.exp(O.LOGIT_SCALE_INIT), rows, rows)
+    da = np.concatenate([o[2] for o in out])
+    db = np.concatenate([o[3] for o in out])
+    for rank, loss, _, _, dt in out:
+        cmp = SO.compare(ref, loss, da[rows], db[rows], dt)
+        assert cmp["ok"], cmp
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

@@ -439,16 +439,20 @@ def test_benchmarked_shapes_against_sampled_oracle(n, d, ls, mix):
 # ------------------------------------------------------------------------------------------------
 # two-sided backward (csrc/kernels_pair2.cuh): one sweep over the logits tiles emits dA and dB
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,d,forced_p", [(4096, 512, 0), (4096, 512, 5), (2048, 256, 3), (2048, 128, 0), (3072, 384, 7)])
-def test_two_sided_backward(monkeypatch, n, d, forced_p):
+@pytest.mark.parametrize("n,d,forced_p,seg", [(4096, 512, 0, 0), (4096, 512, 5, 1), (2048, 256, 3, 1), (2048, 128, 0, 0),
+                                                (3072, 384, 7, 1), (4096, 512, 5, 2), (4096, 256, 0, 2), (2048, 512, 70, 8)])
+def test_two_sided_backward(monkeypatch, n, d, forced_p, seg):
     """clipnce_backward_both_dx against the dense float64 closed form AND against the two-sweep path on the same inputs.
-    `forced_p` producer pairs force several row-block waves (the last one partly filled), ring wrap-around and the
-    read-modify-write of dB across waves at a size the dense oracle still reaches."""
+    `forced_p` producer pairs force several rounds of work items (the last one partly filled), ring wrap-around and the
+    read-modify-write of dB across rounds at a size the dense oracle still reaches; `seg` column segments force rounds
+    that straddle segment boundaries (several consumer tasks per step) and per-segment dA slabs."""
     from clip_dplm_b200.engine import CudaEngine
     monkeypatch.setenv("CLIPNCE_BWD2_MIN_N", "256")
     if forced_p:
         monkeypatch.setenv("CLIPNCE_BWD2_P", str(forced_p))
-    assert CudaEngine().backward_both_bytes(n, d, torch.bfloat16, 1 / 0.07) > 0, "two-sided backward not served on this device"
+    if seg:
+        monkeypatch.setenv("CLIPNCE_BWD2_SEG", str(seg))
+    assert CudaEngine().backward_both_bytes(n, n, d, torch.bfloat16, 1 / 0.07) > 0, "two-sided backward not served on this device"
     a, b = O.make_inputs(n, d, seed=91)
     loss2, da2, db2, dt2 = run_fused(a, b, O.LOGIT_SCALE_INIT, torch.bfloat16)
     monkeypatch.setenv("CLIPNCE_NO_BWD2", "1")
