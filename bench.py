@@ -102,7 +102,7 @@ def visible_gpu_index(local_rank):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_step_sample(n_global, d, rows, steps, warmup, threads):
+def reference_step_sample(n_global, d, rows, steps, warmup, threads, scale=1 / 0.07, mix=0.5):
     """The reference's own op sequence (oracle/ref_step.py == old/clip.py:63-67 + rna_clip_codes.ipynb:
     1952-1953 + loss.backward()) on the host cores, on a bounded sample of the workload: a block of
     `rows` rows of the global batch against ALL n_global columns, so every sampled pair costs what it costs
@@ -114,8 +114,8 @@ def reference_step_sample(n_global, d, rows, steps, warmup, threads):
     g = torch.Generator().manual_seed(1234)
     a = torch.randn(rows, d, generator=g).to(torch.bfloat16).float()
     b = torch.randn(n_global, d, generator=g).to(torch.bfloat16).float()
-    b[:rows] = (0.5 * a + 0.5 * b[:rows]).to(torch.bfloat16).float()
-    t = torch.tensor(O.LOGIT_SCALE_INIT)
+    b[:rows] = (mix * a + (1.0 - mix) * b[:rows]).to(torch.bfloat16).float()
+    t = torch.tensor(math.log(scale))
     times = []
     for it in range(warmup + steps):
         ar, br, tr = a.clone().requires_grad_(True), b.clone().requires_grad_(True), t.clone().requires_grad_(True)
@@ -137,9 +137,14 @@ def workload_desc(n, d):
             f"logit_scale = ln(1/0.07)")
 
 
-def config_dict(n, d):
+def config_dict(n, d, scale=1 / 0.07, mix=0.5):
     """`config` of the JSON line -- byte-identical on both arms (what differs between them lives under `run`)."""
-    return {"workload": workload_desc(n, d), "global_batch": n, "d": d,
+    wl = workload_desc(n, d)
+    if abs(scale - 1 / 0.07) > 1e-9:
+        wl = wl.replace("logit_scale = ln(1/0.07)", f"logit_scale = ln({scale:g})")
+    if mix != 0.5:
+        wl = wl.replace("b = 0.5a + 0.5 noise", f"b = {mix:g}a + {1 - mix:g} noise")
+    return {"workload": wl, "global_batch": n, "d": d,
             "l2": f"no flush: operands + outputs + partials of one step (>= {max(1, 8 * n * d // 1000000)} MB at this size; "
                   "450 MB at N=65536) exceed the 126 MB L2"}
 
@@ -149,13 +154,13 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     rows = args.ref_rows
-    value, t_med = reference_step_sample(args.n, args.d, rows, args.steps, max(args.warmup, 1), threads)
+    value, t_med = reference_step_sample(args.n, args.d, rows, args.steps, max(args.warmup, 1), threads, args.scale, args.mix)
     sample = (f"{rows} rows of the global batch x all {args.n} columns per step (per-pair cost identical to the full "
               f"problem; full N^2 fp32 logits do not fit in host RAM), fp32, torch CPU {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_med, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.n, args.d),
+            "config": config_dict(args.n, args.d, args.scale, args.mix),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -343,9 +348,9 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce = wrap("all_reduce", _orig_ar)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     a = torch.randn(n_local, d, device=dev, generator=g)
-    b = (0.5 * a + 0.5 * torch.randn(n_local, d, device=dev, generator=g)).to(torch.bfloat16)
+    b = (args.mix * a + (1.0 - args.mix) * torch.randn(n_local, d, device=dev, generator=g)).to(torch.bfloat16)
     a = a.to(torch.bfloat16)
-    logit_scale = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+    logit_scale = torch.tensor(math.log(args.scale), device=dev, requires_grad=True)
     a_host = a.cpu().pin_memory()
     b_host = b.cpu().pin_memory()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
@@ -508,14 +513,14 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, t_med = reference_step_sample(n_global, d, args.ref_rows, 3, 1, threads)
+        v, t_med = reference_step_sample(n_global, d, args.ref_rows, 3, 1, threads, args.scale, args.mix)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.ref_rows} rows x all {n_global} columns per step, fp32 torch CPU, median of 3 ({t_med:.2f} s/step)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": config_dict(n_global, d),
+        "config": config_dict(n_global, d, args.scale, args.mix),
         "run": {"rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                 "comm": {"link": "own kernels over NVLink peer memory (fused normalise+gather, pushes, device barriers)",
                          "nccl": "NCCL collectives", "none": "none"}.get(comm, comm),
@@ -555,6 +560,10 @@ def main():
     # (--global-batch / --embed-dim: torchrun's own parser rejects "--n" as an ambiguous abbreviation of its options)
     ap.add_argument("--n", "--global-batch", dest="n", type=int, default=65536, help="global batch")
     ap.add_argument("--d", "--embed-dim", dest="d", type=int, default=512)
+    ap.add_argument("--scale", type=float, default=1 / 0.07, help="s = exp(logit_scale); beyond 40 the kernels with true "
+                    "running maxima serve the step (the clamp(max=100) regime of old/clip_opt.py:100)")
+    ap.add_argument("--mix", type=float, default=0.5, help="b = mix a + (1 - mix) noise (use ~0.1 with --scale 100: at 0.5 the "
+                    "loss underflows to 0)")
     ap.add_argument("--ref-rows", type=int, default=1024, help="row block of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row oracle check of the benchmarked step")

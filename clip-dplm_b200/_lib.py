@@ -18,6 +18,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "clipnce.h")
 
 BF16, F32 = 0, 1
 FLAG_FORCE_EXACT = 1
+FLAG_UNBOUNDED = 2
 
 _lock = threading.Lock()
 _lib = None

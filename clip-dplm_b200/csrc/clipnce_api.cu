@@ -46,16 +46,24 @@ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t elem_size(int dtype) { return dtype == CLIPNCE_BF16 ? 2 : 4; }
 
-bool tc_eligible(int dtype, int64_t d, float scale, int flags) {
-  return dtype == CLIPNCE_BF16 && !(flags & CLIPNCE_FLAG_FORCE_EXACT) && d >= 8 && d % 8 == 0 && d <= 768 &&
-         scale > 0.f && 2.f * scale <= 86.f;
-}
-
 // CTA-pair kernels (kernels_pair.cuh): the main tensor-core path.  CLIPNCE_NO_PAIR=1 forces the single-CTA kernels.
 bool pair_eligible(int64_t d) {
   static const bool off = [] { const char* e = getenv("CLIPNCE_NO_PAIR"); return e && atoi(e) != 0; }();
   return !off && d % 128 == 0 && d >= 128 && d <= 768;
 }
+
+// Kernel family.  0: exact CUDA-core kernels (fp32 check mode, shapes the tensor-core kernels do not take).
+// 1: tensor cores with the FIXED shift -- |S_ij| <= s, so exp(S - s) needs no running maximum; valid while e^(-2s) is a
+//    normal fp32.  The host's s may be a step or two stale (functional._ScaleHint), hence 2 s <= 80 instead of 86.
+// 2: tensor cores with TRUE maxima (online soft-max forward, two-exponential backward): any s -- the clamp(max=100)
+//    regime of old/clip_opt.py:100, run1/full.py:76 -- and logits not bounded by s (CLIPNCE_FLAG_UNBOUNDED: the
+//    un-normalised queue rows of tong/utils/losses.py:10-14).  CTA-pair kernels only (d % 128 == 0).
+int tc_family(int dtype, int64_t d, float scale, int flags) {
+  if (dtype != CLIPNCE_BF16 || (flags & CLIPNCE_FLAG_FORCE_EXACT) || d < 8 || d % 8 != 0 || d > 768 || !(scale > 0.f)) return 0;
+  if (!(flags & CLIPNCE_FLAG_UNBOUNDED) && 2.f * scale <= 80.f) return 1;
+  return pair_eligible(d) ? 2 : 0;
+}
+bool tc_eligible(int dtype, int64_t d, float scale, int flags) { return tc_family(dtype, d, scale, flags) == 1; }
 
 // ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda) ----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -63,7 +71,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
-bool g_attr_done[12] = {};
+bool g_attr_done[16] = {};
 
 int get_encode(EncodeTiledFn* out) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -187,8 +195,10 @@ int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams
   return 0;
 }
 
+template <bool TWO_EXP>
 int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_t st) {
-  auto kern = pair::bwd_kernel;
+  auto kern = pair::bwd_kernel<TWO_EXP>;
+  constexpr int attr_slot = TWO_EXP ? 12 : 6;
   const int total = (pair::SMEM_LIMIT - pair::bwd_smem_bytes(p.nkc, 0)) / pair::STAGE_BYTES;
   if (total < 4) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for the TMA rings", p.d);
   auto cap = [](int v) { return v > pair::MAX_STAGES ? pair::MAX_STAGES : v; };
@@ -202,9 +212,9 @@ int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_
   if ((rc = make_tmap(&tyg, y, p.d, p.n_cols, p.d, 64))) return rc;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_attr_done[6]) {
+    if (!g_attr_done[attr_slot]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
-      g_attr_done[6] = true;
+      g_attr_done[attr_slot] = true;
     }
   }
   const int grid = 2 * p.n_pairs * (int)ceil_div(p.n_steps, p.split_steps);
@@ -247,9 +257,7 @@ extern "C" {
 int clipnce_version(void) { return CLIPNCE_VERSION; }
 const char* clipnce_last_error(void) { return g_err.c_str(); }
 
-int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags) {
-  return tc_eligible(dtype, d, scale, flags) ? 1 : 0;
-}
+int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags) { return tc_family(dtype, d, scale, flags); }
 
 int clipnce_needs_transposed(int dtype, int64_t d, float scale, int flags) {
   return (tc_eligible(dtype, d, scale, flags) && !pair_eligible(d)) ? 1 : 0;
@@ -274,6 +282,8 @@ int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype
   size_t pair_fwd = sizeof(float) * (2 * (size_t)ceil_div(n_rows, 128) * (size_t)round_up(n_cols, 256) +
                                      (size_t)pair::MAX_SPLIT * (size_t)n_rows);
   if (pair_fwd > tc_fwd) tc_fwd = pair_fwd;
+  const size_t online_fwd = sizeof(float) * 2 * (size_t)pair::MAX_SPLIT * (size_t)(n_rows + n_cols);   // (max, sum) partials, both launches
+  if (online_fwd > tc_fwd) tc_fwd = online_fwd;
   SimtFwdWs w = simt_fwd_ws(nullptr, n_rows, n_cols);
   size_t simt_bwd = sizeof(float) * (size_t)ceil_div(n_rows, simt::TILE);
   size_t m = tc_fwd;
@@ -345,6 +355,40 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
   cudaStream_t st = as_stream(stream);
   int rc = check_device_sm100();
   if (rc) return rc;
+
+  if (tc_family(dtype, d, scale, flags) == 2) {
+    // online soft-max: row statistics of (x, y), then of (y, x) -- the column statistics -- with true running maxima
+    if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
+    const int rows = d <= 512 ? 128 : 64;
+    float* wsf = reinterpret_cast<float*>(workspace);
+    size_t used = 0;
+    for (int side = 0; side < 2; ++side) {
+      const int64_t nr = side == 0 ? n_rows : n_cols, nc = side == 0 ? n_cols : n_rows;
+      pair::FwdParams p;
+      memset(&p, 0, sizeof p);
+      p.n_rows = (int)nr; p.n_cols = (int)nc; p.d = (int)d;
+      p.nkc = (int)ceil_div(d, 64); p.n_steps = (int)ceil_div(nc, pair::STEP_J);
+      p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev;
+      p.rinv_x = side == 0 ? rinv_x : rinv_y; p.rinv_y = side == 0 ? rinv_y : rinv_x;
+      p.diag = side == 0 ? diag : nullptr;
+      p.n_pairs = (int)ceil_div(nr, 2 * rows);
+      p.split_steps = pick_split_steps(p.n_pairs, p.n_steps, pair::MAX_SPLIT);
+      const int n_split = (int)ceil_div(p.n_steps, p.split_steps);
+      const size_t need = used + sizeof(float) * 2 * (size_t)n_split * (size_t)nr;
+      if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
+      p.row_part_m = wsf + used / sizeof(float);
+      p.row_part = p.row_part_m + (size_t)n_split * (size_t)nr;
+      used = need;
+      const void* xs = side == 0 ? x : y;
+      const void* ys = side == 0 ? y : x;
+      rc = rows == 128 ? launch_pair_fwd<128, 2>(7, xs, ys, p, st) : launch_pair_fwd<64, 2>(11, xs, ys, p, st);
+      if (rc) return rc;
+      aux::reduce_ml_partials<<<(unsigned)ceil_div(nr, 256), 256, 0, st>>>(p.row_part_m, p.row_part, n_split, nr, nr,
+                                                                            side == 0 ? row_m : col_m, side == 0 ? row_l : col_l);
+      CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+  }
 
   if (tc_eligible(dtype, d, scale, flags)) {
     if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
@@ -448,7 +492,8 @@ int backward_impl(const void* x, const void* y, const void* y_t, int64_t ld_t, c
   int rc = check_device_sm100();
   if (rc) return rc;
 
-  if (tc_eligible(dtype, d, scale, flags) && pair_eligible(d)) {
+  const int fam = tc_family(dtype, d, scale, flags);
+  if ((fam == 1 && pair_eligible(d)) || fam == 2) {
     if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "backward: operands must be 16-byte aligned");
     const int64_t n_blk = ceil_div(n_rows, 8);
     const size_t part_bytes = round_up(sizeof(float) * (size_t)n_blk, 256);
@@ -468,7 +513,7 @@ int backward_impl(const void* x, const void* y, const void* y_t, int64_t ld_t, c
     if (workspace_bytes < part_bytes) return fail(CLIPNCE_EWORKSPACE, "backward: workspace %zu < %zu", workspace_bytes, part_bytes);
     float* dx_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part_bytes);
     p.dx = n_split > 1 ? dx_part : dx_hat;
-    if ((rc = launch_pair_bwd(x, y, p, st))) return rc;
+    if ((rc = fam == 2 ? launch_pair_bwd<true>(x, y, p, st) : launch_pair_bwd<false>(x, y, p, st))) return rc;
     if (defer) {
       defer->parts = p.dx;
       defer->n_split = n_split;
@@ -727,7 +772,7 @@ bool bwd2_plan(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale
   auto cap = [](int v) { return v > pair2::MAXS ? pair2::MAXS : v; };
   pl->stages_b = cap(total / 2);
   pl->stages_a = cap(total - total / 2);
-  pl->stages_c = cap((pair::SMEM_LIMIT - pair2::SMALL) / pair2::C_STAGE);
+  pl->stages_c = cap((pair::SMEM_LIMIT - pair2::consumer_smem(0)) / pair2::C_STAGE);
   const int ps = pair2::producer_smem(nkc, pl->stages_a + pl->stages_b), cs = pair2::consumer_smem(pl->stages_c);
   pl->smem = ps > cs ? ps : cs;
   size_t off = 0;

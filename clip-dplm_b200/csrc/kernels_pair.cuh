@@ -71,7 +71,7 @@ constexpr int BWD_THREADS = 32 * (4 + BWD_EPI_WARPS);
 constexpr int BWD_ROWS = 64;                       // resident rows per CTA (128 per pair)
 constexpr int BWD_X_CHUNK = BWD_ROWS * 128;        // [64 rows][64 k] bf16
 constexpr int BWD_G_BYTES = 4 * 8192;              // gradient tile [64 i][256 j] bf16 = four K-major boxes
-constexpr int BWD_SMALL = 8192;                    // barriers (512) | tmem ptr | column vectors 2 x 3 x 256 f32 at +1024
+constexpr int BWD_SMALL = 10240;                   // barriers (512) | tmem ptr | column vectors 2 x 4 x 256 f32 at +1024
 
 struct BwdParams {
   int n_rows, n_cols, d;
@@ -97,6 +97,11 @@ __host__ __device__ constexpr int bwd_smem_bytes(int nkc, int stages) {
   return nkc * BWD_X_CHUNK + BWD_G_BYTES + stages * STAGE_BYTES + BWD_SMALL;
 }
 
+// TWO_EXP = false: the fixed-shift form, ONE ex2 per logit -- exp(S - s) (u_i + v_j) with u, v carrying exp(s - m).
+// TWO_EXP = true: exp(S - m_i) w_i + exp(S - m_j) w_j with the (shift, sum) pairs as they are, two ex2 per logit: valid
+// for ANY logit range (s up to the clamp at 100, un-normalised queue rows), because every exponent is <= 0 by
+// construction of the shifts (true maxima, or s where |S| <= s).
+template <bool TWO_EXP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
 bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 rows}
            const __grid_constant__ CUtensorMap tmap_y,    // Y  box {64 k, 128 rows}   (logits operand, K-major)
@@ -123,7 +128,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
   const uint32_t bars = base + small_off;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + small_off + 512);
-  float* const colv = reinterpret_cast<float*>(smem + small_off + 1024);   // [2][3][256]
+  float* const colv = reinterpret_cast<float*>(smem + small_off + 1024);   // [2][4][256]
 
   const int S_COL0 = TMEM_COLS - 128 * p.nsbuf;
   const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;   // s
@@ -281,7 +286,9 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float rx = row_ok ? p.rinv_x[i_glob] : 0.f;
     // u_i = row_w_i exp(s - row_m_i): exp(S - s) u_i = exp(S - row_m_i) row_w_i from ONE ex2 per logit
-    const float u = row_ok ? p.row_w[i_glob] * ex2((sc - p.row_m_in[i_glob]) * LOG2E) : 0.f;
+    const float u = (!TWO_EXP && row_ok) ? p.row_w[i_glob] * ex2((sc - p.row_m_in[i_glob]) * LOG2E) : 0.f;
+    const float rm2 = (TWO_EXP && row_ok) ? p.row_m_in[i_glob] * LOG2E : 0.f;   // TWO_EXP: exp(S - m_i) w_i directly
+    const float rw = (TWO_EXP && row_ok) ? p.row_w[i_glob] : 0.f;
     const uint32_t g_row = g_smem + kc * 8192 + (i_local >> 3) * 1024 + (i_local & 7) * 128;
     const uint32_t sw = i_local & 7;
     const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
@@ -292,20 +299,22 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
       const long long jn = (long long)(t_begin + t) * STEP_J + te;
       const bool ok = t < n_t && jn < p.n_cols;
       cw = (ok && p.col_w != nullptr) ? p.col_w[jn] : 0.f;
-      cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : sc;
+      cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : (TWO_EXP ? 0.f : sc);
       ry = ok ? p.rinv_y[jn] : 0.f;
+      if (TWO_EXP && !(cw > 0.f)) cm = 0.f;   // weight 0 (extra negative columns: sum = +inf): keep the exponent finite
     };
     float cw_n, cm_n, ry_n;
     load_col(0, cw_n, cm_n, ry_n);
 
     for (int t = 0; t < n_t; ++t) {
       const int sb = t % p.nsbuf;
-      float* const cv = colv + (t & 1) * 768;
+      float* const cv = colv + (t & 1) * 1024;
       {
-        const float vj = cw_n * ex2((sc - cm_n) * LOG2E);
+        const float vj = TWO_EXP ? cw_n : cw_n * ex2((sc - cm_n) * LOG2E);
         cv[te] = ry_n * k2;          // S_ij log2(e) = acc * rinv_x[i] * cj
         cv[256 + te] = vj * ry_n;      // G is contracted against the RAW y_j -> fold rinv_y[j] into it
         cv[512 + te] = ry_n;
+        if (TWO_EXP) cv[768 + te] = cm_n * LOG2E;
       }
       load_col(t + 1, cw_n, cm_n, ry_n);
       named_bar_sync(1, BWD_EPI_WARPS * 32);
@@ -335,11 +344,23 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
           const float vrv[4] = {vr4.x, vr4.y, vr4.z, vr4.w};
           const float ryv[4] = {ry4.x, ry4.y, ry4.z, ry4.w};
           float g[4];
+          if constexpr (TWO_EXP) {
+            const float4 cm4 = *reinterpret_cast<const float4*>(cjp + 768 + 4 * x4);
+            const float cmv[4] = {cm4.x, cm4.y, cm4.z, cm4.w};
 #pragma unroll
-          for (int xx = 0; xx < 4; ++xx) {
-            const float y = __uint_as_float(r[4 * x4 + xx]) * rx;
-            const float ev = ex2(fmaf(y, cjv[xx], -k2));              // exp(S_ij - s)
-            g[xx] = ev * fmaf(u, ryv[xx], vrv[xx]);                     // (u_i + v_j) rinv_y[j]
+            for (int xx = 0; xx < 4; ++xx) {
+              const float y = __uint_as_float(r[4 * x4 + xx]) * rx;
+              const float er = ex2(fmaf(y, cjv[xx], -rm2)) * rw;        // exp(S_ij - m_i) w_i
+              const float ec = ex2(fmaf(y, cjv[xx], -cmv[xx]));         // exp(S_ij - m_j)
+              g[xx] = fmaf(er, ryv[xx], ec * vrv[xx]);                    // (...) rinv_y[j]
+            }
+          } else {
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx) {
+              const float y = __uint_as_float(r[4 * x4 + xx]) * rx;
+              const float ev = ex2(fmaf(y, cjv[xx], -k2));              // exp(S_ij - s)
+              g[xx] = ev * fmaf(u, ryv[xx], vrv[xx]);                     // (u_i + v_j) rinv_y[j]
+            }
           }
           if (has_diag) {
 #pragma unroll
@@ -409,7 +430,8 @@ struct FwdParams {
   const float* scale_dev;  // optional DEVICE scalar s (see BwdParams)
   const float* rinv_x;
   const float* rinv_y;
-  float* row_part;    // [n_split][n_rows] partial sum_j exp(S_ij - s) over the item's columns
+  float* row_part;    // [n_split][n_rows] partial sum_j exp(S_ij - s) over the item's columns (MODE 2: sum_j exp(S_ij - m))
+  float* row_part_m;  // MODE 2: [n_split][n_rows] the item's running row maximum m (natural-log units)
   float* col_part;    // [gridDim.x][col_ld] partial sum_i exp(S_ij - s) over this CTA's rows
   long long col_ld;   // n_steps * 256
   float* diag;        // [n_rows]
@@ -428,13 +450,18 @@ __host__ __device__ constexpr int fwd_smem_bytes(int rows, int nkc, int stages) 
 // ROWS = resident rows per CTA: 128 (M = 256, lane = row) for d <= 512, else 64 (M = 128, 2x2 layout).
 // MODE 0: InfoNCE forward statistics.  MODE 1 (ROWS = 128 only): retrieval -- the same similarity sweep with a running
 // top-KT per row instead of the soft-max sums (run1/full.py:152 argmax, :157 cosine_similarity; BASELINE config 5).
+// MODE 2: ROW statistics only, with a true running maximum (online soft-max): for logit scales beyond the fixed shift's
+// range -- exp().clamp(max=100) of old/clip_opt.py:100, run1/full.py:76 -- and for un-normalised queue rows
+// (tong/utils/losses.py:10-14), where |S_ij| <= s does not hold.  The column statistics come from a second launch with
+// the operands swapped (thread = row makes the row maximum a thread-local scalar; a column maximum would need a
+// cross-lane reduction per tile).
 template <int ROWS, int MODE = 0, int KT = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS rows}
            const __grid_constant__ CUtensorMap tmap_y,   // Y box {64 k, 128 rows}
            const FwdParams p) {
   static_assert(ROWS == 64 || ROWS == 128, "ROWS");
-  static_assert(MODE == 0 || ROWS == 128, "retrieval uses the 128-row variant");
+  static_assert(MODE != 1 || ROWS == 128, "retrieval uses the 128-row variant");
   constexpr int X_CHUNK = ROWS * 128;
   constexpr int SBUF_COLS = ROWS == 128 ? 256 : 128;       // TMEM columns of one logits buffer
   constexpr int NCH = ROWS == 128 ? 2 : 1;                 // 32-column chunks per warp per step
@@ -646,6 +673,104 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
       for (int k = 0; k < KT; ++k) {
         p.cand_score[o + k] = bv[k] * rx;
         p.cand_idx[o + k] = bi[k] < 0 ? -1 : (int)(p.col_offset + bi[k]);
+      }
+    }
+  } else if (warp >= 4 && MODE == 2) {
+    // ================================================================= epilogue (online soft-max): row (max, sum), diagonal
+    const int e = warp - 4;
+    const int q = warp & 3;
+    const int cgp = e >> 2;
+    const int i_local = ROWS == 128 ? 32 * q + lane : 32 * (q & 1) + lane;
+    const long long i_glob = (long long)i0 + i_local;
+    const bool row_ok = i_glob < p.n_rows;
+    const int col0 = (ROWS == 128 ? 64 : 32) * cgp;
+    const int jl0 = (ROWS == 128 ? 0 : 128 * (q >> 1)) + col0;
+    const int te = threadIdx.x - 128;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float rx = row_ok ? p.rinv_x[i_glob] : 0.f;
+    const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
+    const long long dcol0 = i_glob + p.diag_offset;
+    float m_run = -1e30f, l_run = 0.f;   // base-2 units: S log2(e)
+
+    float ry_n = 0.f;
+    if (te < STEP_J) {
+      const long long j = (long long)t_begin * STEP_J + te;
+      ry_n = (j < p.n_cols) ? p.rinv_y[j] : -1.f;
+    }
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tl = t - t_begin;
+      const int sb = tl & 1;
+      float* const cv = colv + (tl & 1) * 512;
+      if (te < STEP_J) {
+        cv[te] = ry_n < 0.f ? 0.f : ry_n * k2;
+        cv[256 + te] = ry_n < 0.f ? -INFINITY : 0.f;   // columns past the end never enter a maximum or a sum
+        const long long jn = (long long)(t + 1) * STEP_J + te;
+        ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
+      }
+      named_bar_sync(1, EPI_THREADS);
+      ptx::mbar_wait(bar(B_SFULL + sb), (tl >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_lane + sb * SBUF_COLS + col0 + 32 * c, r);
+        ptx::tmem_ld_wait();
+        if (c == NCH - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(sempty_leader + 8u * sb);
+        }
+        const float* const cjp = cv + jl0 + 32 * c;
+        const long long dl = dcol0 - ((long long)t * STEP_J + jl0 + 32 * c);
+        if (p.diag != nullptr && row_ok && dl >= 0 && dl < 32) {
+#pragma unroll
+          for (int x = 0; x < 32; ++x)
+            if (dl == x) p.diag[i_glob] = __uint_as_float(r[x]) * rx * cjp[x] * LN2;
+        }
+        float y[32];
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int x4 = 0; x4 < 8; ++x4) {
+          const float4 cj4 = *reinterpret_cast<const float4*>(cjp + 4 * x4);
+          const float4 c04 = *reinterpret_cast<const float4*>(cjp + 256 + 4 * x4);
+          const float cjv[4] = {cj4.x, cj4.y, cj4.z, cj4.w};
+          const float c0v[4] = {c04.x, c04.y, c04.z, c04.w};
+#pragma unroll
+          for (int xx = 0; xx < 4; ++xx) {
+            y[4 * x4 + xx] = fmaf(__uint_as_float(r[4 * x4 + xx]) * rx, cjv[xx], c0v[xx]);
+            tmax = fmaxf(tmax, y[4 * x4 + xx]);
+          }
+        }
+        const float nm = fmaxf(m_run, tmax);
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int x = 0; x < 32; ++x) r4[x & 3] += ex2(y[x] - nm);
+        l_run = fmaf(l_run, ex2(m_run - nm), (r4[0] + r4[1]) + (r4[2] + r4[3]));
+        m_run = nm;
+      }
+    }
+    // combine the warps that share a row (column groups; for the 2x2 layout both column halves) in fixed order
+    float* const rowred_m = colred;          // [16][32]   (the column-partial staging is unused in this mode)
+    rowred_m[e * 32 + lane] = m_run;
+    rowred[e * 32 + lane] = l_run;
+    named_bar_sync(1, EPI_THREADS);
+    if (te < ROWS) {
+      const int rq = te >> 5, rl = te & 31;
+      float mm = -1e30f;
+#pragma unroll
+      for (int w = 0; w < FWD_EPI_WARPS; ++w) {
+        const bool mine = ROWS == 128 ? ((w & 3) == rq) : ((w & 1) == rq);
+        if (mine) mm = fmaxf(mm, rowred_m[w * 32 + rl]);
+      }
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < FWD_EPI_WARPS; ++w) {
+        const bool mine = ROWS == 128 ? ((w & 3) == rq) : ((w & 1) == rq);
+        if (mine) tot += rowred[w * 32 + rl] * ex2(rowred_m[w * 32 + rl] - mm);
+      }
+      if ((long long)i0 + te < p.n_rows) {
+        p.row_part_m[(long long)split * p.n_rows + i0 + te] = mm * LN2;
+        p.row_part[(long long)split * p.n_rows + i0 + te] = tot;
       }
     }
   } else if (warp >= 4) {

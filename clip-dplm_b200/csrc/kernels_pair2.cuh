@@ -95,7 +95,13 @@ struct Params {
 };
 
 __host__ __device__ constexpr int producer_smem(int nkc, int stages) { return nkc * X_CHUNK + G_BYTES + stages * STAGE_BYTES + SMALL; }
-__host__ __device__ constexpr int consumer_smem(int stages) { return stages * C_STAGE + SMALL; }
+constexpr int FLUSH_BYTES = EPI_WARPS * 4096;   // consumer epilogue: one [32 rows][32 f32] transposing scratch per warp
+__host__ __device__ constexpr int consumer_smem(int stages) { return stages * C_STAGE + FLUSH_BYTES + SMALL; }
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void publish(uint32_t* flag) {   // TMA stores of this thread (already waited for) -> visible, then count
   ptx::fence_proxy_async_all();
@@ -591,6 +597,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
       const int hcol = (warp - 4) >> 2;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       const uint32_t accempty_leader = ptx::mapa(bar(B_ACCEMPTY), 0);
+      const uint32_t scratch = ring_c + p.stages_c * C_STAGE + (warp - 4) * 4096;
       uint32_t nt = 0;
       for (int r = 0; r < p.n_rounds; ++r) {
         const int nsub = round_subs(p, r);
@@ -610,33 +617,44 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
               const int wq = min(256, p.d - 256 * hh);
               const int wh = wq >> 1;                  // columns per epilogue-warp half
               const long long col0 = 256 * hh + hcol * wh;
-              float* const lrow = p.dy + j * p.d + col0;
-              // the segment's last contribution of a row-sharded step goes to the owner's slot in peer memory
-              float* const orow = (sub.last && p.world > 0)
-                                      ? p.dy_peer[sub.seg] + (j - (long long)sub.seg * p.seg_steps * STEP_J) * p.d + col0
-                                      : lrow;
+              // Rows leave the warp as full 128-byte lines: the accumulator arrives with thread = row (32 consecutive
+              // floats each), is staged through a swizzled [32][32] scratch and written with 8 lanes per row -- 16-byte
+              // stores scattered over 32 rows reached 75 GB/s into NVLink peer memory, whole lines ride at link rate.
+              // The segment's last contribution of a row-sharded step goes to the owner's slot in peer memory.
+              const long long j0 = j - lane;           // first row of this warp
+              const bool remote = sub.last && p.world > 0;
+              float* const obase = remote ? p.dy_peer[sub.seg] + (j0 - (long long)sub.seg * p.seg_steps * STEP_J) * p.d + col0
+                                          : p.dy + j0 * p.d + col0;
+              const float* const lbase = p.dy + j0 * p.d + col0;
+              const int rsub = lane >> 3, ch = lane & 7;
               for (int c = 0; c < (wh >> 5); ++c) {
                 uint32_t rr[32];
                 ptx::tmem_ld_32x32b_x32(t_lane + buf * 256 + hcol * wh + 32 * c, rr);
                 ptx::tmem_ld_wait();
-                float4* const dst = reinterpret_cast<float4*>(orow + 32 * c);
-                if (sub.first) {
 #pragma unroll
-                  for (int x4 = 0; x4 < 8; ++x4)
-                    dst[x4] = make_float4(__uint_as_float(rr[4 * x4]) * osc, __uint_as_float(rr[4 * x4 + 1]) * osc,
-                                          __uint_as_float(rr[4 * x4 + 2]) * osc, __uint_as_float(rr[4 * x4 + 3]) * osc);
-                } else {
-                  const float4* const src = reinterpret_cast<const float4*>(lrow + 32 * c);
+                for (int k4 = 0; k4 < 8; ++k4)
+                  pair::st_shared_v4(scratch + lane * 128 + ((static_cast<uint32_t>(k4) ^ (lane & 7)) << 4),
+                                     __float_as_uint(__uint_as_float(rr[4 * k4]) * osc), __float_as_uint(__uint_as_float(rr[4 * k4 + 1]) * osc),
+                                     __float_as_uint(__uint_as_float(rr[4 * k4 + 2]) * osc), __float_as_uint(__uint_as_float(rr[4 * k4 + 3]) * osc));
+                __syncwarp();
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int row = 4 * i + rsub;
+                  v[i] = ld_shared_v4(scratch + row * 128 + ((static_cast<uint32_t>(ch) ^ (row & 7)) << 4));
+                }
+                if (!sub.first) {
                   float4 old[8];
 #pragma unroll
-                  for (int x4 = 0; x4 < 8; ++x4) old[x4] = src[x4];
+                  for (int i = 0; i < 8; ++i)
+                    old[i] = *reinterpret_cast<const float4*>(lbase + (long long)(4 * i + rsub) * p.d + 32 * c + 4 * ch);
 #pragma unroll
-                  for (int x4 = 0; x4 < 8; ++x4)
-                    dst[x4] = make_float4(fmaf(__uint_as_float(rr[4 * x4]), osc, old[x4].x),
-                                          fmaf(__uint_as_float(rr[4 * x4 + 1]), osc, old[x4].y),
-                                          fmaf(__uint_as_float(rr[4 * x4 + 2]), osc, old[x4].z),
-                                          fmaf(__uint_as_float(rr[4 * x4 + 3]), osc, old[x4].w));
+                  for (int i = 0; i < 8; ++i) { v[i].x += old[i].x; v[i].y += old[i].y; v[i].z += old[i].z; v[i].w += old[i].w; }
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  *reinterpret_cast<float4*>(obase + (long long)(4 * i + rsub) * p.d + 32 * c + 4 * ch) = v[i];
+                __syncwarp();
               }
               ptx::tc_fence_before();
               __syncwarp();

@@ -72,9 +72,9 @@ class CudaEngine:
         return bool(self.lib.clipnce_uses_tensor_cores(_DT[dtype], d, float(scale), flags))
 
     def fixed_shift(self, dtype, d, scale, flags=0):
-        """True when forward() returns col_m == row_m == scale (the tensor-core kernels' fixed shift): partial sums of
+        """True when forward() returns col_m == row_m == scale (kernel family 1, the fixed shift): partial sums of
         different ranks then add up directly, no max exchange needed."""
-        return self.uses_tensor_cores(dtype, d, scale, flags)
+        return self.lib.clipnce_uses_tensor_cores(_DT[dtype], d, float(scale), flags) == 1
 
     def needs_transposed(self, dtype, d, scale, flags=0):
         return bool(self.lib.clipnce_needs_transposed(_DT[dtype], d, float(scale), flags))

@@ -156,7 +156,8 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
     symmetric     (CE(S) + CE(S^T)) / 2 (rna_clip_codes.ipynb:1953) or CE(S) only (run1/full.py:133).
     extra_cols    [M,d] additional negative columns (hard-negative cache old/clip_opt.py:118-121, memory
                   queue tong/utils/losses.py:10-11), used as stored, no gradient.  ``extra_normalized=False``
-                  (rows of arbitrary norm) routes to the exact kernels.
+                  (rows of arbitrary norm: logits no longer bounded by s) selects the kernels with true
+                  running maxima.
     group         torch.distributed process group: rows are this rank's shard of a global batch; negatives
                   are global, gradients are exact (both sides complete on their owner), the returned loss is the global mean.
     ddp           with ``group``: the model producing ``a``/``b`` is wrapped in DistributedDataParallel (how the reference
@@ -177,7 +178,7 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
         compute_dtype = torch.bfloat16 if low else torch.float32
     flags = 0
     if extra_cols is not None and not extra_normalized:
-        flags |= _step.FLAG_FORCE_EXACT
+        flags |= _step.FLAG_UNBOUNDED
     loss, row_lse, col_lse, diag = _FusedClipLoss.apply(a, b, logit_scale, extra_cols, symmetric, scale_is_log,
                                                         clamp_max, group, compute_dtype, flags, engine, bool(return_stats),
                                                         torch.is_grad_enabled(), bool(ddp))

@@ -26,6 +26,7 @@ import torch.distributed as dist
 from . import exchange as _exchange
 
 FLAG_FORCE_EXACT = 1
+FLAG_UNBOUNDED = 2    # extra columns of arbitrary norm: |S| <= s does not hold (tensor-core kernels with true maxima)
 
 
 @dataclass

@@ -37,6 +37,8 @@ extern "C" {
 
 /* flags */
 #define CLIPNCE_FLAG_FORCE_EXACT 1   /* use the CUDA-core exact (online-max) kernels even for bf16 */
+#define CLIPNCE_FLAG_UNBOUNDED   2   /* |S_ij| <= s does not hold (un-normalised extra columns, tong/utils/losses.py:10-14):
+                                        tensor-core kernels with true running maxima instead of the fixed shift */
 
 /* error codes */
 #define CLIPNCE_OK            0
@@ -48,8 +50,11 @@ extern "C" {
 int         clipnce_version(void);
 const char* clipnce_last_error(void);
 
-/* 1 if (dtype, d, scale, flags) is served by the tcgen05 tensor-core kernels, 0 if by the exact
- * CUDA-core kernels (dtype F32, d % 8 != 0, d > 768, or 2*scale > 86 where exp(S - s) leaves fp32). */
+/* Kernel family serving (dtype, d, scale, flags):
+ *   0  exact CUDA-core kernels (dtype F32, d % 8 != 0, d > 768, CLIPNCE_FLAG_FORCE_EXACT);
+ *   1  tcgen05 tensor-core kernels with the fixed shift exp(S - s)   (2 * scale <= 80 and |S| <= s);
+ *   2  tcgen05 kernels with true running maxima (online soft-max forward, two-exponential backward): larger scales --
+ *      exp().clamp(max=100), old/clip_opt.py:100 -- and CLIPNCE_FLAG_UNBOUNDED; d % 128 == 0. */
 int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags);
 
 /* 1 if clipnce_backward needs the transposed copy y_t for these arguments.  The CTA-pair kernels (d % 128 == 0,

@@ -99,7 +99,9 @@ def test_host_only_entry_points():
     assert lib.clipnce_workspace_bytes(0, 10, 512, _lib.BF16, 0, ctypes.byref(nbytes)) == -1
     assert b"bad shape" in lib.clipnce_last_error()
     assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 14.3, 0) == 1
-    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 100.0, 0) == 0      # exp(S - s) would leave fp32
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 100.0, 0) == 2      # exp(S - s) would leave fp32: true running maxima
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 14.3, _lib.FLAG_UNBOUNDED) == 2
+    assert lib.clipnce_uses_tensor_cores(_lib.BF16, 192, 100.0, 0) == 0      # family 2 lives in the CTA-pair kernels (d % 128)
     assert lib.clipnce_uses_tensor_cores(_lib.F32, 512, 14.3, 0) == 0        # check mode
     assert lib.clipnce_uses_tensor_cores(_lib.BF16, 516, 14.3, 0) == 0       # d % 8
     assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 14.3, _lib.FLAG_FORCE_EXACT) == 0

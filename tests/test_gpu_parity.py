@@ -467,3 +467,33 @@ def test_two_sided_backward(monkeypatch, n, d, forced_p, seg):
     # rerun: bit-identical (fixed-order accumulation, no atomics on data)
     _, da3, db3, _ = run_fused(a, b, O.LOGIT_SCALE_INIT, torch.bfloat16)
     assert torch.equal(da2, da3) and torch.equal(db2, db3)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel family 2: tensor cores with true running maxima (s up to the clamp at 100, unbounded logits)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m_extra,d,s,symmetric,normalized", [(1500, 0, 256, 100.0, True, True), (1024, 0, 768, 60.0, True, True),
+                                                                (777, 300, 128, 100.0, True, True), (900, 500, 512, 10.0, False, False),
+                                                                (2048, 0, 512, 100.0, False, True)])
+def test_large_scale_and_unbounded_logits_on_tensor_cores(eng, n, m_extra, d, s, symmetric, normalized):
+    """old/clip_opt.py:100 / run1/full.py:76 clamp the logit scale at 100, tong/utils/losses.py:10-14 appends queue rows of
+    arbitrary norm: both leave the fixed shift's range and must still run on the tcgen05 kernels (family 2: online
+    soft-max forward -- two launches, rows and columns -- and the two-exponential backward), against the float64 oracle."""
+    from clip_dplm_b200 import _lib
+    flags = 0 if normalized else _lib.FLAG_UNBOUNDED
+    assert eng.lib.clipnce_uses_tensor_cores(_lib.BF16, d, float(s), flags) == 2
+    a, b = O.make_inputs(n, d, seed=13, n_cols=n + m_extra, mix=0.12 if s > 50 else 0.5)
+    extra = None
+    if m_extra:
+        extra = b[n:].double()
+        extra = torch.nn.functional.normalize(extra, dim=-1) if normalized else extra * 0.2   # norms ~4.5: logits up to ~45
+        extra = extra.to(torch.bfloat16).double()
+        b = b[:n]
+    kw = dict(symmetric=symmetric, scale_is_log=False)
+    okw = dict(kw, **({"extra_cols": extra} if extra is not None else {}))
+    ref = O.ref_step(a.double(), b.double(), s, **okw)
+    fkw = dict(kw, **({"extra_cols": extra.float(), "extra_normalized": normalized} if extra is not None else {}))
+    loss, da, db, dt = run_fused(a, b, s, torch.bfloat16, **fkw)
+    assert abs(loss - float(ref["loss"])) <= LOSS_RTOL_BF16 * abs(float(ref["loss"]))
+    assert rel(da, ref["d_a"]) <= GRAD_RTOL_BF16 and rel(db, ref["d_b"]) <= GRAD_RTOL_BF16
+    assert abs(dt - float(ref["d_logit_scale"])) <= GRAD_RTOL_BF16 * abs(float(ref["d_logit_scale"])) + 1e-7
