@@ -93,6 +93,11 @@ class CollectiveExchange:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
+    generation = 0
+
+    def owned_by(self, generation) -> bool:
+        return True
+
     def release(self):
         self._rows = None
 
@@ -151,6 +156,7 @@ class PeerExchange:
         # must win the SM slots that free up after the sweep's first wave instead of queueing behind its last one
         self.side = torch.cuda.Stream(device=device, priority=-1)
         self._side_busy = False
+        self.generation = 0     # bumped at every lease: a step remembers the generation it was given
 
         def view(o, count, dt):
             e = 2 if dt == torch.bfloat16 else 4
@@ -214,6 +220,10 @@ class PeerExchange:
     def barrier(self, phase):
         self.engine.link_barrier(self.peers, self.world, self.rank, phase)
 
+    def owned_by(self, generation) -> bool:
+        """False once the buffers were reclaimed for a later step (see _Pool.lease)."""
+        return self.generation == generation
+
     def check(self):
         """Host check of the status word (synchronises): raises if a barrier timed out.  A timeout also traps on the
         device (kernels_link.cuh), so in practice the synchronisation inside this read raises first."""
@@ -231,6 +241,7 @@ class _Pool:
     a forward whose autograd graph is dropped without a backward keeps its lease until `reset()`."""
 
     free = {}
+    live = {}          # key -> exchanges out on lease, oldest first
     n_alloc = {}
     max_per_key = 8
     mode = {}          # group name -> "link" | "nccl"
@@ -262,8 +273,19 @@ class _Pool:
     def lease(cls, engine, group, n_local, d, n_cols, compute_dtype, device):
         key = (group.group_name, n_local, d, n_cols, compute_dtype, device)
         fl = cls.free.setdefault(key, [])
+        lv = cls.live.setdefault(key, [])
+        if not fl and cls.n_alloc.get(key, 0) >= cls.max_per_key and lv:
+            # Every buffer is out on lease: forwards whose backward never ran (an evaluation loop under enable_grad).
+            # Reclaim the OLDEST lease -- the same one on every rank, since all ranks run the same sequence of steps; a
+            # backward that still turns up for it finds a newer generation and raises (PeerExchange.owned_by).
+            x = lv.pop(0)
+            x.generation += 1
+            fl.append(x)
         if fl:
-            return fl.pop()
+            x = fl.pop()
+            x.generation += 1
+            lv.append(x)
+            return x
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("clip_dplm_b200: run one eager step of this shape before capturing a CUDA graph (the peer "
                                "exchange buffers are allocated by a host-side rendezvous)")
@@ -284,11 +306,16 @@ class _Pool:
             cls.mode[group.group_name] = "nccl"
             return None
         cls.n_alloc[key] = cls.n_alloc.get(key, 0) + 1
+        x.generation += 1
+        lv.append(x)
         return x
 
     @classmethod
     def give_back(cls, x):
-        cls.free.setdefault(x.pool_key, []).append(x)
+        lv = cls.live.get(x.pool_key, [])
+        if x in lv:
+            lv.remove(x)
+            cls.free.setdefault(x.pool_key, []).append(x)
 
 
 def reset():
@@ -296,6 +323,7 @@ def reset():
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     _Pool.free.clear()
+    _Pool.live.clear()
     _Pool.n_alloc.clear()
     _Pool.mode.clear()
 

@@ -119,7 +119,7 @@ class _FusedClipLoss(torch.autograd.Function):
         st, engine = ctx.st, ctx.engine
         s, clamped, scale_is_log, s_dev, raw_dev, clamp_max = ctx.scale_info
         if g_loss is None:   # the loss did not take part in the differentiated graph
-            if st.xchg is not None:   # still close the step on every rank and hand the exchange buffers back
+            if st.xchg is not None and st.xchg.owned_by(st.xchg_generation):   # close the step on every rank, hand the buffers back
                 st.xchg.sum_scalars(torch.zeros(1, dtype=torch.float32, device=st.diag.device), _step._exchange.PHASE_CLOSE)
                 st.xchg.release()
                 st.xchg = None

@@ -62,6 +62,7 @@ class StepState:
     compute_dtype: torch.dtype
     xchg: object = None             # the exchange of this step (exchange.py); None on one GPU
     both_sharded: bool = False      # the backward will run the row-sharded two-sided kernel (no gathered A rows needed)
+    xchg_generation: int = 0        # lease generation of the exchange buffers (exchange._Pool reclaims abandoned leases)
 
 
 def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, group=None,
@@ -138,7 +139,7 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
             xchg = None
     st = StepState(a, b, a_c, b_c, y, y_t, xa, None, rinv_a, rinv_b, rinv_y, rinv_xa, row_m, row_l, row_m_all, row_l_all,
                    col_m, col_l, diag, scale, scale_dev, symmetric, n_local, n_global, diag_offset, flags, group, want_t,
-                   compute_dtype, xchg, both_sharded)
+                   compute_dtype, xchg, both_sharded, xchg.generation if xchg is not None else 0)
     return loss, st
 
 
@@ -149,6 +150,9 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
     n_glob, n, off = st.n_global, st.n_local, st.diag_offset
     if st.xa is None:
         raise RuntimeError("clip_dplm_b200: this step was run without need_grad")
+    if st.xchg is not None and not st.xchg.owned_by(st.xchg_generation):
+        raise RuntimeError("clip_dplm_b200: the exchange buffers of this forward were reclaimed by later steps (more than "
+                           f"{_exchange._Pool.max_per_key} row-sharded forwards of one shape were live without a backward)")
     coef = 1.0 / ((2.0 if st.symmetric else 1.0) * n_glob)
     if st.row_l_all is st.row_l:
         row_w = row_w_all = engine.softmax_weights(st.row_l, coef)

@@ -10,7 +10,8 @@ What it does
        - old/clip_opt.py       optimized_clip_loss                               (:130-151)
        - tong/utils/losses.py  contrastive_loss                                  (:4-19)
        - current/rna_clip_codes.ipynb cells 24+28  RNARBPCLIPModel               (raw :1925-1954)
-       - current/tf_clip_codes (1).ipynb cell 41   ContrastiveModel loss lines   (raw :13146-13165)
+     (current/tf_clip_codes (1).ipynb cell 41, raw :13146-13165, repeats the notebook lines above for three pairs with one
+      shared logit scale; it is NOT loaded -- its loss is three calls of the pinned pair form)
   2. asserts oracle/ref_step.py reproduces each of them EXACTLY (torch.equal) on seeded inputs,
   3. stores inputs (bf16-rounded, as uint16 bit patterns) + reference outputs as small fixtures.
 
