@@ -14,6 +14,7 @@
 
 #include "../../include/clipnce.h"
 #include "kernels_aux.cuh"
+#include "kernels_head.cuh"
 #include "kernels_link.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_pair2.cuh"
@@ -1050,6 +1051,58 @@ int clipnce_loss(const float* row_m, const float* row_l, const float* col_m, con
   const double inv = 1.0 / ((symmetric ? 2.0 : 1.0) * (double)n_global);
   aux::loss_reduce<<<1, 1024, 0, as_stream(stream)>>>(row_m, row_l, col_m, col_l, diag, n_rows, diag_offset, inv,
                                                        symmetric, loss);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- projection-head tail (kernels_head.cuh) -----------------------------------------------------------------------------
+int clipnce_head_tail(const void* h, const void* w, const float* bias, const float* gamma, const float* beta, int64_t n,
+                      int64_t k, int64_t p, float ln_eps, void* e, void* zhat, float* rstd, float* rinv, void* stream) {
+  if (!h || !w || !gamma || !beta || !e || !rinv) return fail(CLIPNCE_EINVAL, "head_tail: null pointer");
+  if (n < 1 || n >= (1ll << 31) || k < 64 || k % 64 != 0 || k > (1 << 16) || p < 128 || p > 512 || p % 128 != 0)
+    return fail(CLIPNCE_EUNSUPPORTED, "head_tail: served for hidden %% 64 == 0 and output width in {128, 256, 384, 512} "
+                                      "(got hidden %lld, width %lld)", (long long)k, (long long)p);
+  if (!aligned16(h) || !aligned16(w) || !aligned16(e) || (zhat && !aligned16(zhat)))
+    return fail(CLIPNCE_EINVAL, "head_tail: operands must be 16-byte aligned");
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  head::Params hp;
+  memset(&hp, 0, sizeof hp);
+  hp.n = (int)n; hp.k = (int)k; hp.p = (int)p; hp.nkb = (int)(k / 64);
+  int stages = (pair::SMEM_LIMIT - head::SMALL) / head::stage_bytes((int)p);
+  if (stages > head::MAX_STAGES) stages = head::MAX_STAGES;
+  if (stages < 2) return fail(CLIPNCE_EUNSUPPORTED, "head_tail: no room for a TMA ring");
+  hp.stages = stages;
+  hp.ln_eps = ln_eps; hp.norm_eps = aux::kNormEps;
+  hp.bias = bias; hp.gamma = gamma; hp.beta = beta;
+  hp.e = reinterpret_cast<__nv_bfloat16*>(e); hp.zhat = reinterpret_cast<__nv_bfloat16*>(zhat); hp.rstd = rstd; hp.rinv = rinv;
+  CUtensorMap th, tw;
+  if ((rc = make_tmap(&th, h, k, n, k, head::ROWS))) return rc;
+  if ((rc = make_tmap(&tw, w, k, p, k, 128))) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_attr_done[13]) {
+      CUDA_TRY(cudaFuncSetAttribute(head::linear_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
+      g_attr_done[13] = true;
+    }
+  }
+  head::linear_ln_kernel<<<(unsigned)ceil_div(n, head::ROWS), head::THREADS, head::smem_bytes((int)p, stages), as_stream(stream)>>>(th, tw, hp);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_head_tail_backward(const void* de, int de_dtype, const void* zhat, const float* rstd, const float* gamma, int64_t n,
+                               int64_t p, void* dz, void* stream) {
+  if (!de || !zhat || !rstd || !gamma || !dz || n < 1 || p < 1) return fail(CLIPNCE_EINVAL, "head_tail_backward: bad argument");
+  if (de_dtype != CLIPNCE_BF16 && de_dtype != CLIPNCE_F32) return fail(CLIPNCE_EINVAL, "head_tail_backward: bad dtype");
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div(n, wpb)), block(32 * wpb);
+  if (de_dtype == CLIPNCE_BF16)
+    head::ln_backward_rows<<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)de, (const __nv_bfloat16*)zhat, rstd, gamma, n,
+                                                                  (int)p, (__nv_bfloat16*)dz);
+  else
+    head::ln_backward_rows<<<grid, block, 0, as_stream(stream)>>>((const float*)de, (const __nv_bfloat16*)zhat, rstd, gamma, n, (int)p,
+                                                                  (__nv_bfloat16*)dz);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

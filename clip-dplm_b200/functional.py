@@ -70,7 +70,7 @@ class _ScaleHint:
 class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, logit_scale, extra, symmetric, scale_is_log, clamp_max, group, compute_dtype, flags, engine,
-                want_stats=True, grad_mode=True, ddp=False):
+                want_stats=True, grad_mode=True, ddp=False, rinv_a=None, rinv_b=None):
         # grad_mode: autograd's mode at the call (always off inside forward()).  Without a backward to come the step
         # neither gathers the rows side B would stream nor keeps its exchange buffers (step.py)
         need_grad = grad_mode and (a.requires_grad or b.requires_grad or
@@ -92,7 +92,7 @@ class _FusedClipLoss(torch.autograd.Function):
         loss, st = _step.contrastive_forward(engine, a.detach().contiguous(), b.detach().contiguous(), scale_arg,
                                              symmetric=symmetric, extra=extra, group=group,
                                              compute_dtype=compute_dtype, flags=flags, need_grad=need_grad,
-                                             scale_dev=s_dev)
+                                             scale_dev=s_dev, rinv_a=rinv_a, rinv_b=rinv_b)
         ctx.st, ctx.engine = st, engine
         # DistributedDataParallel AVERAGES parameter gradients over the ranks.  dA / dB are the exact gradient of the GLOBAL
         # mean loss with respect to the LOCAL rows (their sum over ranks is the parameter gradient), d logit_scale is the
@@ -124,7 +124,7 @@ class _FusedClipLoss(torch.autograd.Function):
                 st.xchg.release()
                 st.xchg = None
             ctx.st = None
-            return (None,) * 14
+            return (None,) * 16
         g = g_loss.reshape(1).to(torch.float32).contiguous()
         g_rows = g * ctx.row_grad_mult if ctx.row_grad_mult != 1.0 else g
         da, db, ds = _step.contrastive_backward(engine, st, grad_scale=g_rows)
@@ -142,13 +142,13 @@ class _FusedClipLoss(torch.autograd.Function):
                 coef = 1.0 if scale_is_log else 1.0 / s
                 d_ls = (ds * g * coef).reshape(()).to(device=ctx.ls_meta[1], dtype=ctx.ls_meta[0])
         ctx.st = None
-        return da, db, d_ls, None, None, None, None, None, None, None, None, None, None, None
+        return da, db, d_ls, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: bool = True,
                     clamp_max: Optional[float] = None, extra_cols=None, extra_normalized: bool = True,
                     group=None, compute_dtype: Optional[torch.dtype] = None, return_stats: bool = False,
-                    ddp: bool = False, engine=None):
+                    ddp: bool = False, rinv_a=None, rinv_b=None, engine=None):
     """Fused CLIP / InfoNCE loss of two [N,d] embedding batches (un-normalised projection-head outputs).
 
     logit_scale   0-d tensor (learnable parameter) or float; ``s = exp(logit_scale)`` (scale_is_log) or
@@ -165,6 +165,8 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
                   by the world size, so that after DDP's mean every parameter -- encoders, heads and logit_scale alike --
                   holds the gradient of the global mean loss.  Default (False): dA/dB are the plain partial derivatives
                   of the global loss with respect to the local rows (sum them over ranks yourself).
+    rinv_a/rinv_b [N] f32 1/max(|row|, 1e-12) of ``a`` / ``b`` when the producer of the rows already has them (the fused
+                  projection-head tail, ``heads.fused_linear_layernorm``): the row-norm pass is skipped.
     compute_dtype torch.bfloat16 (tcgen05 tensor-core kernels) or torch.float32 (exact check mode).
                   Default: bf16 for bf16/fp16 inputs or under autocast, else fp32 (the reference's numerics).
     """
@@ -181,7 +183,9 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
         flags |= _step.FLAG_UNBOUNDED
     loss, row_lse, col_lse, diag = _FusedClipLoss.apply(a, b, logit_scale, extra_cols, symmetric, scale_is_log,
                                                         clamp_max, group, compute_dtype, flags, engine, bool(return_stats),
-                                                        torch.is_grad_enabled(), bool(ddp))
+                                                        torch.is_grad_enabled(), bool(ddp),
+                                                        rinv_a.detach() if rinv_a is not None else None,
+                                                        rinv_b.detach() if rinv_b is not None else None)
     if return_stats:
         return loss, {"row_lse": row_lse, "col_lse": col_lse, "diag": diag}
     return loss

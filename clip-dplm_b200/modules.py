@@ -59,8 +59,53 @@ def fused_normalize(x: torch.Tensor) -> torch.Tensor:
     return _Normalize.apply(x)
 
 
+class LazyOutputs(dict):
+    """The reference's output dict (old/clip.py:69-74) whose expensive entries are computed on first access; membership
+    tests, ``keys()`` / ``items()`` / ``values()`` / ``get`` see every entry (listing the values materialises them)."""
+
+    def __init__(self, eager=()):
+        super().__init__(eager)
+        self._makers = {}
+
+    def lazy(self, key, maker):
+        self._makers[key] = maker
+
+    def __missing__(self, key):
+        maker = self._makers.pop(key)        # KeyError for unknown keys, like a dict
+        value = maker()
+        self[key] = value
+        return value
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._makers
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def _all(self):
+        for k in list(self._makers):
+            self[k]
+        return self
+
+    def keys(self):
+        return list(dict.keys(self)) + list(self._makers)
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return dict.__len__(self) + len(self._makers)
+
+
 class LazyLogits:
-    """Stands in for ``matmul(a, b.t()) * logit_scale`` (old/clip.py:67).  Nothing is computed until used."""
+    """Stands in for ``matmul(a, b.t()) * logit_scale`` (old/clip.py:67).  Nothing is computed until used; ``materialize``
+    (any torch function applied to the stand-in) is a plain dense matmul for inspection and debugging, not a training path."""
 
     def __init__(self, a_hat, b_hat, scale):
         self.a_hat, self.b_hat, self.scale = a_hat, b_hat, scale
@@ -124,13 +169,34 @@ def _mlp_head(dims, dropout):
 
 
 class ProjectionHead(nn.Module):
-    """Linear-LN-GELU-Dropout-Linear-LN  (old/clip.py:20-36)."""
+    """Linear-LN-GELU-Dropout-Linear-LN  (old/clip.py:20-36).
+
+    In bf16 (bf16 activations, or under autocast) on CUDA the last Linear -> LayerNorm pair runs as ONE tcgen05 kernel that
+    also takes the row norms (heads.fused_linear_layernorm): the returned rows carry their 1/norm as ``_clipnce_rinv``,
+    which the fused loss picks up instead of re-reading them.  fp32 models keep the reference's fp32 ops (``fuse_tail``
+    switches the fusion off altogether)."""
+
+    fuse_tail = True
+    # measured on B200 (tools/bench_config2.py, 1280 -> 1024 -> 512 heads, whole step as one CUDA graph): at 4096 rows the
+    # 32-CTA tail kernel loses to cuBLAS + two row kernels (0.61 vs 0.49 ms per step), at 65536 rows it wins (18.96 vs 19.56)
+    fuse_tail_min_rows = 8192
 
     def __init__(self, input_dim, output_dim, hidden_dim=None, dropout=0.1):
         super().__init__()
         self.projection = _mlp_head([input_dim, hidden_dim or input_dim, output_dim], dropout)
 
     def forward(self, x):
+        from .heads import fused_linear_layernorm, tail_is_served
+        lin, ln = self.projection[-2], self.projection[-1]
+        if (self.fuse_tail and x.is_cuda and x.dim() == 2 and x.shape[0] >= self.fuse_tail_min_rows
+                and tail_is_served(lin.in_features, lin.out_features)
+                and (x.dtype == torch.bfloat16 or torch.is_autocast_enabled())):
+            h = x
+            for m in list(self.projection)[:-2]:
+                h = m(h)
+            e, rinv = fused_linear_layernorm(h, lin, ln)
+            e._clipnce_rinv = rinv
+            return e
         return self.projection(x)
 
 
@@ -168,14 +234,21 @@ class _PairCLIP(nn.Module):
 
     def _tail(self, emb_a, emb_b, extra_cols=None, group=None):
         loss = fused_clip_loss(emb_a, emb_b, self.logit_scale, symmetric=self.symmetric, clamp_max=self.clamp_max,
-                               extra_cols=extra_cols, group=group, ddp=self.ddp_gradients and group is not None)
-        a_hat, b_hat = fused_normalize(emb_a), fused_normalize(emb_b)
-        s = self.logit_scale.detach().exp()
-        if self.clamp_max is not None:
-            s = s.clamp(max=self.clamp_max)
+                               extra_cols=extra_cols, group=group, ddp=self.ddp_gradients and group is not None,
+                               rinv_a=getattr(emb_a, "_clipnce_rinv", None), rinv_b=getattr(emb_b, "_clipnce_rinv", None))
         na, nb = self.names
-        return {f"logits_per_{na}_{nb}": LazyLogits(a_hat.detach(), b_hat.detach(), s), f"{na}_embeds": a_hat,
-                f"{nb}_embeds": b_hat, "loss": loss}
+
+        def scale():
+            s = self.logit_scale.detach().exp()
+            return s.clamp(max=self.clamp_max) if self.clamp_max is not None else s
+
+        # the normalised embeddings and the logits stand-in are only formed if somebody asks for them: a training loop
+        # that reads outputs["loss"] pays for no pass over [N, d] beyond the fused loss itself
+        out = LazyOutputs({"loss": loss})
+        out.lazy(f"{na}_embeds", lambda: fused_normalize(emb_a))
+        out.lazy(f"{nb}_embeds", lambda: fused_normalize(emb_b))
+        out.lazy(f"logits_per_{na}_{nb}", lambda: LazyLogits(out[f"{na}_embeds"].detach(), out[f"{nb}_embeds"].detach(), scale()))
+        return out
 
 
 class RNAProteinCLIPModule(_PairCLIP):
@@ -250,9 +323,8 @@ class OptimizedCLIPModule(_PairCLIP):
         cache = self.protein_embedding_cache[:self.cache_ptr]
         group = dist.group.WORLD if (gather_distributed and dist.is_available() and dist.is_initialized()) else None
         out = self._tail(ea, eb, extra_cols=cache if cache.shape[0] else None, group=group)
-        a_hat = out["diffmap_embeds"]
-        s = self.logit_scale.detach().exp().clamp(max=100.0)
-        out["logits_per_diffmap_cache"] = LazyLogits(a_hat.detach(), cache, s)
+        out.lazy("logits_per_diffmap_cache", lambda: LazyLogits(out["diffmap_embeds"].detach(), cache,
+                                                                 self.logit_scale.detach().exp().clamp(max=100.0)))
         return out
 
 

@@ -66,7 +66,7 @@ class StepState:
 
 
 def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, group=None,
-                        compute_dtype=torch.bfloat16, flags=0, need_grad=True, scale_dev=None):
+                        compute_dtype=torch.bfloat16, flags=0, need_grad=True, scale_dev=None, rinv_a=None, rinv_b=None):
     """Returns (loss [1] f32 -- the GLOBAL mean loss, identical on every rank --, StepState).
 
     ``scale`` is s as a float, or a zero-argument callable returning it: the callable is invoked only after the
@@ -83,7 +83,9 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
 
     xchg = None
     both_sharded = False
-    rinv_a, _ = engine.normalize(a)
+    # rinv_a / rinv_b: 1/norms that came with the rows (the fused projection-head tail, heads.py): nothing to recompute
+    if rinv_a is None:
+        rinv_a, _ = engine.normalize(a)
     a_c, _ = engine.stage(a, compute_dtype)
     if world > 1:
         # the exchange buffers do not depend on the number of extra columns (a hard-negative cache that grows from step
@@ -100,7 +102,8 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
             if not both_sharded:   # side B of the backward streams every rank's A rows; they travel behind the forward sweep
                 xchg.gather_rows_begin(a, a_c, rinv_a, compute_dtype)
     else:
-        rinv_b, _ = engine.normalize(b)
+        if rinv_b is None:
+            rinv_b, _ = engine.normalize(b)
         b_c, _ = engine.stage(b, compute_dtype)
         y, rinv_y = b_c, rinv_b
     if callable(scale):

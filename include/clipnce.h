@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 104
+#define CLIPNCE_VERSION 105
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -259,6 +259,22 @@ int clipnce_topk_workspace_bytes(int64_t n_q, int64_t n_lib, int64_t d, int k, i
 int clipnce_topk(const void* q, const void* lib, const float* rinv_q, const float* rinv_lib,
                  int64_t n_q, int64_t n_lib, int64_t d, int64_t col_offset, int k, int dtype,
                  float* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Projection-head tail fused in front of the loss (the last two layers of the reference's heads + the normalise):
+ *   e = nn.LayerNorm(p)(nn.Linear(k, p)(h))     old/clip.py:26-33, old/clip_opt.py:16-44, rna_clip_codes.ipynb:1901-1909
+ *   rinv = 1 / max(|e|, 1e-12)                  F.normalize, old/clip.py:63-64
+ * One tcgen05 GEMM whose epilogue is the LayerNorm and the row norm (the output row of p <= 512 columns lives in one
+ * CTA's TMEM, so both are thread-local).  h [n,k] bf16, w [p,k] bf16 (nn.Linear's layout), bias/gamma/beta [p] f32
+ * (bias may be NULL); e [n,p] bf16 and rinv [n] feed clipnce_forward / clipnce_backward* directly; zhat [n,p] bf16 and
+ * rstd [n] (both optional) are what clipnce_head_tail_backward needs.  Served for k % 64 == 0, p in {128,256,384,512}.
+ */
+int clipnce_head_tail(const void* h, const void* w, const float* bias, const float* gamma, const float* beta, int64_t n,
+                      int64_t k, int64_t p, float ln_eps, void* e, void* zhat, float* rstd, float* rinv, void* stream);
+/* LayerNorm backward of the tail: dz = rstd (g - mean(g) - z_hat mean(g z_hat)), g = de * gamma; de [n,p] de_dtype,
+ * dz [n,p] bf16 -- the operand of the two GEMMs dW = dz^T h, dh = dz W (plain library GEMMs, left to the caller). */
+int clipnce_head_tail_backward(const void* de, int de_dtype, const void* zhat, const float* rstd, const float* gamma,
+                               int64_t n, int64_t p, void* dz, void* stream);
 
 /*
  * Exchange steps of the row-sharded global batch over NVLink / NVSwitch peer memory.  Replaces the reference's

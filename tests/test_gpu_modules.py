@@ -96,3 +96,67 @@ def test_notebook_model_and_tong_loss():
     assert abs(float(l) - float(ref)) <= 1e-5 * abs(float(ref))
     tri = M.trimodal_contrastive_losses(x, y, torch.randn(33, 40, device="cuda"), torch.tensor(2.0, device="cuda"))
     assert abs(float(tri["loss"]) - float(tri["cell_pert_loss"] + tri["cell_protein_loss"] + tri["pert_protein_loss"])) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ projection-head tail
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,p", [(1000, 1024, 512), (4096, 1280, 512), (300, 256, 128), (513, 640, 384)])
+def test_fused_head_tail_matches_linear_layernorm_normalize(n, k, p):
+    """heads.fused_linear_layernorm (one tcgen05 kernel: Linear -> LayerNorm -> row norm) against the reference's own
+    ops on the same bf16-rounded operands (old/clip.py:26-33 last two layers + F.normalize :63-64), forward and backward."""
+    import torch.nn.functional as F
+    from clip_dplm_b200.heads import fused_linear_layernorm
+    torch.manual_seed(7)
+    lin = torch.nn.Linear(k, p).cuda()
+    ln = torch.nn.LayerNorm(p).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.3, 0.3)
+        lin.weight.copy_(lin.weight.bfloat16().float())
+    h = torch.randn(n, k, device="cuda").bfloat16().requires_grad_(True)
+    e, rinv = fused_linear_layernorm(h, lin, ln)
+    href = h.detach().double().requires_grad_(True)
+    lin64, ln64 = torch.nn.Linear(k, p).cuda().double(), torch.nn.LayerNorm(p).cuda().double()
+    lin64.load_state_dict({kk: v.double() for kk, v in lin.state_dict().items()})
+    ln64.load_state_dict({kk: v.double() for kk, v in ln.state_dict().items()})
+    eref = ln64(lin64(href))
+    assert rel(e, eref) <= 5e-3                                           # bf16 output rounding
+    assert torch.allclose(rinv.double(), 1.0 / e.double().norm(dim=1).clamp_min(1e-12), rtol=1e-5)
+    assert rel(e.double() * rinv.double()[:, None], F.normalize(eref, dim=-1)) <= 5e-3
+    g = torch.randn(n, p, device="cuda")
+    e.backward(g.bfloat16())
+    eref.backward(g.bfloat16().double())
+    assert rel(h.grad, href.grad) <= 2e-2
+    assert rel(lin.weight.grad, lin64.weight.grad) <= 2e-2 and rel(lin.bias.grad, lin64.bias.grad) <= 2e-2
+    assert rel(ln.weight.grad, ln64.weight.grad) <= 2e-2 and rel(ln.bias.grad, ln64.bias.grad) <= 2e-2
+
+
+@pytest.mark.gpu
+def test_module_with_fused_tail_matches_unfused_module():
+    """RNAProteinCLIPModule in bf16: heads with the fused tail (rows + 1/norm handed straight to the loss) against the same
+    module with fuse_tail off -- loss and every parameter gradient; and the lazily formed output entries."""
+    from clip_dplm_b200 import modules as M
+    c = cfg(96, 160, 256)
+    torch.manual_seed(3)
+    m1 = M.RNAProteinCLIPModule(c).cuda().bfloat16()
+    m2 = M.RNAProteinCLIPModule(c).cuda().bfloat16()
+    m2.load_state_dict(m1.state_dict())
+    for mod in m1.modules():
+        if isinstance(mod, M.ProjectionHead):
+            mod.fuse_tail_min_rows = 1          # the default only fuses from 8192 rows on
+    for mod in m2.modules():
+        if isinstance(mod, M.ProjectionHead):
+            mod.fuse_tail = False
+    for mod in list(m1.modules()) + list(m2.modules()):
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    xa, xb = torch.randn(640, 96, device="cuda").bfloat16(), torch.randn(640, 160, device="cuda").bfloat16()
+    o1, o2 = m1(xa, xb), m2(xa, xb)
+    assert set(o1.keys()) == {"loss", "rna_embeds", "protein_embeds", "logits_per_rna_protein"} and "rna_embeds" in o1
+    o1["loss"].backward()
+    o2["loss"].backward()
+    assert abs(float(o1["loss"]) - float(o2["loss"])) <= 2e-2 * abs(float(o2["loss"]))
+    assert rel(o1["rna_embeds"], o2["rna_embeds"]) <= 2e-2
+    for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p2.grad is not None and float(p2.grad.float().norm()) > 0:
+            assert rel(p1.grad, p2.grad) <= 6e-2, n1        # two bf16 models: rounding of every intermediate differs
