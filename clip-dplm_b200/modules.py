@@ -395,12 +395,25 @@ class RNARBPCLIPModel(nn.Module):
 def trimodal_contrastive_losses(cell_embed, pert_embed, protein_embed, logit_scale):
     """Three pairwise symmetric InfoNCE losses sharing one logit_scale, summed
     (tf_clip_codes (1).ipynb:13146-13165).  Inputs are the three projection outputs (un-normalised)."""
-    cp = fused_clip_loss(cell_embed, pert_embed, logit_scale)
-    cq = fused_clip_loss(cell_embed, protein_embed, logit_scale)
-    pq = fused_clip_loss(pert_embed, protein_embed, logit_scale)
-    return {"cell_embed": fused_normalize(cell_embed), "pert_embed": fused_normalize(pert_embed),
-            "protein_embed": fused_normalize(protein_embed), "loss": cp + cq + pq, "cell_pert_loss": cp,
-            "cell_protein_loss": cq, "pert_protein_loss": pq}
+    # every embedding is an operand of two pairs: its row norms are taken ONCE (or arrive with it from the fused head
+    # tail) and handed to both pair steps; the normalised copies of the reference's output dict are formed on demand
+    embs = (cell_embed, pert_embed, protein_embed)
+    if all(e.is_cuda for e in embs):
+        eng = default_engine()
+        rinv = [getattr(e, "_clipnce_rinv", None) for e in embs]
+        rinv = [r if r is not None else eng.normalize(e.detach().contiguous() if e.dtype != torch.float16
+                                                      else e.detach().to(torch.bfloat16).contiguous())[0]
+                for r, e in zip(rinv, embs)]
+    else:
+        rinv = [None, None, None]
+    cp = fused_clip_loss(cell_embed, pert_embed, logit_scale, rinv_a=rinv[0], rinv_b=rinv[1])
+    cq = fused_clip_loss(cell_embed, protein_embed, logit_scale, rinv_a=rinv[0], rinv_b=rinv[2])
+    pq = fused_clip_loss(pert_embed, protein_embed, logit_scale, rinv_a=rinv[1], rinv_b=rinv[2])
+    out = LazyOutputs({"loss": cp + cq + pq, "cell_pert_loss": cp, "cell_protein_loss": cq, "pert_protein_loss": pq})
+    out.lazy("cell_embed", lambda: fused_normalize(cell_embed))
+    out.lazy("pert_embed", lambda: fused_normalize(pert_embed))
+    out.lazy("protein_embed", lambda: fused_normalize(protein_embed))
+    return out
 
 
 def contrastive_loss(x, y, temperature=0.1, queue=None):
