@@ -67,6 +67,39 @@ class _ScaleHint:
         return h.value
 
 
+FAMILY_SWITCH = 40.0      # include/clipnce.h: the fixed shift serves 2 s <= 80
+
+
+def _agree_near_threshold(hint, group, device):
+    """Every rank picks kernels -- and with them the exchange steps it issues -- from ITS copy of s, read at slightly
+    different moments.  Far from the family switch all copies select the same kernels; within 12 % of it the ranks agree
+    on the largest copy (one small blocking all-reduce per step, only while the scale crosses the switch)."""
+    if group is None or abs(hint / FAMILY_SWITCH - 1.0) > 0.12 or torch.cuda.is_current_stream_capturing():
+        return hint
+    import torch.distributed as dist
+    t = torch.tensor([hint], dtype=torch.float32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def scale_family(logit_scale, scale_is_log, clamp_max, compute_dtype, d, flags, engine):
+    """Kernel family (include/clipnce.h: 0 exact, 1 fixed shift, 2 true maxima) the NEXT step with this logit scale would
+    select, from the host-side hint -- without a host synchronisation when the tensor has been seen before.  Used by
+    `graph.GraphedClipStep` to notice that a captured graph froze a family the scale has since left."""
+    if torch.is_tensor(logit_scale) and logit_scale.is_cuda:
+        t_dev = logit_scale.detach().to(torch.float32).reshape(1)
+        raw = t_dev.exp() if scale_is_log else t_dev.clone()
+        s_dev = raw.clamp(max=float(clamp_max)) if clamp_max is not None else raw
+        hint = _ScaleHint.get(logit_scale, s_dev) * 1.05
+        s = min(hint, float(clamp_max)) if clamp_max is not None else hint
+    else:
+        s = _scale_value(logit_scale, scale_is_log, clamp_max)[1]
+    return engine.lib.clipnce_uses_tensor_cores(_DT_CODE[compute_dtype], d, float(s), flags)
+
+
+_DT_CODE = {torch.bfloat16: 0, torch.float32: 1}
+
+
 class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, logit_scale, extra, symmetric, scale_is_log, clamp_max, group, compute_dtype, flags, engine,
@@ -83,6 +116,7 @@ class _FusedClipLoss(torch.autograd.Function):
             raw_dev = t_dev.exp() if scale_is_log else t_dev.clone()
             s_dev = raw_dev.clamp(max=float(clamp_max)) if clamp_max is not None else raw_dev
             hint = _ScaleHint.get(logit_scale, s_dev) * 1.05   # stale by a step or two at most: keep a margin
+            hint = _agree_near_threshold(hint, group, logit_scale.device)
             scale_arg = min(hint, float(clamp_max)) if clamp_max is not None else hint
         else:
             def scale_arg():   # called by the step after the scale-independent kernels and the all-gather are enqueued

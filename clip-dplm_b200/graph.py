@@ -11,8 +11,10 @@ one graph:
     loss, d_a, d_b, d_logit_scale = step(a, b, logit_scale)
 
 ``a``, ``b`` ([n_local, d], the step's dtype) and ``logit_scale`` (0-d) are copied into the graph's static inputs; the
-returned tensors are the graph's static outputs (valid until the next call).  The kernel family (tensor-core vs exact)
-is chosen from the logit scale seen at capture time; re-capture (``step.recapture()``) if exp(logit_scale) crosses 43.
+returned tensors are the graph's static outputs (valid until the next call).  The kernel family (fixed shift vs true
+running maxima, include/clipnce.h) is chosen from the logit scale seen at capture time; every ``family_check_every``
+replays the step compares it with the family the current scale selects (a non-blocking read, functional.scale_family) and
+re-captures by itself when exp(logit_scale) has crossed 40 -- a frozen fixed-shift graph would underflow beyond 43.
 """
 from __future__ import annotations
 
@@ -21,7 +23,7 @@ from typing import Optional
 import torch
 
 from .engine import default_engine
-from .functional import fused_clip_loss
+from .functional import fused_clip_loss, scale_family
 
 
 class GraphedClipStep:
@@ -39,6 +41,10 @@ class GraphedClipStep:
         self.warmup = warmup
         self.graph = None
         self._primed = False
+        self.family_check_every = 16 if group is None else 64   # with a group the check is a (tiny, synchronising) all-reduce
+        self._family = None
+        self._replays = 0
+        self._fam_args = (scale_is_log, clamp_max, dtype, d)
 
     def _eager(self):
         a = self.a.detach().requires_grad_(True)
@@ -57,10 +63,23 @@ class GraphedClipStep:
                 self._eager()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        self._family = self._current_family()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._eager()
         return self
+
+    def _current_family(self):
+        sil, cm, dt, d = self._fam_args
+        fam = scale_family(self.logit_scale, sil, cm, dt, d, 0, self.engine)
+        if self.group is not None:
+            # ranks read their (possibly stale) copies of s at different moments: agree on one answer, or some ranks would
+            # re-capture -- eager steps with barriers in them -- while others replay
+            import torch.distributed as dist
+            t = torch.tensor([fam], dtype=torch.int32, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            fam = int(t.item())
+        return fam
 
     def close(self):
         """Drop the captured graph.  Call before ``dist.destroy_process_group()``: a live graph that holds captured NCCL
@@ -75,6 +94,9 @@ class GraphedClipStep:
         embeddings straight into them -- e.g. an H2D copy -- skip the device-to-device copies of ``__call__``)."""
         if self.graph is None:
             self.recapture()
+        self._replays += 1
+        if self.family_check_every and self._replays % self.family_check_every == 0 and self._current_family() != self._family:
+            self.recapture()      # the scale left the captured kernel family's range (same decision on every rank's schedule)
         self.graph.replay()
         return self.out
 
@@ -89,8 +111,7 @@ class GraphedClipStep:
         if self.graph is None:
             # capture with REAL inputs in the static buffers: the row norms etc. of the warm-up steps are then finite
             self.recapture()
-        self.graph.replay()
-        return self.out
+        return self.replay()
 
 
 class HostFedClipStep:
