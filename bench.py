@@ -265,6 +265,14 @@ def run_ours(args, rank, local_rank, world):
             self.launches += 1
             return super().finish_slots(*a, **k)
 
+        def backward_both_sharded_sweep(self, *a, **k):
+            self.launches += 1          # the two-sided contraction + reduce-scatter kernel
+            return self._timed("bwd2", super().backward_both_sharded_sweep, *a, **k)
+
+        def finish_sharded(self, *a, **k):
+            self.launches += 2          # both tails in one launch + the scalar reduction
+            return super().finish_sharded(*a, **k)
+
         def normalize(self, *a, **k):
             self.launches += 1
             return super().normalize(*a, **k)

@@ -896,7 +896,7 @@ int clipnce_backward_both_sharded(const void* x, const void* y, const float* rin
                                   const float* grad_scale, void* dx, int out_dtype, float* d_scale_sum,
                                   void* const* peer_base, int world, int rank, int64_t slots_offset, void* workspace,
                                   size_t workspace_bytes, void* stream) {
-  if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !col_m || !col_w || !x_orig || !dx || !workspace || !peer_base)
+  if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_w || !col_m || !col_w || !x_orig || !workspace || !peer_base)
     return fail(CLIPNCE_EINVAL, "backward_both_sharded: null pointer");
   if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
     return fail(CLIPNCE_EINVAL, "backward_both_sharded: bad dtype");
@@ -921,10 +921,49 @@ int clipnce_backward_both_sharded(const void* x, const void* y, const float* rin
   if ((rc = bwd2_launch(pl, x, y, rinv_x, rinv_y, n_rows, n_cols, d, diag_offset, scale, scale_dev, row_m, row_w, col_m, col_w,
                         diag_w, ws, dy_peer, world, st)))
     return rc;
+  if (!dx) return 0;   // both tails are left to clipnce_finish_sharded (one launch for the two sides, behind the barrier)
   float* ds_part = reinterpret_cast<float*>(ws + pl.off_part);
   if ((rc = launch_finish(reinterpret_cast<float*>(ws + pl.off_dxh), pl.n_seg, n_rows * d, x, x_orig, in_dtype, rinv_x, grad_scale,
                           n_rows, d, dx, out_dtype, d_scale_sum ? ds_part : nullptr, st)))
     return rc;
+  if (d_scale_sum) {
+    aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)ceil_div(n_rows, 8), 1.f, d_scale_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int clipnce_finish_sharded(const void* x, const void* x_orig, const float* rinv_x, void* dx, const void* y_local,
+                           const void* y_orig, const float* rinv_y_local, void* dy, const float* slots, int64_t n_rows,
+                           int64_t n_cols, int64_t d, int dtype, float scale, int flags, int world, int in_dtype,
+                           int out_dtype, const float* grad_scale, float* d_scale_sum, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!x || !x_orig || !rinv_x || !dx || !y_local || !y_orig || !rinv_y_local || !dy || !slots || !workspace)
+    return fail(CLIPNCE_EINVAL, "finish_sharded: null pointer");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "finish_sharded: bad dtype");
+  Bwd2Plan pl;
+  if (!bwd2_plan(n_rows, n_cols, d, dtype, scale, flags, world, &pl))
+    return fail(CLIPNCE_EUNSUPPORTED, "finish_sharded: shape not served by the two-sided backward");
+  if (workspace_bytes < pl.bytes) return fail(CLIPNCE_EWORKSPACE, "finish_sharded: workspace %zu < %zu", workspace_bytes, pl.bytes);
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* ds_part = reinterpret_cast<float*>(ws + pl.off_part);
+  aux::FinishSide s0, s1;
+  s0.parts = reinterpret_cast<float*>(ws + pl.off_dxh); s0.n_split = pl.n_seg; s0.slab = n_rows * d; s0.xc = x; s0.xo = x_orig;
+  s0.rinv = rinv_x; s0.dx = dx; s0.ds_part = d_scale_sum ? ds_part : nullptr;
+  s1.parts = slots; s1.n_split = world; s1.slab = n_rows * d; s1.xc = y_local; s1.xo = y_orig; s1.rinv = rinv_y_local; s1.dx = dy;
+  s1.ds_part = nullptr;
+  const dim3 grid((unsigned)ceil_div(n_rows, 8), 2);
+  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  const int di = (int)d;
+#define FINISHD(TI, TO) aux::finish_rows_v4_dual<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(s0, s1, grad_scale, n_rows, di)
+  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISHD(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == CLIPNCE_BF16) FINISHD(__nv_bfloat16, float);
+  else if (out_dtype == CLIPNCE_BF16) FINISHD(float, __nv_bfloat16);
+  else FINISHD(float, float);
+#undef FINISHD
+  CUDA_TRY(cudaGetLastError());
   if (d_scale_sum) {
     aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)ceil_div(n_rows, 8), 1.f, d_scale_sum);
     CUDA_TRY(cudaGetLastError());

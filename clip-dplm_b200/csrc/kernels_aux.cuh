@@ -389,6 +389,76 @@ __global__ void finish_rows_v4(const float* __restrict__ parts, int n_split, int
   }
 }
 
+// Two finish_rows_v4 passes in ONE launch (blockIdx.y = side): the tails of the row-sharded two-sided backward -- side 0 sums
+// the segment slabs of dA_hat, side 1 the ranks' slots of dB_hat -- share the GPU instead of queueing behind each other.
+struct FinishSide {
+  const float* parts;
+  int n_split;
+  int64_t slab;
+  const void* xc;
+  const void* xo;
+  const float* rinv;
+  void* dx;
+  float* ds_part;
+};
+template <typename TC, typename TI, typename TO>
+__global__ void finish_rows_v4_dual(FinishSide s0, FinishSide s1, const float* __restrict__ grad_scale, int64_t n, int d) {
+  const FinishSide& s = blockIdx.y == 0 ? s0 : s1;
+  extern __shared__ __align__(16) float g4_sh[];   // [8][d]
+  __shared__ float dot_sh[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 8 + w;
+  float* g = g4_sh + (size_t)w * d;
+  float dot_c = 0.f;
+  if (row < n) {
+    const float ri = s.rinv[row];
+    const float gs = grad_scale ? grad_scale[0] : 1.f;
+    const float* pr = s.parts + row * d;
+    const TC* xcr = reinterpret_cast<const TC*>(s.xc) + row * d;
+    const TI* xor_ = reinterpret_cast<const TI*>(s.xo) + row * d;
+    const bool same = s.xc == s.xo;
+    float dot_o = 0.f;
+    for (int k = lane * 4; k < d; k += 128) {
+      float4 acc = ld4_f(pr + k);
+#pragma unroll 4
+      for (int q = 1; q < s.n_split; ++q) {
+        const float4 v = ld4_f(pr + (int64_t)q * s.slab + k);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(g + k) = acc;
+      const float4 vc = ld4_f(xcr + k);
+      dot_c = fmaf(vc.x, acc.x, dot_c); dot_c = fmaf(vc.y, acc.y, dot_c);
+      dot_c = fmaf(vc.z, acc.z, dot_c); dot_c = fmaf(vc.w, acc.w, dot_c);
+      if (!same) {
+        const float4 vo = ld4_f(xor_ + k);
+        dot_o = fmaf(vo.x, acc.x, dot_o); dot_o = fmaf(vo.y, acc.y, dot_o);
+        dot_o = fmaf(vo.z, acc.z, dot_o); dot_o = fmaf(vo.w, acc.w, dot_o);
+      }
+    }
+    dot_c = warp_sum(dot_c) * ri;
+    dot_o = same ? dot_c : warp_sum(dot_o) * ri;
+    if (ri >= 0.5f / kNormEps) dot_o = 0.f;
+    const float k2 = ri * gs;
+    TO* out = reinterpret_cast<TO*>(s.dx);
+    for (int k = lane * 4; k < d; k += 128) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + k);
+      const float4 xv = ld4_f(xor_ + k);
+      float4 o;
+      o.x = (gv.x - xv.x * ri * dot_o) * k2;
+      o.y = (gv.y - xv.y * ri * dot_o) * k2;
+      o.z = (gv.z - xv.z * ri * dot_o) * k2;
+      o.w = (gv.w - xv.w * ri * dot_o) * k2;
+      st4_f(out + row * d + k, o);
+    }
+  }
+  if (s.ds_part != nullptr) {
+    if (lane == 0) dot_sh[w] = dot_c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s.ds_part[blockIdx.x] = ((dot_sh[0] + dot_sh[1]) + (dot_sh[2] + dot_sh[3])) + ((dot_sh[4] + dot_sh[5]) + (dot_sh[6] + dot_sh[7]));
+  }
+}
+
 // *dst += coef * sum_p part[p]: 256 threads, strided fp64 partial sums + a fixed-order tree (deterministic).
 __global__ void reduce_scalar_partials_par(const float* __restrict__ part, int n_part, float coef, float* __restrict__ dst) {
   __shared__ double sh[256];

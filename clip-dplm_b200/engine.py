@@ -242,6 +242,38 @@ class CudaEngine:
         return dx, ds
 
     @_guard
+    def backward_both_sharded_sweep(self, x, y, rinv_x, rinv_y, diag_offset, scale, row_m, row_w, col_m, col_w, diag_w, peers,
+                                    world, rank, slots_off, flags=0, scale_dev=None):
+        """The sweep of `backward_both_sharded` alone: dA_hat stays in the workspace as segment slabs, the partial dB_hat goes
+        to the owners' slots; finish both sides behind the barrier with `finish_sharded`."""
+        n, d = x.shape
+        n_cols = y.shape[0]
+        ws = self._both_ws(n, n_cols, d, x.dtype, scale, flags, world, x.device)
+        _lib.check(self.lib.clipnce_backward_both_sharded(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n, n_cols, d, int(diag_offset),
+                                                          float(scale), _p(scale_dev), _p(row_m), _p(row_w), _p(col_m), _p(col_w),
+                                                          float(diag_w), _DT[x.dtype], flags, _p(x), _DT[x.dtype], None, None,
+                                                          _DT[x.dtype], None, peers, world, rank, int(slots_off), _p(ws),
+                                                          ws.numel(), _stream()), "backward_both_sharded")
+
+    @_guard
+    def finish_sharded(self, x, x_orig, rinv_x, y_local, y_orig, rinv_y_local, slots, n_cols, scale, world, out_dtype,
+                       grad_scale=None, flags=0, want_dscale=True):
+        """Both tails of the row-sharded two-sided backward in one launch -> dx, dy [n,d] in ``out_dtype``, d_scale_sum."""
+        n, d = x.shape
+        dev = x.device
+        ws = self._both_ws(n, n_cols, d, x.dtype, scale, flags, world, dev)
+        dx = torch.empty((n, d), dtype=out_dtype, device=dev)
+        dy = torch.empty((n, d), dtype=out_dtype, device=dev)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+        xo = x if x_orig.dtype == x.dtype else x_orig
+        yo = y_local if y_orig.dtype == y_local.dtype else y_orig
+        _lib.check(self.lib.clipnce_finish_sharded(_p(x), _p(xo), _p(rinv_x), _p(dx), _p(y_local), _p(yo), _p(rinv_y_local), _p(dy),
+                                                   _p(slots), n, n_cols, d, _DT[x.dtype], float(scale), flags, world, _DT[xo.dtype],
+                                                   _DT[out_dtype], _p(grad_scale), _p(ds), _p(ws), ws.numel(), _stream()),
+                   "finish_sharded")
+        return dx, dy, ds
+
+    @_guard
     def finish_slots(self, slots, n_slots, x, x_orig, rinv, out_dtype, grad_scale=None):
         """dx = normalise-backward(sum of the n_slots partial gradients [n_slots][n,d] f32), fixed order."""
         n, d = x.shape

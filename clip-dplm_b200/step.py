@@ -182,11 +182,20 @@ def contrastive_backward(engine, st: StepState, grad_scale=None, grad_dtype_a=No
         # row-sharded: ONE kernel sweeps local A rows x all columns, emits dA and stores every owner's partial dB straight
         # into its slot over NVLink peer memory (contraction + reduce-scatter); after the barrier the owner sums its slots
         x = st.xchg
-        da, ds = engine.backward_both_sharded(st.a_c, st.y, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w, col_m, col_w,
-                                              diag_w, st.a, grad_dtype_a or st.a.dtype, x.peers, x.world, x.rank, x.o_slots,
-                                              grad_scale, st.flags, want_dscale=True, **kw)
-        x.barrier(_exchange.PHASE_GRADS)
-        db = engine.finish_slots(x.slots, x.world, st.b_c, st.b, st.rinv_b, grad_dtype_b or st.b.dtype, grad_scale)
+        same_types = st.a.dtype == st.b.dtype and (grad_dtype_a or st.a.dtype) == (grad_dtype_b or st.b.dtype)
+        if same_types and hasattr(engine, "finish_sharded"):
+            # sweep -> barrier -> ONE launch for both tails (they share the GPU instead of queueing behind each other)
+            engine.backward_both_sharded_sweep(st.a_c, st.y, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w, col_m, col_w,
+                                               diag_w, x.peers, x.world, x.rank, x.o_slots, st.flags, **kw)
+            x.barrier(_exchange.PHASE_GRADS)
+            da, db, ds = engine.finish_sharded(st.a_c, st.a, st.rinv_a, st.b_c, st.b, st.rinv_b, x.slots, n_glob, st.scale,
+                                               x.world, grad_dtype_a or st.a.dtype, grad_scale, st.flags)
+        else:
+            da, ds = engine.backward_both_sharded(st.a_c, st.y, st.rinv_a, st.rinv_y, off, st.scale, st.row_m, row_w, col_m,
+                                                  col_w, diag_w, st.a, grad_dtype_a or st.a.dtype, x.peers, x.world, x.rank,
+                                                  x.o_slots, grad_scale, st.flags, want_dscale=True, **kw)
+            x.barrier(_exchange.PHASE_GRADS)
+            db = engine.finish_slots(x.slots, x.world, st.b_c, st.b, st.rinv_b, grad_dtype_b or st.b.dtype, grad_scale)
         ds = x.sum_scalars(ds, _exchange.PHASE_CLOSE)
         x.release()
         st.xchg = None

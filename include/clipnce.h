@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 105
+#define CLIPNCE_VERSION 106
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -212,6 +212,16 @@ int clipnce_backward_both_sharded(const void* x, const void* y, const float* rin
                                   float* d_scale_sum,
                                   void* const* peer_base, int world, int rank, int64_t slots_offset,
                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Both tails of clipnce_backward_both_sharded in ONE launch, to be enqueued behind the barrier: call the sweep with
+ * dx = NULL (its dA_hat segment slabs then stay in `workspace`, which must be the same buffer) and finish here --
+ * dx = normalise-backward(sum of the slabs), dy = normalise-backward(sum of the world slots), d_scale_sum += sum G.S.
+ * y_local / y_orig / rinv_y_local: this rank's B rows [n_rows,d].  Same dtype rules as clipnce_backward_dx. */
+int clipnce_finish_sharded(const void* x, const void* x_orig, const float* rinv_x, void* dx, const void* y_local,
+                           const void* y_orig, const float* rinv_y_local, void* dy, const float* slots, int64_t n_rows,
+                           int64_t n_cols, int64_t d, int dtype, float scale, int flags, int world, int in_dtype,
+                           int out_dtype, const float* grad_scale, float* d_scale_sum, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* dx_i = normalise-backward( sum_k slots[k][i, :] ), k < n_slots in fixed order: the tail of the row-sharded two-sided
  * backward (slots [n_slots][n, d] f32 = the ranks' partial gradients of the normalised rows x_hat). */
