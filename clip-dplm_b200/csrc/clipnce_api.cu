@@ -682,7 +682,7 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
 // ---- two-sided backward (kernels_pair2.cuh) ----------------------------------------------------------------------------
 namespace {
 struct Bwd2Plan {
-  int P, Q, n_rb, n_seg, seg_steps, n_items, n_rounds, n_steps, n_half, depth, stages_a, stages_b, stages_c, smem;
+  int P, Q, n_rb, n_seg, seg_steps, n_items, n_rounds, n_steps, n_half, depth, stages_a, stages_b, stages_c, gbuf, smem;
   size_t off_flags, off_ring, off_dxh, off_dyh, off_part, bytes;
 };
 
@@ -768,13 +768,16 @@ bool bwd2_plan(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale
   pl->depth = pair2::RING_DEPTH;
   if (const char* e = getenv("CLIPNCE_BWD2_DEPTH")) { const int v = atoi(e); if (v >= 2 && v <= 64) pl->depth = v; }
   const int nkc = (int)(d / 64);
-  const int total = (pair::SMEM_LIMIT - pair2::producer_smem(nkc, 0)) / pair::STAGE_BYTES;
+  pl->gbuf = 1;
+  if (const char* e = getenv("CLIPNCE_BWD2_GBUF")) { if (atoi(e) == 2) pl->gbuf = 2; }
+  int total = (pair::SMEM_LIMIT - pair2::producer_smem(nkc, 0, pl->gbuf)) / pair::STAGE_BYTES;
+  if (total < 4 && pl->gbuf == 2) { pl->gbuf = 1; total = (pair::SMEM_LIMIT - pair2::producer_smem(nkc, 0, 1)) / pair::STAGE_BYTES; }
   if (total < 4) return false;
   auto cap = [](int v) { return v > pair2::MAXS ? pair2::MAXS : v; };
   pl->stages_b = cap(total / 2);
   pl->stages_a = cap(total - total / 2);
   pl->stages_c = cap((pair::SMEM_LIMIT - pair2::consumer_smem(0)) / pair2::C_STAGE);
-  const int ps = pair2::producer_smem(nkc, pl->stages_a + pl->stages_b), cs = pair2::consumer_smem(pl->stages_c);
+  const int ps = pair2::producer_smem(nkc, pl->stages_a + pl->stages_b, pl->gbuf), cs = pair2::consumer_smem(pl->stages_c);
   pl->smem = ps > cs ? ps : cs;
   size_t off = 0;
   auto region = [&](size_t bytes) { const size_t o = off; off = (size_t)round_up((int64_t)(off + bytes), 256); return o; };
@@ -819,7 +822,7 @@ int bwd2_launch(const Bwd2Plan& pl, const void* x, const void* y, const float* r
   p.nkc = (int)(d / 64); p.nq2 = (int)ceil_div(d, 256); p.n_half = pl.n_half;
   p.n_rb = pl.n_rb; p.n_seg = pl.n_seg; p.seg_steps = pl.seg_steps; p.n_items = pl.n_items; p.n_rounds = pl.n_rounds;
   p.P = pl.P; p.Q = pl.Q; p.depth = pl.depth;
-  p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c;
+  p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c; p.gbuf = pl.gbuf;
   p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev; p.diag_w = diag_w;
   p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_w = row_w; p.col_m = col_m; p.col_w = col_w;
   p.dx = reinterpret_cast<float*>(ws + pl.off_dxh);
