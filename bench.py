@@ -73,20 +73,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def measured_traffic(n_global, d, world):
+def measured_traffic(n_global, d, world, two_sided):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (dram__bytes_read.sum +
-    dram__bytes_write.sum of pair::bwd_kernel), valid for the configuration it was captured on; None otherwise."""
+    dram__bytes_write.sum), valid for the configuration it was captured on (N = 65536, d = 512, one GPU); None otherwise.
+    Round 2: pair2::bwd2_kernel (profiles/r2_ncu_full_two_sided_n65536.csv, column 3); round-1 kernel: pair::bwd_kernel."""
     if (n_global, d, world) != (65536, 512, 1):
         return None
+    name, unit = ("r2_ncu_full_two_sided_n65536.csv", "Gbyte") if two_sided else ("r1_ncu_full_pair_kernels_n65536.csv", "Mbyte")
     try:
         import csv
         rd = wr = None
-        for row in csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_pair_kernels_n65536.csv"))):
-            if row and row[0].startswith("dram__bytes_read.sum") and row[1] == "Mbyte":
+        for row in csv.reader(open(os.path.join(ROOT, "profiles", name))):
+            if row and row[0].startswith("dram__bytes_read.sum") and row[1] == unit:
                 rd = float(row[3])
-            if row and row[0].startswith("dram__bytes_write.sum") and row[1] == "Mbyte":
+            if row and row[0].startswith("dram__bytes_write.sum") and row[1] == unit:
                 wr = float(row[3])
-        return (rd + wr) * 1e6 if rd is not None and wr is not None else None
+        mult = 1e9 if unit == "Gbyte" else 1e6
+        return (rd + wr) * mult if rd is not None and wr is not None else None
     except Exception:
         return None
 
@@ -543,7 +546,7 @@ def run_ours(args, rank, local_rank, world):
                                 "algorithmic 4 N^2 d of 6 N^2 d executed, cta_group::2)" if two_sided else
                                 "pair::bwd_kernel (one backward side: logits recompute + gradient GEMM, cta_group::2)"),
                      "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": measured_traffic(n_global, d, world),
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": measured_traffic(n_global, d, world, two_sided),
                      "peak_kind": f"{peaks['src']} sustained bf16 cuBLAS", "frac_of_burst": achieved / peaks["burst"],
                      "ms_per_launch": t_bwd, "fwd_ms_per_launch": t_fwd,
                      "fwd_achieved": 2.0 * n_local * n_global * d / (t_fwd * 1e-3) / 1e12,

@@ -823,6 +823,10 @@ int bwd2_launch(const Bwd2Plan& pl, const void* x, const void* y, const float* r
   p.n_rb = pl.n_rb; p.n_seg = pl.n_seg; p.seg_steps = pl.seg_steps; p.n_items = pl.n_items; p.n_rounds = pl.n_rounds;
   p.P = pl.P; p.Q = pl.Q; p.depth = pl.depth;
   p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c; p.gbuf = pl.gbuf;
+  {
+    const char* e = getenv("CLIPNCE_BWD2_L2HINT");
+    p.l2_hints = e ? atoi(e) : 1;
+  }
   p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev; p.diag_w = diag_w;
   p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.row_m = row_m; p.row_w = row_w; p.col_m = col_m; p.col_w = col_w;
   p.dx = reinterpret_cast<float*>(ws + pl.off_dxh);

@@ -76,6 +76,7 @@ struct Params {
   int P, Q, depth;
   int stages_a, stages_b, stages_c;
   int gbuf;                   // 1 or 2 copies of the producer's G tile in shared memory
+  int l2_hints;               // ring stores / loads carry the evict_last L2 policy
   long long diag_offset;      // column of row i's positive = i + diag_offset
   float scale, diag_w;
   const float* scale_dev;
@@ -344,6 +345,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
         uint32_t gs = 0;
         bool pending = false;
         uint32_t g_prev = 0;
+        const uint64_t keep = ptx::l2_policy_evict_last();   // ring lines stay in L2 until their slot is overwritten
         for (int r = 0; r < p.n_rounds; ++r) {
           if (r * p.P + pair_id >= p.n_items) break;
           const bool more_rounds = (r + 1) * p.P + pair_id < p.n_items;
@@ -354,7 +356,8 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
             const uint32_t gb = g_buf(gs);
             for (int kc = 0; kc < 4; ++kc) {
               ptx::mbar_wait(bar(B_GSFULL + 4 * gb + kc), g_par(gs));
-              ptx::tma_store_2d(&tmap_g, g_smem + gb * G_BYTES + kc * 8192, 64 * kc, row0);
+              if (p.l2_hints) ptx::tma_store_2d_hint(&tmap_g, g_smem + gb * G_BYTES + kc * 8192, 64 * kc, row0, keep);
+              else ptx::tma_store_2d(&tmap_g, g_smem + gb * G_BYTES + kc * 8192, 64 * kc, row0);
               ptx::bulk_commit_group();
             }
             ptx::bulk_wait_group_read0();               // shared memory of the four boxes has been read
@@ -520,6 +523,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
       if (ptx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
+        const uint64_t keep = ptx::l2_policy_evict_last();
         for (int r = 0; r < p.n_rounds; ++r) {
           const int pw = round_items(p, r);
           const int nsub = round_subs(p, r);
@@ -546,8 +550,12 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
                     const uint32_t st = ring_c + stage * C_STAGE;
                     const int grow = (slot * p.P + pp) * 128 + 64 * kb;
                     const int xrow = (sub.rb_lo + pp - sub.p_lo) * 128 + 64 * kb;
-                    for (int gi = 0; gi < 2; ++gi)
-                      ptx::tma_load_2d_pair(st + gi * 8192, &tmap_g, bar(B_FULL_A + stage), 128 * (int)rank + 64 * gi, grow);
+                    for (int gi = 0; gi < 2; ++gi) {
+                      if (p.l2_hints)
+                        ptx::tma_load_2d_pair_hint(st + gi * 8192, &tmap_g, bar(B_FULL_A + stage), 128 * (int)rank + 64 * gi, grow, keep);
+                      else
+                        ptx::tma_load_2d_pair(st + gi * 8192, &tmap_g, bar(B_FULL_A + stage), 128 * (int)rank + 64 * gi, grow);
+                    }
                     for (int gi = 0; gi < ngr; ++gi)
                       ptx::tma_load_2d_pair(st + 16384 + gi * 8192, &tmap_x, bar(B_FULL_A + stage),
                                             256 * hh + (wq >> 1) * (int)rank + 64 * gi, xrow);
