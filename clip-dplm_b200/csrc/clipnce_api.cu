@@ -714,7 +714,7 @@ bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resid
 // world == 0: one GPU (n_rows == n_cols, every column segment stays local); world >= 2: row-sharded step, the rank's
 // n_rows = n_cols / world rows against all columns, one segment per owner rank.
 bool bwd2_plan(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale, int flags, int world, Bwd2Plan* pl) {
-  if (!tc_eligible(dtype, d, scale, flags) || !pair_eligible(d) || d > 512) return false;
+  if (!tc_eligible(dtype, d, scale, flags) || !pair_eligible(d)) return false;
   if (world == 1 || world < 0 || world > pair2::MAX_WORLD) return false;
   if (world == 0 ? n_rows != n_cols : n_rows * world != n_cols) return false;
   int64_t min_pairs = 16384ll * 16384ll;   // below this the items do not fill the producer pairs (CLIPNCE_BWD2_MIN_N: test hook)
@@ -820,6 +820,7 @@ int bwd2_launch(const Bwd2Plan& pl, const void* x, const void* y, const float* r
   memset(&p, 0, sizeof p);
   p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
   p.nkc = (int)(d / 64); p.nq2 = (int)ceil_div(d, 256); p.n_half = pl.n_half;
+  p.nsbuf = p.nq2 <= 2 ? 2 : 1;   // 128 nq2 accumulator columns + 128 per logits buffer <= 512
   p.n_rb = pl.n_rb; p.n_seg = pl.n_seg; p.seg_steps = pl.seg_steps; p.n_items = pl.n_items; p.n_rounds = pl.n_rounds;
   p.P = pl.P; p.Q = pl.Q; p.depth = pl.depth;
   p.stages_a = pl.stages_a; p.stages_b = pl.stages_b; p.stages_c = pl.stages_c; p.gbuf = pl.gbuf;

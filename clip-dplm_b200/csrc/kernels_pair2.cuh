@@ -70,7 +70,8 @@ constexpr int B_FULL_A = 0, B_EMPTY_A = MAXS, B_FULL_B = 2 * MAXS, B_EMPTY_B = 3
 static_assert(B_COUNT * 8 <= 1000, "barrier block");
 
 struct Params {
-  int n_rows, n_cols, d;      // n_rows % 128 == 0, n_cols % (256 n_seg) == 0, d % 128 == 0, d <= 512
+  int n_rows, n_cols, d;      // n_rows % 128 == 0, n_cols % (256 n_seg) == 0, d % 128 == 0, d <= 768
+  int nsbuf;                  // producer logits buffers: 2 (d <= 512), 1 beyond (384 accumulator columns + 128)
   int nkc, nq2, n_half;
   int n_rb, n_seg, seg_steps, n_items, n_rounds;
   int P, Q, depth;
@@ -213,7 +214,9 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
     auto g_buf = [&](uint32_t gs) -> uint32_t { return p.gbuf == 2 ? (gs & 1u) : 0u; };
     auto g_par = [&](uint32_t gs) -> uint32_t { return p.gbuf == 2 ? ((gs >> 1) & 1u) : (gs & 1u); };
     const uint32_t ring_b = ring_a + p.stages_a * STAGE_BYTES;
-    constexpr int S_COL0 = TMEM_COLS - 256;   // two logits buffers of 128 columns behind the accumulators
+    const int S_COL0 = TMEM_COLS - 128 * p.nsbuf;   // logits buffers of 128 columns behind the accumulators
+    auto s_buf = [&](uint32_t gs) -> int { return p.nsbuf == 2 ? (int)(gs & 1u) : 0; };
+    auto s_par = [&](uint32_t gs) -> uint32_t { return p.nsbuf == 2 ? ((gs >> 1) & 1u) : (gs & 1u); };
 
     if (warp == 0) {
       // ------------------------------------------------------------- TMA: resident X per item, then Y rows (K-major)
@@ -279,8 +282,8 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
           if (r * p.P + pair_id >= p.n_items) break;
           ptx::mbar_wait(bar(B_XFULL), r & 1);
           for (int t = 0; t < p.seg_steps; ++t, ++gs) {
-            const int sb = gs & 1;
-            ptx::mbar_wait(bar(B_SEMPTY + sb), ((gs >> 1) & 1) ^ 1u);
+            const int sb = s_buf(gs);
+            ptx::mbar_wait(bar(B_SEMPTY + sb), s_par(gs) ^ 1u);
             const uint32_t d_tmem = tmem_base + S_COL0 + sb * 128;
             for (int g = 0; g < p.nkc; ++g) {
               if (!ready) ptx::mbar_wait(bar(B_FULL_A + stage), phase);
@@ -416,7 +419,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
         }
 
         for (int t = t0; t < t0 + p.seg_steps; ++t, ++gs) {
-          const int sb = gs & 1;
+          const int sb = s_buf(gs);
           float* const cv = colv + (gs & 1) * 768;
           cv[te] = ry_n * k2;                                                   // S_ij log2(e) = acc * rinv_x[i] * cj
           cv[256 + te] = cw_n * pair::ex2((sc - cm_n) * LOG2E) * ry_n;          // v_j / |y_j|
@@ -429,7 +432,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
           const long long dl = dcol - ((long long)t * STEP_J + jl0);   // step-local index of the positive, if in [0, 64)
           const bool has_diag = dl >= 0 && dl < 64;
 
-          ptx::mbar_wait(bar(B_SFULL + sb), (gs >> 1) & 1);
+          ptx::mbar_wait(bar(B_SFULL + sb), s_par(gs));
           ptx::tc_fence_after();
           uint32_t pk[32];
 #pragma unroll

@@ -440,7 +440,7 @@ def test_benchmarked_shapes_against_sampled_oracle(n, d, ls, mix):
 # two-sided backward (csrc/kernels_pair2.cuh): one sweep over the logits tiles emits dA and dB
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,d,forced_p,seg", [(4096, 512, 0, 0), (4096, 512, 5, 1), (2048, 256, 3, 1), (2048, 128, 0, 0),
-                                                (3072, 384, 7, 1), (4096, 512, 5, 2), (4096, 256, 0, 2), (2048, 512, 70, 8)])
+                                                (3072, 384, 7, 1), (4096, 512, 5, 2), (4096, 256, 0, 2), (2048, 512, 70, 8), (2048, 768, 0, 0), (2560, 640, 9, 1)])
 def test_two_sided_backward(monkeypatch, n, d, forced_p, seg):
     """clipnce_backward_both_dx against the dense float64 closed form AND against the two-sweep path on the same inputs.
     `forced_p` producer pairs force several rounds of work items (the last one partly filled), ring wrap-around and the
