@@ -48,6 +48,11 @@ SIGNATURES = {
     "clipnce_finish_slots": [_vp, _int, _vp, _int, _vp, _int, _vp, _vp, _i64, _i64, _vp, _int, _vp],
     "clipnce_backward_both_dx": [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _int, _int, _vp, _vp,
                                  _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp],
+    "clipnce_group_workspace_bytes": [_int, _int, _i64, _i64, _int, _f32, _int, ctypes.POINTER(_sz)],
+    "clipnce_group_forward": [_vp, _vp, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), _i64, _i64, _f32, _vp, _int,
+                              _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "clipnce_group_backward": [_vp, _vp, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_int), _i64, _i64, _f32, _vp, _vp,
+                               _vp, _int, _int, _vp, _int, _vp, _vp, _int, _vp, _vp, _vp, _sz, _vp],
     "clipnce_head_tail": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
     "clipnce_head_tail_backward": [_vp, _int, _vp, _vp, _vp, _i64, _i64, _vp, _vp],
     "clipnce_softmax_weights": [_vp, _i64, _f32, _vp, _vp],
@@ -100,7 +105,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError here == header/library mismatch
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if lib.clipnce_version() != 106:
+        if lib.clipnce_version() != 107:
             raise RuntimeError("clip_dplm_b200: libclipnce.so version mismatch; rebuild")
         _lib = lib
         return lib

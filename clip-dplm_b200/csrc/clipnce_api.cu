@@ -181,8 +181,9 @@ int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams
   p.stages = stages;
   CUtensorMap tx, ty;
   int rc;
-  if ((rc = make_tmap(&tx, x, p.d, p.n_rows, p.d, ROWS))) return rc;
-  if ((rc = make_tmap(&ty, y, p.d, p.n_cols, p.d, 128))) return rc;
+  // several problems in one launch: both operands are members of one stacked matrix, indexed by stack row
+  if ((rc = make_tmap(&tx, x, p.d, p.grp.n_prob ? p.grp.stack_rows : p.n_rows, p.d, ROWS))) return rc;
+  if ((rc = make_tmap(&ty, y, p.d, p.grp.n_prob ? p.grp.stack_rows : p.n_cols, p.d, 128))) return rc;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_attr_done[attr_slot]) {
@@ -208,9 +209,10 @@ int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_
   p.nsbuf = p.nq2 <= 2 ? 2 : 1;   // 128 nq2 accumulator columns + 128 per logits buffer <= 512
   CUtensorMap tx, ty, tyg;
   int rc;
-  if ((rc = make_tmap(&tx, x, p.d, p.n_rows, p.d, pair::BWD_ROWS))) return rc;
-  if ((rc = make_tmap(&ty, y, p.d, p.n_cols, p.d, 128))) return rc;
-  if ((rc = make_tmap(&tyg, y, p.d, p.n_cols, p.d, 64))) return rc;
+  const int64_t x_rows = p.grp.n_prob ? p.grp.stack_rows : p.n_rows, y_rows = p.grp.n_prob ? p.grp.stack_rows : p.n_cols;
+  if ((rc = make_tmap(&tx, x, p.d, x_rows, p.d, pair::BWD_ROWS))) return rc;
+  if ((rc = make_tmap(&ty, y, p.d, y_rows, p.d, 128))) return rc;
+  if ((rc = make_tmap(&tyg, y, p.d, y_rows, p.d, 64))) return rc;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_attr_done[attr_slot]) {
@@ -672,6 +674,229 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
   CUDA_TRY(cudaGetLastError());
   if (df.ds_pending) {
     aux::reduce_scalar_partials_par<<<1, 256, 0, st>>>(ds_part, (int)n_blk, 1.f, d_scale_sum);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- several pair problems in one launch (pair::Group) ------------------------------------------------------------------
+namespace {
+struct GroupPlan {
+  int fam, rows;            // kernel family (1 / 2); resident rows per CTA of the forward (128 / 64)
+  int64_t n_pad, V;         // rows per member (n rounded up to 256); virtual rows of the forward: n_prob * n_pad
+  int fwd_pairs, bwd_pairs; // row blocks per problem
+  int steps;                // 256-column steps per problem
+  int bwd_split_steps, bwd_n_split;
+  size_t off_w, off_ds, off_sq, off_slab, bytes;   // backward layout of the workspace
+  size_t fwd_bytes;
+  int n_blk;
+};
+
+int group_plan(int n_members, int n_prob, int64_t n, int64_t d, int dtype, float scale, int flags, GroupPlan* pl) {
+  memset(pl, 0, sizeof *pl);
+  if (n_members < 1 || n_members > aux::FG_MEMBERS || n_prob < 1 || 2 * n_prob > pair::MAX_GROUP || n < 1 || d < 1)
+    return fail(CLIPNCE_EINVAL, "group: 1..%d members, 1..%d problems", aux::FG_MEMBERS, pair::MAX_GROUP / 2);
+  pl->fam = tc_family(dtype, d, scale, flags);
+  if (!((pl->fam == 1 && pair_eligible(d)) || pl->fam == 2) || (flags & CLIPNCE_FLAG_UNBOUNDED)) { pl->fam = 0; return 0; }
+  pl->rows = d <= 512 ? 128 : 64;
+  pl->n_pad = round_up(n, 256);
+  pl->V = (int64_t)n_prob * pl->n_pad;
+  if ((int64_t)n_members * pl->n_pad > (1ll << 30) || 2 * pl->V > (1ll << 30)) { pl->fam = 0; return 0; }
+  pl->fwd_pairs = (int)(pl->n_pad / (2 * pl->rows));
+  pl->bwd_pairs = (int)(pl->n_pad / (2 * pair::BWD_ROWS));
+  pl->steps = (int)(pl->n_pad / pair::STEP_J);
+  // forward scratch: fixed shift -- column partials [2 fwd_pairs][V] + row partials [MAX_SPLIT][V];
+  // true maxima -- (max, sum) row partials of both launches
+  const size_t f1 = sizeof(float) * ((size_t)2 * pl->fwd_pairs + pair::MAX_SPLIT) * (size_t)pl->V;
+  const size_t f2 = sizeof(float) * 4 * (size_t)pair::MAX_SPLIT * (size_t)pl->V;
+  pl->fwd_bytes = round_up(pl->fam == 2 ? f2 : f1, 256);
+  // backward: soft-max weights [2 V] | row-dot and |dx|^2 block partials | split slabs [n_split][2 V, d] f32 (<= 512 MiB)
+  pl->n_blk = (int)ceil_div(pl->n_pad, 8);
+  const size_t slab = sizeof(float) * 2 * (size_t)pl->V * (size_t)d;
+  int max_split = (int)(((size_t)512 << 20) / slab);
+  if (max_split < 1) max_split = 1;
+  if (max_split > pair::MAX_SPLIT) max_split = pair::MAX_SPLIT;
+  pl->bwd_split_steps = max_split >= 2 ? pick_split_steps(2 * n_prob * pl->bwd_pairs, pl->steps, max_split) : pl->steps;
+  pl->bwd_n_split = (int)ceil_div(pl->steps, pl->bwd_split_steps);
+  pl->off_w = 0;
+  pl->off_ds = round_up(sizeof(float) * 2 * (size_t)pl->V, 256);
+  pl->off_sq = pl->off_ds + round_up(sizeof(float) * (size_t)n_members * pl->n_blk, 256);
+  pl->off_slab = pl->off_sq + round_up(sizeof(float) * (size_t)n_members * pl->n_blk, 256);
+  pl->bytes = pl->off_slab + (size_t)pl->bwd_n_split * slab;
+  if (pl->fwd_bytes > pl->bytes) pl->bytes = pl->fwd_bytes;
+  return 0;
+}
+
+int group_members_ok(int n_members, int n_prob, const int* xm, const int* ym) {
+  if (!xm || !ym) return fail(CLIPNCE_EINVAL, "group: null member list");
+  for (int k = 0; k < n_prob; ++k)
+    if (xm[k] < 0 || xm[k] >= n_members || ym[k] < 0 || ym[k] >= n_members)
+      return fail(CLIPNCE_EINVAL, "group: problem %d names a member outside 0..%d", k, n_members - 1);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int clipnce_group_workspace_bytes(int n_members, int n_prob, int64_t n, int64_t d, int dtype, float scale, int flags,
+                                  size_t* out) {
+  if (!out) return fail(CLIPNCE_EINVAL, "group_workspace_bytes: null pointer");
+  GroupPlan pl;
+  int rc = group_plan(n_members, n_prob, n, d, dtype, scale, flags, &pl);
+  if (rc) return rc;
+  *out = pl.fam ? pl.bytes : 0;
+  return 0;
+}
+
+int clipnce_group_forward(const void* stack, const float* rinv, int n_members, int n_prob, const int* x_member,
+                          const int* y_member, int64_t n, int64_t d, float scale, const float* scale_dev, int dtype,
+                          int flags, float* stat_m, float* stat_l, float* diag, float* loss, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!stack || !rinv || !stat_m || !stat_l || !diag || !loss || !workspace)
+    return fail(CLIPNCE_EINVAL, "group_forward: null pointer");
+  if (!std::isfinite(scale)) return fail(CLIPNCE_EINVAL, "group_forward: scale is not finite");
+  GroupPlan pl;
+  int rc = group_plan(n_members, n_prob, n, d, dtype, scale, flags, &pl);
+  if (rc) return rc;
+  if (!pl.fam) return fail(CLIPNCE_EUNSUPPORTED, "group_forward: shape / type not served (bf16, d %% 128 == 0, d <= 768)");
+  if ((rc = group_members_ok(n_members, n_prob, x_member, y_member))) return rc;
+  if (workspace_bytes < pl.fwd_bytes) return fail(CLIPNCE_EWORKSPACE, "group_forward: workspace %zu < %zu", workspace_bytes, pl.fwd_bytes);
+  if (!aligned16(stack)) return fail(CLIPNCE_EINVAL, "group_forward: the stack must be 16-byte aligned");
+  if ((rc = check_device_sm100())) return rc;
+  cudaStream_t st = as_stream(stream);
+  const int64_t V = pl.V;
+
+  pair::FwdParams p;
+  memset(&p, 0, sizeof p);
+  p.n_rows = (int)V; p.n_cols = (int)V; p.d = (int)d;
+  p.nkc = (int)ceil_div(d, 64); p.n_steps = pl.steps;
+  p.diag_offset = 0; p.scale = scale; p.scale_dev = scale_dev;
+  p.rinv_x = rinv; p.rinv_y = rinv;
+  p.n_pairs = n_prob * pl.fwd_pairs;
+  p.split_steps = pick_split_steps(p.n_pairs, p.n_steps, pair::MAX_SPLIT);
+  const int n_split = (int)ceil_div(p.n_steps, p.split_steps);
+  p.grp.n_prob = n_prob; p.grp.pairs_per_prob = pl.fwd_pairs; p.grp.steps_per_prob = pl.steps; p.grp.n_valid = (int)n;
+  p.grp.stack_rows = (int)(n_members * pl.n_pad);
+  float* wsf = reinterpret_cast<float*>(workspace);
+
+  if (pl.fam == 2) {   // true maxima: row statistics of (x, y), then of (y, x) = the column statistics
+    for (int side = 0; side < 2; ++side) {
+      for (int k = 0; k < n_prob; ++k) {
+        const int res = side == 0 ? x_member[k] : y_member[k], str = side == 0 ? y_member[k] : x_member[k];
+        p.grp.xshift[k] = (int)((res - k) * pl.n_pad);
+        p.grp.yshift[k] = (int)((str - k) * pl.n_pad);
+      }
+      p.diag = side == 0 ? diag : nullptr;
+      p.row_part_m = wsf + (size_t)side * 2 * (size_t)n_split * (size_t)V;
+      p.row_part = p.row_part_m + (size_t)n_split * (size_t)V;
+      rc = pl.rows == 128 ? launch_pair_fwd<128, 2>(7, stack, stack, p, st) : launch_pair_fwd<64, 2>(11, stack, stack, p, st);
+      if (rc) return rc;
+      aux::reduce_ml_partials<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(p.row_part_m, p.row_part, n_split, V, V,
+                                                                           stat_m + side * V, stat_l + side * V);
+      CUDA_TRY(cudaGetLastError());
+    }
+  } else {
+    for (int k = 0; k < n_prob; ++k) {
+      p.grp.xshift[k] = (int)((x_member[k] - k) * pl.n_pad);
+      p.grp.yshift[k] = (int)((y_member[k] - k) * pl.n_pad);
+    }
+    p.diag = diag;
+    p.col_ld = V;
+    const int n_part = 2 * pl.fwd_pairs;
+    p.col_part = wsf;
+    p.row_part = wsf + (size_t)n_part * (size_t)V;
+    rc = pl.rows == 128 ? launch_pair_fwd<128>(4, stack, stack, p, st) : launch_pair_fwd<64>(5, stack, stack, p, st);
+    if (rc) return rc;
+    aux::reduce_col_partials<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(p.col_part, n_part, V, V, scale, scale_dev,
+                                                                          stat_m + V, stat_l + V);
+    aux::reduce_col_partials<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(p.row_part, n_split, V, V, scale, scale_dev,
+                                                                          stat_m, stat_l);
+    CUDA_TRY(cudaGetLastError());
+  }
+  aux::loss_reduce_group<<<1, 1024, 0, st>>>(stat_m, stat_l, diag, n_prob, n, pl.n_pad, loss);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_group_backward(const void* stack, const float* rinv, int n_members, int n_prob, const int* x_member,
+                           const int* y_member, int64_t n, int64_t d, float scale, const float* scale_dev,
+                           const float* stat_m, const float* stat_l, int dtype, int flags, const void* stack_orig,
+                           int in_dtype, const float* grad_scale, void* d_stack, int out_dtype, float* d_scale_sum,
+                           float* grad_sumsq, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!stack || !rinv || !stat_m || !stat_l || !stack_orig || !d_stack || !workspace)
+    return fail(CLIPNCE_EINVAL, "group_backward: null pointer");
+  if ((in_dtype != CLIPNCE_BF16 && in_dtype != CLIPNCE_F32) || (out_dtype != CLIPNCE_BF16 && out_dtype != CLIPNCE_F32))
+    return fail(CLIPNCE_EINVAL, "group_backward: bad dtype");
+  if (in_dtype == dtype && stack_orig != stack) return fail(CLIPNCE_EINVAL, "group_backward: stack_orig of the compute type must be the stack itself");
+  if (!std::isfinite(scale)) return fail(CLIPNCE_EINVAL, "group_backward: scale is not finite");
+  GroupPlan pl;
+  int rc = group_plan(n_members, n_prob, n, d, dtype, scale, flags, &pl);
+  if (rc) return rc;
+  if (!pl.fam) return fail(CLIPNCE_EUNSUPPORTED, "group_backward: shape / type not served (bf16, d %% 128 == 0, d <= 768)");
+  if ((rc = group_members_ok(n_members, n_prob, x_member, y_member))) return rc;
+  if (workspace_bytes < pl.bytes) return fail(CLIPNCE_EWORKSPACE, "group_backward: workspace %zu < %zu", workspace_bytes, pl.bytes);
+  if (!aligned16(stack) || !aligned16(stack_orig) || !aligned16(d_stack))
+    return fail(CLIPNCE_EINVAL, "group_backward: buffers must be 16-byte aligned");
+  if (sizeof(float) * 8 * (size_t)d > 48 * 1024) return fail(CLIPNCE_EUNSUPPORTED, "group_backward: d too large");
+  if ((rc = check_device_sm100())) return rc;
+  cudaStream_t st = as_stream(stream);
+  const int64_t V = pl.V;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* w = reinterpret_cast<float*>(ws + pl.off_w);
+  float* ds_part = reinterpret_cast<float*>(ws + pl.off_ds);
+  float* sq_part = reinterpret_cast<float*>(ws + pl.off_sq);
+  float* slabs = reinterpret_cast<float*>(ws + pl.off_slab);
+
+  // w = 1 / (2 n l) for row and column sums alike (entries of the padding are never read)
+  aux::softmax_weights<<<(unsigned)ceil_div(2 * V, 256), 256, 0, st>>>(stat_l, 2 * V, 1.0f / (2.0f * (float)n), w);
+  CUDA_TRY(cudaGetLastError());
+
+  // ONE sweep launch over 2 n_prob virtual problems: k < n_prob the X side of problem k (rows of x_member[k] resident),
+  // k >= n_prob the Y side of problem k - n_prob (rows of y_member resident; the column statistics play the row role)
+  pair::BwdParams p;
+  memset(&p, 0, sizeof p);
+  p.n_rows = (int)(2 * V); p.n_cols = (int)(2 * V); p.d = (int)d;
+  p.nkc = (int)ceil_div(d, 64); p.nq2 = (int)ceil_div(d, 256); p.n_steps = pl.steps;
+  p.diag_offset = 0; p.scale = scale; p.scale_dev = scale_dev; p.diag_w = 1.0f / (float)n; p.grad_out = 1.0f;
+  p.rinv_x = rinv; p.rinv_y = rinv; p.row_m_in = stat_m; p.row_w = w; p.col_m_in = stat_m; p.col_w = w;
+  p.n_pairs = 2 * n_prob * pl.bwd_pairs;
+  p.split_steps = pl.bwd_split_steps;
+  p.dx = slabs;
+  p.grp.n_prob = 2 * n_prob; p.grp.pairs_per_prob = pl.bwd_pairs; p.grp.steps_per_prob = pl.steps; p.grp.n_valid = (int)n;
+  p.grp.stack_rows = (int)(n_members * pl.n_pad);
+  p.grp.gscale = grad_scale; p.grp.gmod = n_prob;
+  aux::FinishGroup fg;
+  memset(&fg, 0, sizeof fg);
+  fg.n_pad = pl.n_pad; fg.n_valid = n;
+  for (int k = 0; k < 2 * n_prob; ++k) {
+    const int q = k % n_prob;
+    const int res = k < n_prob ? x_member[q] : y_member[q], str = k < n_prob ? y_member[q] : x_member[q];
+    p.grp.xshift[k] = (int)((res - k) * pl.n_pad);
+    p.grp.yshift[k] = (int)((str - k) * pl.n_pad);
+    p.grp.cshift[k] = (int)(k < n_prob ? V : -V);
+    if (fg.n_contrib[res] >= aux::FG_CONTRIB) return fail(CLIPNCE_EINVAL, "group_backward: too many problems share member %d", res);
+    fg.vprob[res][fg.n_contrib[res]++] = k;
+  }
+  if ((rc = pl.fam == 2 ? launch_pair_bwd<true>(stack, stack, p, st) : launch_pair_bwd<false>(stack, stack, p, st))) return rc;
+
+  const int di = (int)d;
+  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  const dim3 grid((unsigned)pl.n_blk, (unsigned)n_members);
+  const int64_t slab_elems = 2 * V * d;
+#define FINISH_G(TI, TO)                                                                                                  \
+  aux::finish_rows_group<__nv_bfloat16, TI, TO><<<grid, 256, smem, st>>>(slabs, pl.bwd_n_split, slab_elems, fg,          \
+                                                                        (const __nv_bfloat16*)stack, (const TI*)stack_orig, \
+                                                                        rinv, di, (TO*)d_stack, ds_part, sq_part)
+  if (in_dtype == CLIPNCE_BF16 && out_dtype == CLIPNCE_BF16) FINISH_G(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == CLIPNCE_BF16) FINISH_G(__nv_bfloat16, float);
+  else if (out_dtype == CLIPNCE_BF16) FINISH_G(float, __nv_bfloat16);
+  else FINISH_G(float, float);
+#undef FINISH_G
+  CUDA_TRY(cudaGetLastError());
+  if (d_scale_sum || grad_sumsq) {
+    aux::reduce_group_scalars<<<1 + n_members, 256, 0, st>>>(ds_part, sq_part, n_members, pl.n_blk, d_scale_sum, grad_sumsq);
     CUDA_TRY(cudaGetLastError());
   }
   return 0;

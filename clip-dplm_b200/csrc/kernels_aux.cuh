@@ -473,4 +473,133 @@ __global__ void reduce_scalar_partials_par(const float* __restrict__ part, int n
   if (threadIdx.x == 0) dst[0] += (float)(sh[0] * (double)coef);
 }
 
+// ---- several pair problems in one launch (kernels_pair.cuh `Group`; the tri-modal model of tf_clip_codes (1).ipynb:13152-13165)
+// Per-problem mean loss of the symmetric InfoNCE, problem k over the virtual rows / columns [k n_pad, k n_pad + n):
+// loss[k] = [ sum_i (r_i - diag_i) + (c_i - diag_i) ] / (2 n), loss[n_prob] = their sum.  stat_* = [row statistics | column
+// statistics], each [n_prob n_pad].  One block, fp64 accumulators, fixed order.
+__global__ void loss_reduce_group(const float* __restrict__ stat_m, const float* __restrict__ stat_l,
+                                  const float* __restrict__ diag, int n_prob, int64_t n, int64_t n_pad,
+                                  float* __restrict__ loss) {
+  __shared__ double sh[1024];
+  const int64_t V = (int64_t)n_prob * n_pad;
+  double total = 0.0;
+  for (int k = 0; k < n_prob; ++k) {
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const int64_t r = (int64_t)k * n_pad + i;
+      const double dg = diag[r];
+      acc += ((double)stat_m[r] - dg) + (double)logf(stat_l[r]);
+      acc += ((double)stat_m[V + r] - dg) + (double)logf(stat_l[V + r]);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+      __syncthreads();
+    }
+    const double lk = sh[0] / (2.0 * (double)n);
+    if (threadIdx.x == 0) loss[k] = (float)lk;
+    total += lk;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[n_prob] = (float)total;
+}
+
+// finish_rows_v4 for the stacked members of a group: the gradient of member m's normalised rows is the sum of the slabs of
+// every virtual problem in which m was the resident operand (its X sides and its Y sides), times the splits -- summed here
+// in fixed order, followed by the row dots and the normalise backward as in finish_rows.  grid = (ceil(n_pad / 8), members).
+//   ds_part[m][block] = sum over the block's rows of <xhat_i, g_i>   (every pair's sum G.S appears once per side: halve)
+//   sq_part[m][block] = sum over the block's rows of |dx_i|^2        (the embeddings' share of a gradient norm)
+constexpr int FG_MEMBERS = 4, FG_CONTRIB = 8;
+struct FinishGroup {
+  int n_contrib[FG_MEMBERS];
+  int vprob[FG_MEMBERS][FG_CONTRIB];   // virtual problems whose resident rows are member m
+  long long n_pad, n_valid;
+};
+template <typename TC, typename TI, typename TO>
+__global__ void finish_rows_group(const float* __restrict__ parts, int n_split, int64_t slab, FinishGroup fg,
+                                  const TC* __restrict__ xc, const TI* __restrict__ xo, const float* __restrict__ rinv,
+                                  int d, TO* __restrict__ dx, float* __restrict__ ds_part, float* __restrict__ sq_part) {
+  extern __shared__ __align__(16) float g4_sh[];   // [8][d]
+  __shared__ float dot_sh[8], sq_sh[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m = blockIdx.y;
+  const int64_t row_m = (int64_t)blockIdx.x * 8 + w;       // row within the member
+  const int64_t row = (int64_t)m * fg.n_pad + row_m;       // stack row
+  float* g = g4_sh + (size_t)w * d;
+  float dot_c = 0.f, sq = 0.f;
+  if (row_m < fg.n_valid) {
+    const float ri = rinv[row];
+    const TC* xcr = xc + row * d;
+    const TI* xor_ = xo + row * d;
+    const bool same = reinterpret_cast<const void*>(xc) == reinterpret_cast<const void*>(xo);
+    const int nc = fg.n_contrib[m];
+    float dot_o = 0.f;
+    for (int k = lane * 4; k < d; k += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < nc; ++c) {
+        const float* pr = parts + ((int64_t)fg.vprob[m][c] * fg.n_pad + row_m) * d + k;
+#pragma unroll 4
+        for (int s = 0; s < n_split; ++s) {
+          const float4 v = ld4_f(pr + (int64_t)s * slab);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      *reinterpret_cast<float4*>(g + k) = acc;
+      const float4 vc = ld4_f(xcr + k);
+      dot_c = fmaf(vc.x, acc.x, dot_c); dot_c = fmaf(vc.y, acc.y, dot_c);
+      dot_c = fmaf(vc.z, acc.z, dot_c); dot_c = fmaf(vc.w, acc.w, dot_c);
+      if (!same) {
+        const float4 vo = ld4_f(xor_ + k);
+        dot_o = fmaf(vo.x, acc.x, dot_o); dot_o = fmaf(vo.y, acc.y, dot_o);
+        dot_o = fmaf(vo.z, acc.z, dot_o); dot_o = fmaf(vo.w, acc.w, dot_o);
+      }
+    }
+    dot_c = warp_sum(dot_c) * ri;
+    dot_o = same ? dot_c : warp_sum(dot_o) * ri;
+    if (ri >= 0.5f / kNormEps) dot_o = 0.f;
+    for (int k = lane * 4; k < d; k += 128) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + k);
+      const float4 xv = ld4_f(xor_ + k);
+      float4 o;
+      o.x = (gv.x - xv.x * ri * dot_o) * ri;
+      o.y = (gv.y - xv.y * ri * dot_o) * ri;
+      o.z = (gv.z - xv.z * ri * dot_o) * ri;
+      o.w = (gv.w - xv.w * ri * dot_o) * ri;
+      sq = fmaf(o.x, o.x, sq); sq = fmaf(o.y, o.y, sq); sq = fmaf(o.z, o.z, sq); sq = fmaf(o.w, o.w, sq);
+      st4_f(dx + row * d + k, o);
+    }
+    sq = warp_sum(sq);
+  }
+  if (lane == 0) { dot_sh[w] = dot_c; sq_sh[w] = sq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t o = (int64_t)m * gridDim.x + blockIdx.x;
+    ds_part[o] = ((dot_sh[0] + dot_sh[1]) + (dot_sh[2] + dot_sh[3])) + ((dot_sh[4] + dot_sh[5]) + (dot_sh[6] + dot_sh[7]));
+    sq_part[o] = ((sq_sh[0] + sq_sh[1]) + (sq_sh[2] + sq_sh[3])) + ((sq_sh[4] + sq_sh[5]) + (sq_sh[6] + sq_sh[7]));
+  }
+}
+
+// block 0: *d_scale_sum += 0.5 sum ds_part[all];  block 1 + m: sumsq[m] = sum sq_part[m][:]   (fp64, fixed-order tree)
+__global__ void reduce_group_scalars(const float* __restrict__ ds_part, const float* __restrict__ sq_part, int n_members,
+                                     int n_blk, float* __restrict__ d_scale_sum, float* __restrict__ sumsq) {
+  __shared__ double sh[256];
+  const int b = blockIdx.x;
+  const float* src = b == 0 ? ds_part : sq_part + (int64_t)(b - 1) * n_blk;
+  const int cnt = b == 0 ? n_members * n_blk : n_blk;
+  if ((b == 0 && d_scale_sum == nullptr) || (b > 0 && sumsq == nullptr)) return;
+  double acc = 0.0;
+  for (int p = threadIdx.x; p < cnt; p += 256) acc += (double)src[p];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (b == 0) d_scale_sum[0] += (float)(0.5 * sh[0]);
+    else sumsq[b - 1] = (float)sh[0];
+  }
+}
+
 }  // namespace aux

@@ -65,6 +65,41 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Several independent (X, Y) problems of equal shape in ONE launch (the tri-modal model's three pairs -- and, for the
+// backward, both sides of each: tf_clip_codes (1).ipynb:13152-13165).  All operands are members of one stacked matrix
+// [n_members][n_pad, d]; the launch sweeps a block-diagonal VIRTUAL problem: problem k owns the virtual rows and columns
+// [k n_pad, k n_pad + n_valid), its row blocks visit its own column steps only.  Statistics and gradients are indexed by
+// virtual row / column; operand rows (and their 1/norms) by virtual index + shift.
+constexpr int MAX_GROUP = 8;
+struct Group {
+  int n_prob;            // 0: one problem, plain indexing
+  int pairs_per_prob;    // row blocks (CTA pairs) per problem
+  int steps_per_prob;    // 256-column steps per problem: n_pad / 256
+  int n_valid;           // rows (= columns) of every problem
+  int xshift[MAX_GROUP];   // stack row of the resident operand minus virtual row
+  int yshift[MAX_GROUP];   // stack row of the streamed operand minus virtual column
+  int cshift[MAX_GROUP];   // backward: index of a column's statistics minus virtual column
+  const float* gscale;     // backward: optional DEVICE [n_prob] upstream gradient per problem (problem k reads gscale[k % gmod])
+  int gmod;
+  int stack_rows;          // host: rows of the stacked operand matrix (extent of the tensor maps)
+};
+struct GroupView {   // what one work item needs of it
+  int t_lo, t_hi, xs, ys, cs, n_rows, n_cols, k;
+};
+__device__ __forceinline__ GroupView group_view(const Group& g, int pair_block, int n_steps, int n_rows, int n_cols) {
+  GroupView v;
+  if (g.n_prob == 0) {
+    v.t_lo = 0; v.t_hi = n_steps; v.xs = v.ys = v.cs = 0; v.n_rows = n_rows; v.n_cols = n_cols; v.k = 0;
+  } else {
+    v.k = pair_block / g.pairs_per_prob;
+    v.t_lo = v.k * g.steps_per_prob;
+    v.t_hi = v.t_lo + g.steps_per_prob;
+    v.xs = g.xshift[v.k]; v.ys = g.yshift[v.k]; v.cs = g.cshift[v.k];
+    v.n_rows = v.n_cols = v.t_lo * STEP_J + g.n_valid;
+  }
+  return v;
+}
+
 // ===================================================================================================== backward
 constexpr int BWD_EPI_WARPS = 8;
 constexpr int BWD_THREADS = 32 * (4 + BWD_EPI_WARPS);
@@ -91,6 +126,7 @@ struct BwdParams {
   const float* col_m_in;   // or nullptr (with col_w)
   const float* col_w;
   float* dx;               // [n_split][n_rows, d] f32 (summed over the splits by aux::sum_splits when n_split > 1)
+  Group grp;               // several problems in one launch (n_prob = 0: one)
 };
 
 __host__ __device__ constexpr int bwd_smem_bytes(int nkc, int stages) {
@@ -117,8 +153,9 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
   const int item = blockIdx.x >> 1;
   const int split = item / p.n_pairs;
   const int i0 = (item % p.n_pairs) * (2 * BWD_ROWS) + (int)rank * BWD_ROWS;   // first resident row of this CTA
-  const int t_begin = split * p.split_steps;
-  const int n_t = min(p.n_steps, t_begin + p.split_steps) - t_begin;          // steps of this work item
+  const GroupView gv = group_view(p.grp, item % p.n_pairs, p.n_steps, p.n_rows, p.n_cols);
+  const int t_begin = gv.t_lo + split * p.split_steps;
+  const int n_t = min(gv.t_hi, t_begin + p.split_steps) - t_begin;            // steps of this work item
 
   const uint32_t x_smem = base;
   const uint32_t g_smem = x_smem + p.nkc * BWD_X_CHUNK;
@@ -133,7 +170,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
   const int S_COL0 = TMEM_COLS - 128 * p.nsbuf;
   const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;   // s
   const float k2 = sc * LOG2E;                                                // s log2(e)
-  const float out_scale = p.grad_out * sc;
+  const float out_scale = p.grad_out * sc * (p.grp.gscale != nullptr ? __ldg(p.grp.gscale + gv.k % p.grp.gmod) : 1.f);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
@@ -176,7 +213,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     if (ptx::elect_one()) {
       if (leader) ptx::mbar_arrive_expect_tx(bar(B_XFULL), 2 * p.nkc * BWD_X_CHUNK);
       for (int kc = 0; kc < p.nkc; ++kc)
-        ptx::tma_load_2d_pair(x_smem + kc * BWD_X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0);
+        ptx::tma_load_2d_pair(x_smem + kc * BWD_X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0 + gv.xs);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < n_t; ++t) {
@@ -184,7 +221,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
           ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
           if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
           ptx::tma_load_2d_pair(ring_a + stage * STAGE_BYTES, &tmap_y, bar(B_FULL_A + stage), g * 64,
-                                (t_begin + t) * STEP_J + (int)rank * 128);
+                                (t_begin + t) * STEP_J + (int)rank * 128 + gv.ys);
           if (++stage == p.stages_a) { stage = 0; phase ^= 1u; }
         }
       }
@@ -205,7 +242,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
             if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_B + stage), 2 * ngr * 8192);
             for (int gi = 0; gi < ngr; ++gi)
               ptx::tma_load_2d_pair(ring_b + stage * STAGE_BYTES + gi * 8192, &tmap_yg, bar(B_FULL_B + stage),
-                                    256 * q + half * (int)rank + 64 * gi, (t_begin + t) * STEP_J + 64 * kc);
+                                    256 * q + half * (int)rank + 64 * gi, (t_begin + t) * STEP_J + 64 * kc + gv.ys);
             if (++stage == p.stages_b) { stage = 0; phase ^= 1u; }
           }
         }
@@ -279,12 +316,12 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
     const int jh = q >> 1;             // 2x2 layout: lanes 64..127 hold columns 128..255 of the step
     const int i_local = 32 * (q & 1) + lane;
     const long long i_glob = (long long)i0 + i_local;
-    const bool row_ok = i_glob < p.n_rows;
+    const bool row_ok = i_glob < gv.n_rows;
     const int te = threadIdx.x - 128;  // 0..255: the step column this thread stages
     const int jl0 = 128 * jh + 64 * h; // first step-local column of this thread == 64 * kc
     const int kc = 2 * jh + h;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float rx = row_ok ? p.rinv_x[i_glob] : 0.f;
+    const float rx = row_ok ? p.rinv_x[i_glob + gv.xs] : 0.f;
     // u_i = row_w_i exp(s - row_m_i): exp(S - s) u_i = exp(S - row_m_i) row_w_i from ONE ex2 per logit
     const float u = (!TWO_EXP && row_ok) ? p.row_w[i_glob] * ex2((sc - p.row_m_in[i_glob]) * LOG2E) : 0.f;
     const float rm2 = (TWO_EXP && row_ok) ? p.row_m_in[i_glob] * LOG2E : 0.f;   // TWO_EXP: exp(S - m_i) w_i directly
@@ -297,10 +334,10 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64 k, 64 ro
 
     auto load_col = [&](int t, float& cw, float& cm, float& ry) {   // t: step local to this work item
       const long long jn = (long long)(t_begin + t) * STEP_J + te;
-      const bool ok = t < n_t && jn < p.n_cols;
-      cw = (ok && p.col_w != nullptr) ? p.col_w[jn] : 0.f;
-      cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn] : (TWO_EXP ? 0.f : sc);
-      ry = ok ? p.rinv_y[jn] : 0.f;
+      const bool ok = t < n_t && jn < gv.n_cols;
+      cw = (ok && p.col_w != nullptr) ? p.col_w[jn + gv.cs] : 0.f;
+      cm = (ok && p.col_w != nullptr) ? p.col_m_in[jn + gv.cs] : (TWO_EXP ? 0.f : sc);
+      ry = ok ? p.rinv_y[jn + gv.ys] : 0.f;
       if (TWO_EXP && !(cw > 0.f)) cm = 0.f;   // weight 0 (extra negative columns: sum = +inf): keep the exponent finite
     };
     float cw_n, cm_n, ry_n;
@@ -441,6 +478,8 @@ struct FwdParams {
   int* row_thr;       // [n_rows] order-preserving int key of a lower bound on each row's final K-th best score, shared
                       // by all work items of the row through atomicMax (initialised to a very negative key)
   long long col_offset;
+  Group grp;          // MODE 0 / 2: several problems in one launch (n_prob = 0: one); the column-partial matrix then has
+                      // 2 * pairs_per_prob rows (the problems own disjoint column ranges)
 };
 
 __host__ __device__ constexpr int fwd_smem_bytes(int rows, int nkc, int stages) {
@@ -478,9 +517,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
   const int item = blockIdx.x >> 1;
   const int split = item / p.n_pairs;
   const int i0 = (item % p.n_pairs) * (2 * ROWS) + (int)rank * ROWS;
-  const int t_begin = split * p.split_steps;
-  const int t_end = min(p.n_steps, t_begin + p.split_steps);
-  const int col_row = 2 * (item % p.n_pairs) + (int)rank;   // this CTA's row of the column-partial matrix
+  const GroupView gv = group_view(p.grp, item % p.n_pairs, p.n_steps, p.n_rows, p.n_cols);
+  const int t_begin = gv.t_lo + split * p.split_steps;
+  const int t_end = min(gv.t_hi, t_begin + p.split_steps);
+  // this CTA's row of the column-partial matrix
+  const int col_row = 2 * (p.grp.n_prob ? (item % p.n_pairs) % p.grp.pairs_per_prob : item % p.n_pairs) + (int)rank;
   const float k2 = (p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale) * LOG2E;
 
   const uint32_t x_smem = base;
@@ -521,7 +562,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
     if (ptx::elect_one()) {
       if (leader) ptx::mbar_arrive_expect_tx(bar(B_XFULL), 2 * p.nkc * X_CHUNK);
       for (int kc = 0; kc < p.nkc; ++kc)
-        ptx::tma_load_2d_pair(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0);
+        ptx::tma_load_2d_pair(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0 + gv.xs);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -529,7 +570,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
           ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
           if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
           ptx::tma_load_2d_pair(ring_a + stage * STAGE_BYTES, &tmap_y, bar(B_FULL_A + stage), g * 64,
-                                t * STEP_J + (int)rank * 128);
+                                t * STEP_J + (int)rank * 128 + gv.ys);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -682,12 +723,12 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
     const int cgp = e >> 2;
     const int i_local = ROWS == 128 ? 32 * q + lane : 32 * (q & 1) + lane;
     const long long i_glob = (long long)i0 + i_local;
-    const bool row_ok = i_glob < p.n_rows;
+    const bool row_ok = i_glob < gv.n_rows;
     const int col0 = (ROWS == 128 ? 64 : 32) * cgp;
     const int jl0 = (ROWS == 128 ? 0 : 128 * (q >> 1)) + col0;
     const int te = threadIdx.x - 128;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float rx = row_ok ? p.rinv_x[i_glob] : 0.f;
+    const float rx = row_ok ? p.rinv_x[i_glob + gv.xs] : 0.f;
     const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
     const long long dcol0 = i_glob + p.diag_offset;
     float m_run = -1e30f, l_run = 0.f;   // base-2 units: S log2(e)
@@ -695,7 +736,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
     float ry_n = 0.f;
     if (te < STEP_J) {
       const long long j = (long long)t_begin * STEP_J + te;
-      ry_n = (j < p.n_cols) ? p.rinv_y[j] : -1.f;
+      ry_n = (j < gv.n_cols) ? p.rinv_y[j + gv.ys] : -1.f;
     }
     for (int t = t_begin; t < t_end; ++t) {
       const int tl = t - t_begin;
@@ -705,7 +746,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         cv[te] = ry_n < 0.f ? 0.f : ry_n * k2;
         cv[256 + te] = ry_n < 0.f ? -INFINITY : 0.f;   // columns past the end never enter a maximum or a sum
         const long long jn = (long long)(t + 1) * STEP_J + te;
-        ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
+        ry_n = (t + 1 < t_end && jn < gv.n_cols) ? p.rinv_y[jn + gv.ys] : -1.f;
       }
       named_bar_sync(1, EPI_THREADS);
       ptx::mbar_wait(bar(B_SFULL + sb), (tl >> 1) & 1);
@@ -768,7 +809,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         const bool mine = ROWS == 128 ? ((w & 3) == rq) : ((w & 1) == rq);
         if (mine) tot += rowred[w * 32 + rl] * ex2(rowred_m[w * 32 + rl] - mm);
       }
-      if ((long long)i0 + te < p.n_rows) {
+      if ((long long)i0 + te < gv.n_rows) {
         p.row_part_m[(long long)split * p.n_rows + i0 + te] = mm * LN2;
         p.row_part[(long long)split * p.n_rows + i0 + te] = tot;
       }
@@ -780,14 +821,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
     const int cgp = e >> 2;            // column group of this warp
     const int i_local = ROWS == 128 ? 32 * q + lane : 32 * (q & 1) + lane;
     const long long i_glob = (long long)i0 + i_local;
-    const bool row_ok = i_glob < p.n_rows;
-    const bool warp_rows_ok = (long long)i0 + (i_local - lane) + 32 <= p.n_rows;   // warp-uniform
+    const bool row_ok = i_glob < gv.n_rows;
+    const bool warp_rows_ok = (long long)i0 + (i_local - lane) + 32 <= gv.n_rows;   // warp-uniform
     const int col0 = (ROWS == 128 ? 64 : 32) * cgp;                 // first TMEM column of this warp
     const int jl0 = (ROWS == 128 ? 0 : 128 * (q >> 1)) + col0;      // its step-local column
     const int slot = ROWS == 128 ? q : (q & 1);
     const int te = threadIdx.x - 128;  // 0..511
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float rx = row_ok ? p.rinv_x[i_glob] : 0.f;
+    const float rx = row_ok ? p.rinv_x[i_glob + gv.xs] : 0.f;
     const uint32_t sempty_leader = ptx::mapa(bar(B_SEMPTY), 0);
     const long long dcol0 = i_glob + p.diag_offset;
     float rsum = 0.f;
@@ -804,7 +845,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
     float ry_n = 0.f;
     if (te < STEP_J) {   // -1 marks a column past the end
       const long long j = (long long)t_begin * STEP_J + te;
-      ry_n = (j < p.n_cols) ? p.rinv_y[j] : -1.f;
+      ry_n = (j < gv.n_cols) ? p.rinv_y[j + gv.ys] : -1.f;
     }
     for (int t = t_begin; t < t_end; ++t) {
       const int tl = t - t_begin;
@@ -814,7 +855,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         cv[te] = ry_n < 0.f ? 0.f : ry_n * k2;
         cv[256 + te] = ry_n < 0.f ? -10000.f : -k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
         const long long jn = (long long)(t + 1) * STEP_J + te;
-        ry_n = (t + 1 < t_end && jn < p.n_cols) ? p.rinv_y[jn] : -1.f;
+        ry_n = (t + 1 < t_end && jn < gv.n_cols) ? p.rinv_y[jn + gv.ys] : -1.f;
       }
       named_bar_sync(1, EPI_THREADS);
       if (t > t_begin) flush_cols(t - 1);
@@ -875,7 +916,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         const bool mine = ROWS == 128 ? ((w & 3) == rq) : ((w & 1) == rq);
         if (mine) tot += rowred[w * 32 + rl];
       }
-      if ((long long)i0 + te < p.n_rows) p.row_part[(long long)split * p.n_rows + i0 + te] = tot;
+      if ((long long)i0 + te < gv.n_rows) p.row_part[(long long)split * p.n_rows + i0 + te] = tot;
     }
   }
 

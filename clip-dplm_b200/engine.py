@@ -283,6 +283,71 @@ class CudaEngine:
                                                  _p(grad_scale), n, d, _p(dx), _DT[out_dtype], _stream()), "finish_slots")
         return dx
 
+    # ------------------------------------------------------------------ several pair problems in one launch
+    def group_bytes(self, n_members, n_prob, n, d, dtype, scale, flags=0):
+        """Workspace of `group_forward` / `group_backward`; 0 = the group is not served (issue the problems one by one)."""
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.clipnce_group_workspace_bytes(n_members, n_prob, n, d, _DT[dtype], float(scale), flags,
+                                                          ctypes.byref(nbytes)), "group_workspace_bytes")
+        return nbytes.value
+
+    def _group_ws(self, n_members, n_prob, n, d, dtype, scale, flags, dev):
+        nbytes = self.group_bytes(n_members, n_prob, n, d, dtype, scale, flags)
+        if nbytes == 0:
+            raise RuntimeError("clip_dplm_b200: the grouped launch does not serve this shape")
+        key = ("group", n_members, n_prob, n, d, dtype, flags, dev, torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
+        return ws
+
+    @staticmethod
+    def _members(x_member, y_member):
+        k = len(x_member)
+        return (ctypes.c_int * k)(*x_member), (ctypes.c_int * k)(*y_member)
+
+    @_guard
+    def group_forward(self, stack, rinv, n_members, x_member, y_member, n, scale, flags=0, scale_dev=None):
+        """Forward statistics and losses of len(x_member) pair problems over the members of ``stack`` [n_members*n_pad, d]
+        (clipnce_group_forward) -> stat_m, stat_l [2, n_prob*n_pad], diag [n_prob*n_pad], loss [n_prob + 1]."""
+        self._chk(stack, (torch.bfloat16,), "stack")
+        d = stack.shape[1]
+        n_prob = len(x_member)
+        n_pad = stack.shape[0] // n_members
+        dev = stack.device
+        ws = self._group_ws(n_members, n_prob, n, d, stack.dtype, scale, flags, dev)
+        stat_m = torch.empty((2, n_prob * n_pad), dtype=torch.float32, device=dev)
+        stat_l = torch.empty((2, n_prob * n_pad), dtype=torch.float32, device=dev)
+        diag = torch.empty(n_prob * n_pad, dtype=torch.float32, device=dev)
+        loss = torch.empty(n_prob + 1, dtype=torch.float32, device=dev)
+        xm, ym = self._members(x_member, y_member)
+        _lib.check(self.lib.clipnce_group_forward(_p(stack), _p(rinv), n_members, n_prob, xm, ym, n, d, float(scale),
+                                                  _p(scale_dev), _DT[stack.dtype], flags, _p(stat_m), _p(stat_l), _p(diag),
+                                                  _p(loss), _p(ws), ws.numel(), _stream()), "group_forward")
+        return stat_m, stat_l, diag, loss
+
+    @_guard
+    def group_backward(self, stack, rinv, n_members, x_member, y_member, n, scale, stat_m, stat_l, stack_orig, out_dtype,
+                       grad_scale=None, flags=0, scale_dev=None, want_dscale=True, want_sumsq=True):
+        """Both backward sides of every problem in one sweep launch + one finishing pass (clipnce_group_backward)
+        -> d_stack [n_members*n_pad, d] in ``out_dtype``, d_scale_sum [1] or None, grad_sumsq [n_members] or None."""
+        d = stack.shape[1]
+        n_prob = len(x_member)
+        dev = stack.device
+        ws = self._group_ws(n_members, n_prob, n, d, stack.dtype, scale, flags, dev)
+        d_stack = torch.zeros(stack.shape, dtype=out_dtype, device=dev) if n % 256 else \
+            torch.empty(stack.shape, dtype=out_dtype, device=dev)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+        sq = torch.empty(n_members, dtype=torch.float32, device=dev) if want_sumsq else None
+        so = stack if stack_orig.dtype == stack.dtype else stack_orig
+        xm, ym = self._members(x_member, y_member)
+        _lib.check(self.lib.clipnce_group_backward(_p(stack), _p(rinv), n_members, n_prob, xm, ym, n, d, float(scale),
+                                                   _p(scale_dev), _p(stat_m), _p(stat_l), _DT[stack.dtype], flags, _p(so),
+                                                   _DT[so.dtype], _p(grad_scale), _p(d_stack), _DT[out_dtype], _p(ds), _p(sq),
+                                                   _p(ws), ws.numel(), _stream()), "group_backward")
+        return d_stack, ds, sq
+
     @_guard
     def softmax_weights(self, l, coef):
         out = torch.empty_like(l)

@@ -223,3 +223,111 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
     if return_stats:
         return loss, {"row_lse": row_lse, "col_lse": col_lse, "diag": diag}
     return loss
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# several pair problems over shared members in one launch per kernel (the tri-modal model)
+# ------------------------------------------------------------------------------------------------------------------------
+GROUP_MAX_ROWS = 16384    # from here on a single pair fills the GPU and has the two-sided backward: issue the pairs one by one
+
+
+class _GroupedClipLoss(torch.autograd.Function):
+    """losses[k] = symmetric InfoNCE of (members[x_member[k]], members[y_member[k]]), losses[-1] = their sum, all sharing
+    one logit scale (tf_clip_codes (1).ipynb:13146-13165).  One normalise launch over the stacked members, one forward
+    sweep, one backward sweep over both sides of every problem, one finishing pass (clipnce_group_*)."""
+
+    @staticmethod
+    def forward(ctx, logit_scale, scale_is_log, clamp_max, x_member, y_member, engine, holder, grad_mode, *members):
+        n, d = members[0].shape
+        n_members, n_prob = len(members), len(x_member)
+        n_pad = (n + 255) // 256 * 256
+        dev = members[0].device
+        if n_pad == n:
+            stack_orig = torch.cat([m.detach() for m in members], dim=0)
+        else:
+            stack_orig = torch.zeros((n_members * n_pad, d), dtype=members[0].dtype, device=dev)
+            for i, m in enumerate(members):
+                stack_orig[i * n_pad:i * n_pad + n] = m.detach()
+        stack = stack_orig if stack_orig.dtype == torch.bfloat16 else stack_orig.to(torch.bfloat16)
+        rinv, _ = engine.normalize(stack_orig)
+        s_dev = raw_dev = None
+        info = None
+        if torch.is_tensor(logit_scale) and logit_scale.is_cuda:
+            t_dev = logit_scale.detach().to(torch.float32).reshape(1)
+            raw_dev = t_dev.exp() if scale_is_log else t_dev.clone()
+            s_dev = raw_dev.clamp(max=float(clamp_max)) if clamp_max is not None else raw_dev
+            hint = _ScaleHint.get(logit_scale, s_dev) * 1.05
+            scale = min(hint, float(clamp_max)) if clamp_max is not None else hint
+        else:
+            info = _scale_value(logit_scale, scale_is_log, clamp_max)
+            scale = info[1]
+        kw = {"scale_dev": s_dev} if s_dev is not None else {}
+        stat_m, stat_l, _diag, loss = engine.group_forward(stack, rinv, n_members, x_member, y_member, n, scale, **kw)
+        need_grad = grad_mode and (any(m.requires_grad for m in members) or
+                                   (torch.is_tensor(logit_scale) and logit_scale.requires_grad))
+        if need_grad:
+            ctx.saved = (stack, stack_orig, rinv, stat_m, stat_l, scale, s_dev, raw_dev, info)
+        ctx.meta = (n, n_pad, n_members, tuple(x_member), tuple(y_member), scale_is_log, clamp_max, engine, holder,
+                    (logit_scale.dtype, logit_scale.device) if torch.is_tensor(logit_scale) else None,
+                    tuple(m.dtype for m in members))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        n, n_pad, n_members, x_member, y_member, scale_is_log, clamp_max, engine, holder, ls_meta, dtypes = ctx.meta
+        stack, stack_orig, rinv, stat_m, stat_l, scale, s_dev, raw_dev, info = ctx.saved
+        ctx.saved = None
+        n_prob = len(x_member)
+        g = g.to(torch.float32)
+        gs = (g[:n_prob] + g[n_prob]).contiguous()     # every problem's loss also feeds the sum
+        kw = {"scale_dev": s_dev} if s_dev is not None else {}
+        d_stack, ds, sq = engine.group_backward(stack, rinv, n_members, x_member, y_member, n, scale, stat_m, stat_l,
+                                                stack_orig, stack_orig.dtype, grad_scale=gs, **kw)
+        if holder is not None:
+            holder["embed_grad_sumsq"] = sq
+        d_ls = None
+        if ls_meta is not None and ctx.needs_input_grad[0]:
+            if s_dev is not None:     # ds already carries the upstream gradients
+                dd = ds if scale_is_log else ds / s_dev
+                if clamp_max is not None:
+                    dd = torch.where(raw_dev > float(clamp_max), torch.zeros_like(dd), dd)
+                d_ls = dd.reshape(()).to(dtype=ls_meta[0])
+            elif info[2]:
+                d_ls = torch.zeros((), dtype=ls_meta[0], device=ls_meta[1])
+            else:
+                d_ls = (ds * (1.0 if scale_is_log else 1.0 / info[1])).reshape(()).to(device=ls_meta[1], dtype=ls_meta[0])
+        grads = tuple(d_stack[i * n_pad:i * n_pad + n] if ctx.needs_input_grad[8 + i] else None for i in range(n_members))
+        return (d_ls, None, None, None, None, None, None, None) + grads
+
+
+def fused_clip_loss_group(members, x_member, y_member, logit_scale, *, scale_is_log: bool = True,
+                          clamp_max: Optional[float] = None, holder=None, engine=None):
+    """Symmetric InfoNCE losses of several pairs over shared embeddings, one launch per kernel for the whole group.
+
+    members     sequence of [N,d] CUDA embeddings of one dtype (bf16, or fp32/fp16 computed in bf16), un-normalised
+    x_member / y_member   problem k pairs members[x_member[k]] (rows) with members[y_member[k]] (columns)
+    Returns a [n_prob + 1] tensor (the problems' losses, then their sum), or ``None`` when the grouped launch does not
+    serve the shapes (use one `fused_clip_loss` per pair).  ``holder`` (a dict) receives ``embed_grad_sumsq`` -- the
+    squared gradient norm of every member, [n_members] f32 -- when the backward runs."""
+    members = [m.to(torch.bfloat16) if m.dtype == torch.float16 else m for m in members]
+    m0 = members[0]
+    if m0.dim() != 2 or not m0.is_cuda:
+        return None
+    engine = engine or default_engine()
+    if not hasattr(engine, "group_forward"):
+        return None
+    if any((not m.is_cuda) or m.shape != m0.shape or m.dtype != m0.dtype or m.device != m0.device for m in members):
+        return None
+    if m0.dtype not in (torch.bfloat16, torch.float32) or m0.shape[0] >= GROUP_MAX_ROWS:
+        return None
+    if m0.dtype == torch.float32 and not torch.is_autocast_enabled():
+        return None     # fp32 rows outside autocast are computed exactly (the reference's numerics): no tensor-core group
+    n, d = m0.shape
+    if torch.is_tensor(logit_scale) and logit_scale.is_cuda:
+        probe = 14.0    # family 1 and 2 serve the same shapes: any positive scale answers "is the group served"
+    else:
+        probe = _scale_value(logit_scale, scale_is_log, clamp_max)[1]
+    if engine.group_bytes(len(members), len(x_member), n, d, torch.bfloat16, probe, 0) == 0:
+        return None
+    return _GroupedClipLoss.apply(logit_scale, scale_is_log, clamp_max, list(x_member), list(y_member), engine, holder,
+                                  torch.is_grad_enabled(), *members)

@@ -31,7 +31,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from .engine import default_engine
-from .functional import fused_clip_loss
+from .functional import fused_clip_loss, fused_clip_loss_group
 
 LOGIT_SCALE_INIT = math.log(1.0 / 0.07)   # 2.6592 (run1/configuration_hybrid_clip.py:100)
 
@@ -398,18 +398,27 @@ def trimodal_contrastive_losses(cell_embed, pert_embed, protein_embed, logit_sca
     # every embedding is an operand of two pairs: its row norms are taken ONCE (or arrive with it from the fused head
     # tail) and handed to both pair steps; the normalised copies of the reference's output dict are formed on demand
     embs = (cell_embed, pert_embed, protein_embed)
-    if all(e.is_cuda for e in embs):
-        eng = default_engine()
-        rinv = [getattr(e, "_clipnce_rinv", None) for e in embs]
-        rinv = [r if r is not None else eng.normalize(e.detach().contiguous() if e.dtype != torch.float16
-                                                      else e.detach().to(torch.bfloat16).contiguous())[0]
-                for r, e in zip(rinv, embs)]
+    # one launch per kernel for the three pairs where the kernels serve the shapes (functional.fused_clip_loss_group):
+    # one normalise pass over the stacked embeddings, one forward sweep, one backward sweep over all six sides
+    holder = {}
+    losses = fused_clip_loss_group(embs, (0, 0, 1), (1, 2, 2), logit_scale, holder=holder)
+    if losses is not None:
+        out = LazyOutputs({"loss": losses[3], "cell_pert_loss": losses[0], "cell_protein_loss": losses[1],
+                           "pert_protein_loss": losses[2]})
+        out.grad_info = holder      # after backward: holder["embed_grad_sumsq"] = |d cell|^2, |d pert|^2, |d protein|^2
     else:
-        rinv = [None, None, None]
-    cp = fused_clip_loss(cell_embed, pert_embed, logit_scale, rinv_a=rinv[0], rinv_b=rinv[1])
-    cq = fused_clip_loss(cell_embed, protein_embed, logit_scale, rinv_a=rinv[0], rinv_b=rinv[2])
-    pq = fused_clip_loss(pert_embed, protein_embed, logit_scale, rinv_a=rinv[1], rinv_b=rinv[2])
-    out = LazyOutputs({"loss": cp + cq + pq, "cell_pert_loss": cp, "cell_protein_loss": cq, "pert_protein_loss": pq})
+        if all(e.is_cuda for e in embs):
+            eng = default_engine()
+            rinv = [getattr(e, "_clipnce_rinv", None) for e in embs]
+            rinv = [r if r is not None else eng.normalize(e.detach().contiguous() if e.dtype != torch.float16
+                                                          else e.detach().to(torch.bfloat16).contiguous())[0]
+                    for r, e in zip(rinv, embs)]
+        else:
+            rinv = [None, None, None]
+        cp = fused_clip_loss(cell_embed, pert_embed, logit_scale, rinv_a=rinv[0], rinv_b=rinv[1])
+        cq = fused_clip_loss(cell_embed, protein_embed, logit_scale, rinv_a=rinv[0], rinv_b=rinv[2])
+        pq = fused_clip_loss(pert_embed, protein_embed, logit_scale, rinv_a=rinv[1], rinv_b=rinv[2])
+        out = LazyOutputs({"loss": cp + cq + pq, "cell_pert_loss": cp, "cell_protein_loss": cq, "pert_protein_loss": pq})
     out.lazy("cell_embed", lambda: fused_normalize(cell_embed))
     out.lazy("pert_embed", lambda: fused_normalize(pert_embed))
     out.lazy("protein_embed", lambda: fused_normalize(protein_embed))

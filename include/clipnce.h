@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 106
+#define CLIPNCE_VERSION 107
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -228,6 +228,41 @@ int clipnce_finish_sharded(const void* x, const void* x_orig, const float* rinv_
 int clipnce_finish_slots(const float* slots, int n_slots, const void* x, int dtype, const void* x_orig, int in_dtype,
                          const float* rinv, const float* grad_scale, int64_t n, int64_t d, void* dx, int out_dtype,
                          void* stream);
+
+/*
+ * Several pair problems of equal shape as ONE launch per kernel: the tri-modal model, whose three symmetric InfoNCE losses
+ * (cell, pert), (cell, protein), (pert, protein) share one logit_scale and whose every embedding is an operand of two pairs
+ *   current/tf_clip_codes (1).ipynb:13146-13165      (three matmul * logit_scale, six cross_entropy, summed)
+ * At the batch sizes that model runs at a single pair leaves most of the GPU idle (N = 4096: 16 of 74 CTA-pair slots);
+ * here the problems are the diagonal blocks of one virtual sweep and the backward runs BOTH sides of ALL problems in one
+ * launch, followed by one pass that sums each member's contributions, applies the normalise backward and emits the
+ * squared norm of the embedding gradients (what clip_grad_norm_, rna_clip_codes.ipynb:2076, would otherwise re-read them for).
+ *
+ * stack      [n_members * n_pad, d] bf16: member m's rows at [m n_pad, m n_pad + n), n_pad = n rounded up to 256; the
+ *            padding rows must hold finite values (zeros).  rinv [n_members * n_pad] from ONE clipnce_normalize call.
+ * problem k  rows of member x_member[k] against the rows of member y_member[k] (HOST arrays), k < n_prob <= 4,
+ *            n_members <= 4; positives on the diagonal.
+ * stat_m, stat_l [2][n_prob * n_pad]: row statistics of problem k at [k n_pad + i], column statistics at
+ *            [n_prob n_pad + k n_pad + j] -- (shift, sum) pairs as in clipnce_forward; diag [n_prob * n_pad].
+ * loss       [n_prob + 1]: the mean symmetric loss of every problem and, last, their sum.
+ * clipnce_group_workspace_bytes returns 0 in *out when the group is not served (then issue the problems one by one):
+ * bf16, d % 128 == 0, d <= 768, kernel families 1 and 2, no CLIPNCE_FLAG_UNBOUNDED.
+ */
+int clipnce_group_workspace_bytes(int n_members, int n_prob, int64_t n, int64_t d, int dtype, float scale, int flags,
+                                  size_t* out);
+int clipnce_group_forward(const void* stack, const float* rinv, int n_members, int n_prob, const int* x_member,
+                          const int* y_member, int64_t n, int64_t d, float scale, const float* scale_dev, int dtype,
+                          int flags, float* stat_m, float* stat_l, float* diag, float* loss, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* grad_scale: optional DEVICE [n_prob] upstream gradients of the problems' losses (NULL = 1 each).
+ * d_stack [n_members * n_pad, d] out_dtype: gradient of the caller's rows stack_orig (in_dtype; the stack itself for bf16
+ * rows); rows of the padding are not written.  *d_scale_sum += sum_k grad_scale[k] sum_ij G_ij S_ij (or NULL).
+ * grad_sumsq [n_members] (or NULL): sum over member m's rows of |d_stack row|^2. */
+int clipnce_group_backward(const void* stack, const float* rinv, int n_members, int n_prob, const int* x_member,
+                           const int* y_member, int64_t n, int64_t d, float scale, const float* scale_dev,
+                           const float* stat_m, const float* stat_l, int dtype, int flags, const void* stack_orig,
+                           int in_dtype, const float* grad_scale, void* d_stack, int out_dtype, float* d_scale_sum,
+                           float* grad_sumsq, void* workspace, size_t workspace_bytes, void* stream);
 
 /* w_i = coef / l_i  (l = +inf -> 0).  Builds row_w / col_w from the forward's sums. */
 int clipnce_softmax_weights(const float* l, int64_t n, float coef, float* w, void* stream);

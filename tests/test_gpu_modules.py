@@ -160,3 +160,91 @@ def test_module_with_fused_tail_matches_unfused_module():
     for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         if p2.grad is not None and float(p2.grad.float().norm()) > 0:
             assert rel(p1.grad, p2.grad) <= 6e-2, n1        # two bf16 models: rounding of every intermediate differs
+
+
+# ------------------------------------------------------------------------------------------------ tri-modal grouped launch
+def _tri_inputs(n, d, seed, mixes=(1.0, 0.5, 0.3)):
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(n, d, generator=g)
+    mk = lambda mix: (mix * base + (1.0 - mix) * torch.randn(n, d, generator=g)).bfloat16().float()
+    return tuple(mk(m) for m in mixes)
+
+
+@pytest.mark.parametrize("n,d,t,dtype", [(256, 128, 2.6592, torch.bfloat16), (1000, 512, 2.6592, torch.bfloat16),
+                                         (4096, 512, 2.6592, torch.bfloat16), (777, 768, 2.6592, torch.bfloat16),
+                                         (640, 256, math.log(100.0), torch.bfloat16), (1536, 384, 2.0, torch.float32)])
+def test_trimodal_grouped_launch_matches_three_reference_pairs(n, d, t, dtype):
+    """modules.trimodal_contrastive_losses through the grouped launch (clipnce_group_*: three pairs in one forward sweep,
+    their six backward sides in one sweep, one finishing pass) against three independent evaluations of the reference's
+    loss lines (tf_clip_codes (1).ipynb:13146-13165) in float64 -- losses, all three embedding gradients (each the sum of
+    two pairs' contributions), d logit_scale, with DIFFERENT upstream weights on the three losses and on their sum."""
+    from clip_dplm_b200 import modules as M
+    from clip_dplm_b200 import functional as Fn
+    # at s = 100 weakly correlated members keep the losses (and gradients) away from zero
+    c, p, q = _tri_inputs(n, d, 11 + n, mixes=(1.0, 0.5, 0.3) if t < 4.0 else (1.0, 0.1, 0.05))
+    w = [0.7, 1.3, -0.4, 0.9]     # weights of cell_pert, cell_protein, pert_protein, total
+
+    # reference: float64 autograd on the same bf16-rounded values
+    rc, rp, rq = (x.double().requires_grad_(True) for x in (c, p, q))
+    rt = torch.tensor(t, dtype=torch.float64, requires_grad=True)
+    l_cp, l_cq, l_pq = O.ref_loss(rc, rp, rt), O.ref_loss(rc, rq, rt), O.ref_loss(rp, rq, rt)
+    (w[0] * l_cp + w[1] * l_cq + w[2] * l_pq + w[3] * (l_cp + l_cq + l_pq)).backward()
+
+    embs = [x.cuda().to(dtype).requires_grad_(True) for x in (c, p, q)]
+    ls = torch.tensor(t, device="cuda", requires_grad=True)
+    calls = []
+    orig = Fn._GroupedClipLoss.apply
+    Fn._GroupedClipLoss.apply = staticmethod(lambda *a: (calls.append(1), orig(*a))[1])
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.float32):
+            out = M.trimodal_contrastive_losses(embs[0], embs[1], embs[2], ls)
+    finally:
+        Fn._GroupedClipLoss.apply = orig
+    assert calls, "the grouped launch did not serve this shape"
+    for key, ref in (("cell_pert_loss", l_cp), ("cell_protein_loss", l_cq), ("pert_protein_loss", l_pq),
+                     ("loss", l_cp + l_cq + l_pq)):
+        assert abs(float(out[key]) - float(ref)) <= 1e-3 * abs(float(ref)) + 1e-6, key
+    (w[0] * out["cell_pert_loss"] + w[1] * out["cell_protein_loss"] + w[2] * out["pert_protein_loss"]
+     + w[3] * out["loss"]).backward()
+    torch.cuda.synchronize()
+    for e, r, name in zip(embs, (rc, rp, rq), ("cell", "pert", "protein")):
+        assert e.grad.dtype == dtype and rel(e.grad, r.grad) <= 2e-2, (name, rel(e.grad, r.grad))
+    assert abs(float(ls.grad) - float(rt.grad)) <= 2e-2 * abs(float(rt.grad)) + 1e-5
+    sq = out.grad_info["embed_grad_sumsq"].cpu()
+    for i, e in enumerate(embs):
+        assert abs(float(sq[i]) - float(e.grad.double().pow(2).sum())) <= 2e-2 * float(sq[i])
+    assert rel(out["pert_embed"], torch.nn.functional.normalize(p.double(), dim=-1)) <= 5e-3
+
+
+def test_trimodal_grouped_launch_is_deterministic_and_graph_capturable():
+    from clip_dplm_b200 import modules as M
+    c, p, q = (x.cuda().bfloat16() for x in _tri_inputs(2048, 512, 5))
+    ls = torch.tensor(2.6592, device="cuda", requires_grad=True)
+
+    def step():
+        embs = [x.clone().requires_grad_(True) for x in (c, p, q)]
+        out = M.trimodal_contrastive_losses(*embs, ls)
+        out["loss"].backward()
+        return out["loss"].detach().clone(), [e.grad for e in embs]
+
+    l0, g0 = step()
+    l1, g1 = step()
+    assert torch.equal(l0, l1) and all(torch.equal(a, b) for a, b in zip(g0, g1))
+    # capture: static inputs, one replay = three pairs forward + backward
+    se = [x.clone().requires_grad_(True) for x in (c, p, q)]
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            o = M.trimodal_contrastive_losses(*se, ls)
+            o["loss"].backward()
+    torch.cuda.current_stream().wait_stream(side)
+    for e in se:
+        e.grad = None
+    ls.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o = M.trimodal_contrastive_losses(*se, ls)
+        o["loss"].backward()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o["loss"].detach(), l0) and all(torch.equal(e.grad, g) for e, g in zip(se, g0))
