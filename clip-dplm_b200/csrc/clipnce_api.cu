@@ -72,7 +72,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
-bool g_attr_done[16] = {};
+bool g_attr_done[32] = {};
 
 int get_encode(EncodeTiledFn* out) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -197,10 +197,17 @@ int launch_pair_fwd(int attr_slot, const void* x, const void* y, pair::FwdParams
   return 0;
 }
 
+// 4-CTA clusters with the streamed tiles multicast to both pairs (pair::bwd_body<.., MC>).  Measured on a B200 at
+// N = 65536, d = 512 (tools/run_mc_ab.sh, parity green both ways): 7.43 ms per side against 7.04 ms with 2-CTA clusters --
+// the sweep is bound per SM (shared-memory port), not by L2 output, and 4-CTA clusters leave SMs of the 18-SM GPCs idle.
+// Off unless CLIPNCE_BWD_MC=1.
+bool bwd_mc_enabled() {
+  static const bool on = [] { const char* e = getenv("CLIPNCE_BWD_MC"); return e && atoi(e) != 0; }();
+  return on;
+}
+
 template <bool TWO_EXP>
 int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_t st) {
-  auto kern = pair::bwd_kernel<TWO_EXP>;
-  constexpr int attr_slot = TWO_EXP ? 12 : 6;
   const int total = (pair::SMEM_LIMIT - pair::bwd_smem_bytes(p.nkc, 0)) / pair::STAGE_BYTES;
   if (total < 4) return fail(CLIPNCE_EUNSUPPORTED, "d=%d leaves no room for the TMA rings", p.d);
   auto cap = [](int v) { return v > pair::MAX_STAGES ? pair::MAX_STAGES : v; };
@@ -213,15 +220,33 @@ int launch_pair_bwd(const void* x, const void* y, pair::BwdParams p, cudaStream_
   if ((rc = make_tmap(&tx, x, p.d, x_rows, p.d, pair::BWD_ROWS))) return rc;
   if ((rc = make_tmap(&ty, y, p.d, y_rows, p.d, 128))) return rc;
   if ((rc = make_tmap(&tyg, y, p.d, y_rows, p.d, 64))) return rc;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_attr_done[attr_slot]) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
-      g_attr_done[attr_slot] = true;
-    }
-  }
+  const size_t smem = pair::bwd_smem_bytes(p.nkc, p.stages_a + p.stages_b);
+  // two pairs per cluster share every streamed tile: needs an even number of row blocks (and, grouped, per problem)
+  const bool mc = bwd_mc_enabled() && p.n_pairs % 2 == 0 && (p.grp.n_prob == 0 || p.grp.pairs_per_prob % 2 == 0);
   const int grid = 2 * p.n_pairs * (int)ceil_div(p.n_steps, p.split_steps);
-  kern<<<grid, pair::BWD_THREADS, pair::bwd_smem_bytes(p.nkc, p.stages_a + p.stages_b), st>>>(tx, ty, tyg, p);
+  if (mc) {
+    auto kern = pair::bwd_kernel_mc<TWO_EXP>;
+    constexpr int attr_slot = TWO_EXP ? 21 : 20;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (!g_attr_done[attr_slot]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
+        g_attr_done[attr_slot] = true;
+      }
+    }
+    kern<<<grid, pair::BWD_THREADS, smem, st>>>(tx, ty, tyg, p);
+  } else {
+    auto kern = pair::bwd_kernel<TWO_EXP>;
+    constexpr int attr_slot = TWO_EXP ? 12 : 6;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (!g_attr_done[attr_slot]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT));
+        g_attr_done[attr_slot] = true;
+      }
+    }
+    kern<<<grid, pair::BWD_THREADS, smem, st>>>(tx, ty, tyg, p);
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

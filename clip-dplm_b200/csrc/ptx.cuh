@@ -317,6 +317,21 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_smem, const C
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// The same box multicast into every CTA of the cluster whose bit is set in `mask` (same CTA-relative offset); each
+// destination counts the bytes on ITS pair leader's mbarrier (peer bit cleared, as in tma_load_2d_pair).
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                    uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// commit arriving on the barrier at this offset in the CTAs of `mask`
+__device__ __forceinline__ void mma_commit_pair_mask(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 // arrive on the barrier at this offset in BOTH CTAs once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

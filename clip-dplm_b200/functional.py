@@ -228,7 +228,7 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
 # ------------------------------------------------------------------------------------------------------------------------
 # several pair problems over shared members in one launch per kernel (the tri-modal model)
 # ------------------------------------------------------------------------------------------------------------------------
-GROUP_MAX_ROWS = 16384    # from here on a single pair fills the GPU and has the two-sided backward: issue the pairs one by one
+GROUP_MAX_ROWS = 8192     # measured (tools/bench_trimodal.py): 3.4x at N = 1024, 1.43x at 4096, 0.92x at 8192 against three pair steps
 
 
 class _GroupedClipLoss(torch.autograd.Function):
