@@ -942,7 +942,8 @@ bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resid
     if (e && atoi(e) != 0) return false;
   }
   static const bool ok = [] {
-    if (cudaFuncSetAttribute(pair2::bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT) != cudaSuccess) {
+    if (cudaFuncSetAttribute(pair2::bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(pair2::bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_LIMIT) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
@@ -951,12 +952,13 @@ bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resid
     cfg.gridDim = dim3(2 * pair_slots());
     cfg.blockDim = dim3(pair2::THREADS);
     cfg.dynamicSmemBytes = pair::SMEM_LIMIT;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, pair2::bwd2_kernel, &cfg) != cudaSuccess) {
+    int n = 0, n2 = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, pair2::bwd2_kernel<false>, &cfg) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n2, pair2::bwd2_kernel<true>, &cfg) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    return n >= pair_slots();
+    return n >= pair_slots() && n2 >= pair_slots();
   }();
   return ok;
 }
@@ -964,7 +966,10 @@ bool bwd2_device_ok() {   // every CTA pair of the persistent grid must be resid
 // world == 0: one GPU (n_rows == n_cols, every column segment stays local); world >= 2: row-sharded step, the rank's
 // n_rows = n_cols / world rows against all columns, one segment per owner rank.
 bool bwd2_plan(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale, int flags, int world, Bwd2Plan* pl) {
-  if (!tc_eligible(dtype, d, scale, flags) || !pair_eligible(d)) return false;
+  // family 1 (fixed shift) or family 2 with bounded logits (scales up to the clamp at 100); not the un-normalised queue
+  // columns (extra columns are not served at all: positives on the diagonal of a square / row-sharded batch only)
+  const int fam = tc_family(dtype, d, scale, flags);
+  if (!((fam == 1 || fam == 2) && pair_eligible(d)) || (flags & CLIPNCE_FLAG_UNBOUNDED)) return false;
   if (world == 1 || world < 0 || world > pair2::MAX_WORLD) return false;
   if (world == 0 ? n_rows != n_cols : n_rows * world != n_cols) return false;
   int64_t min_pairs = 16384ll * 16384ll;   // below this the items do not fill the producer pairs (CLIPNCE_BWD2_MIN_N: test hook)
@@ -1091,7 +1096,10 @@ int bwd2_launch(const Bwd2Plan& pl, const void* x, const void* y, const float* r
   if ((rc = make_tmap(&ty, y, d, n_cols, d, 128))) return rc;
   if ((rc = make_tmap(&tyg, y, d, n_cols, d, 64))) return rc;
   if ((rc = make_tmap(&tg, ws + pl.off_ring, 256, (int64_t)pl.depth * pl.P * 128, 256, 64))) return rc;
-  pair2::bwd2_kernel<<<2 * (pl.P + pl.Q), pair2::THREADS, pl.smem, st>>>(tx, ty, tyg, tg, p);
+  if (tc_family(CLIPNCE_BF16, d, scale, 0) == 2)
+    pair2::bwd2_kernel<true><<<2 * (pl.P + pl.Q), pair2::THREADS, pl.smem, st>>>(tx, ty, tyg, tg, p);
+  else
+    pair2::bwd2_kernel<false><<<2 * (pl.P + pl.Q), pair2::THREADS, pl.smem, st>>>(tx, ty, tyg, tg, p);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -57,7 +57,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int ROWS = 64;                     // resident rows per producer CTA (128 per pair)
 constexpr int X_CHUNK = ROWS * 128;          // [64 rows][64 k] bf16
 constexpr int G_BYTES = 4 * 8192;            // [64 i][256 j] bf16 = four K-major boxes
-constexpr int SMALL = 8192;                  // barriers (1000) | tmem ptr at +1016 | column vectors 2 x 3 x 256 f32 at +1024
+constexpr int SMALL = 10240;                 // barriers (1000) | tmem ptr at +1016 | column vectors 2 x 4 x 256 f32 at +1024
 constexpr int C_STAGE = 32768;               // consumer stage: A = 2 boxes G^T [64 i][64 j], B = 2 boxes X [64 i][64 d]
 constexpr int MAXS = 6;
 constexpr int RING_DEPTH = 16;               // steps of G tiles the ring holds
@@ -136,6 +136,10 @@ __device__ __forceinline__ Sub round_sub(const Params& p, int r, int k) {
   return s;
 }
 
+// TWO_EXP: the producers form G from the (shift, sum) pairs as they are -- exp(S - m_i) w_i + exp(S - m_j) w_j, two ex2 per
+// logit, every exponent <= 0 -- instead of the fixed shift's single exp(S - s) (u_i + v_j): kernel family 2, logit scales up
+// to the reference's clamp(max=100) (old/clip_opt.py:100, run1/full.py:76), as in pair::bwd_kernel<true>.
+template <bool TWO_EXP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 rows}     resident rows (K-major) / dY operand (MN-major)
             const __grid_constant__ CUtensorMap tmap_y,    // Y  box {64 k, 128 rows}  logits B operand, K-major
@@ -157,7 +161,7 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
   const uint32_t bars = base + body;
   auto bar = [&](int i) -> uint32_t { return bars + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + body + 1016);
-  float* const colv = reinterpret_cast<float*>(smem + body + 1024);   // [2][3][256]
+  float* const colv = reinterpret_cast<float*>(smem + body + 1024);   // [2][4][256]
 
   const float sc = p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale;
   const float k2 = sc * LOG2E;
@@ -410,7 +414,9 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
         const int t0 = seg * p.seg_steps;
         const int i_glob = (item % p.n_rb) * (2 * ROWS) + (int)rank * ROWS + i_local;
         const float rx = p.rinv_x[i_glob];
-        const float u = p.row_w[i_glob] * pair::ex2((sc - p.row_m[i_glob]) * LOG2E);
+        const float u = TWO_EXP ? 0.f : p.row_w[i_glob] * pair::ex2((sc - p.row_m[i_glob]) * LOG2E);
+        const float rm2 = TWO_EXP ? p.row_m[i_glob] * LOG2E : 0.f;
+        const float rw = TWO_EXP ? p.row_w[i_glob] : 0.f;
         const long long dcol = (long long)i_glob + p.diag_offset;   // column of this row's positive
         float cw_n, cm_n, ry_n;
         {
@@ -420,10 +426,11 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
 
         for (int t = t0; t < t0 + p.seg_steps; ++t, ++gs) {
           const int sb = s_buf(gs);
-          float* const cv = colv + (gs & 1) * 768;
+          float* const cv = colv + (gs & 1) * 1024;
           cv[te] = ry_n * k2;                                                   // S_ij log2(e) = acc * rinv_x[i] * cj
-          cv[256 + te] = cw_n * pair::ex2((sc - cm_n) * LOG2E) * ry_n;          // v_j / |y_j|
+          cv[256 + te] = (TWO_EXP ? cw_n : cw_n * pair::ex2((sc - cm_n) * LOG2E)) * ry_n;   // v_j / |y_j|  (TWO_EXP: w_j / |y_j|)
           cv[512 + te] = ry_n;
+          if (TWO_EXP) cv[768 + te] = cw_n > 0.f ? cm_n * LOG2E : 0.f;          // weight 0: keep the exponent finite
           if (t + 1 < t0 + p.seg_steps) {
             const long long jn = (long long)(t + 1) * STEP_J + te;
             cw_n = p.col_w[jn]; cm_n = p.col_m[jn]; ry_n = p.rinv_y[jn];
@@ -455,11 +462,23 @@ bwd2_kernel(const __grid_constant__ CUtensorMap tmap_x,    // X  box {64, 64 row
               const float vrv[4] = {vr4.x, vr4.y, vr4.z, vr4.w};
               const float ryv[4] = {ry4.x, ry4.y, ry4.z, ry4.w};
               float g[4];
+              if constexpr (TWO_EXP) {
+                const float4 cm4 = *reinterpret_cast<const float4*>(cjp + 768 + 4 * x4);
+                const float cmv[4] = {cm4.x, cm4.y, cm4.z, cm4.w};
 #pragma unroll
-              for (int xx = 0; xx < 4; ++xx) {
-                const float y = __uint_as_float(rr[4 * x4 + xx]) * rx;
-                const float ev = pair::ex2(fmaf(y, cjv[xx], -k2)) * rx;     // exp(S_ij - s) / |x_i|
-                g[xx] = ev * fmaf(u, ryv[xx], vrv[xx]);                       // (u_i + v_j) / |y_j|
+                for (int xx = 0; xx < 4; ++xx) {
+                  const float y = __uint_as_float(rr[4 * x4 + xx]) * rx;
+                  const float er = pair::ex2(fmaf(y, cjv[xx], -rm2)) * rw;    // exp(S_ij - m_i) w_i
+                  const float ec = pair::ex2(fmaf(y, cjv[xx], -cmv[xx]));     // exp(S_ij - m_j)
+                  g[xx] = rx * fmaf(er, ryv[xx], ec * vrv[xx]);                 // (...) / (|x_i| |y_j|)
+                }
+              } else {
+#pragma unroll
+                for (int xx = 0; xx < 4; ++xx) {
+                  const float y = __uint_as_float(rr[4 * x4 + xx]) * rx;
+                  const float ev = pair::ex2(fmaf(y, cjv[xx], -k2)) * rx;     // exp(S_ij - s) / |x_i|
+                  g[xx] = ev * fmaf(u, ryv[xx], vrv[xx]);                       // (u_i + v_j) / |y_j|
+                }
               }
               if (has_diag) {
 #pragma unroll

@@ -469,6 +469,34 @@ def test_two_sided_backward(monkeypatch, n, d, forced_p, seg):
     assert torch.equal(da2, da3) and torch.equal(db2, db3)
 
 
+@pytest.mark.parametrize("n,d,s,forced_p,seg", [(4096, 512, 100.0, 0, 0), (2048, 256, 60.0, 5, 1), (2048, 768, 100.0, 0, 0),
+                                                  (3072, 384, 100.0, 7, 2)])
+def test_two_sided_backward_large_scale(monkeypatch, n, d, s, forced_p, seg):
+    """The two-sided backward in kernel family 2 (bwd2_kernel<true>: exp(S - m_i) w_i + exp(S - m_j) w_j from the true
+    maxima of the online soft-max forward) -- the clamp(max=100) regime of old/clip_opt.py:100, run1/full.py:76 -- against
+    the float64 oracle and against the two-sweep family-2 path."""
+    from clip_dplm_b200.engine import CudaEngine
+    monkeypatch.setenv("CLIPNCE_BWD2_MIN_N", "256")
+    if forced_p:
+        monkeypatch.setenv("CLIPNCE_BWD2_P", str(forced_p))
+    if seg:
+        monkeypatch.setenv("CLIPNCE_BWD2_SEG", str(seg))
+    assert CudaEngine().backward_both_bytes(n, n, d, torch.bfloat16, s) > 0, "two-sided backward (family 2) not served"
+    a, b = O.make_inputs(n, d, seed=17, mix=0.12)
+    kw = dict(scale_is_log=False)
+    loss2, da2, db2, dt2 = run_fused(a, b, s, torch.bfloat16, **kw)
+    monkeypatch.setenv("CLIPNCE_NO_BWD2", "1")
+    loss1, da1, db1, dt1 = run_fused(a, b, s, torch.bfloat16, **kw)
+    monkeypatch.delenv("CLIPNCE_NO_BWD2")
+    ref = O.ref_step(a.double(), b.double(), s, **kw)
+    assert loss1 == loss2 and abs(loss2 - float(ref["loss"])) <= LOSS_RTOL_BF16 * abs(float(ref["loss"]))
+    assert rel(da2, ref["d_a"]) <= GRAD_RTOL_BF16 and rel(db2, ref["d_b"]) <= GRAD_RTOL_BF16
+    assert abs(dt2 - float(ref["d_logit_scale"])) <= GRAD_RTOL_BF16 * abs(float(ref["d_logit_scale"])) + 1e-7
+    assert rel(da2, da1) <= 5e-3 and rel(db2, db1) <= 5e-3
+    _, da3, db3, _ = run_fused(a, b, s, torch.bfloat16, **kw)
+    assert torch.equal(da2, da3) and torch.equal(db2, db3)
+
+
 # ------------------------------------------------------------------------------------------------
 # kernel family 2: tensor cores with true running maxima (s up to the clamp at 100, unbounded logits)
 # ------------------------------------------------------------------------------------------------
