@@ -73,12 +73,30 @@ SIGNATURES = {
 _RESTYPES = {"clipnce_last_error": ctypes.c_char_p}
 
 
+def _source_hash(files) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(files):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU)."""
+    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU).  The library is reused only when
+    the hash of its sources, recorded next to it at build time, still matches (file times do not survive a checkout or
+    the copy onto a GPU box); where nvcc is missing (a box that received a prebuilt library) the existing file is kept."""
+    import shutil
     src_files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
+    want = _source_hash(src_files)
+    stamp = LIB_PATH + ".srchash"
     if not force and os.path.exists(LIB_PATH):
-        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(f) for f in src_files):
+        have = open(stamp).read().strip() if os.path.exists(stamp) else None
+        if have == want or (have is None and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(f) for f in src_files)):
             return LIB_PATH
+        if shutil.which("nvcc") is None:
+            raise RuntimeError("clip_dplm_b200: libclipnce.so was built from different sources and nvcc is not available")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler",
            "-fPIC", "-shared", "-diag-suppress", "177", "-o", LIB_PATH, os.path.join(CSRC, "clipnce_api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -87,6 +105,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(res.stdout, res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libclipnce.so:\n" + res.stderr)
+    with open(stamp, "w") as fh:
+        fh.write(want + "\n")
     return LIB_PATH
 
 

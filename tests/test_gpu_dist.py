@@ -15,7 +15,7 @@ from oracle import ref_step as O
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, d, comm, q, both=False):
+def _worker(rank, world, port, n, d, comm, q, both=False, ls=O.LOGIT_SCALE_INIT, mix=0.5):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if both:
@@ -28,11 +28,11 @@ def _worker(rank, world, port, n, d, comm, q, both=False):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from clip_dplm_b200 import fused_clip_loss
-        a, b = O.make_inputs(n, d, seed=33)
+        a, b = O.make_inputs(n, d, seed=33, mix=mix)
         nl = n // world
         ac = a[rank * nl:(rank + 1) * nl].cuda().bfloat16().requires_grad_(True)
         bc = b[rank * nl:(rank + 1) * nl].cuda().bfloat16().requires_grad_(True)
-        t = torch.tensor(O.LOGIT_SCALE_INIT, device="cuda", requires_grad=True)
+        t = torch.tensor(ls, device="cuda", requires_grad=True)
         loss = fused_clip_loss(ac, bc, t, group=dist.group.WORLD)
         loss.backward()
         torch.cuda.synchronize()
@@ -40,7 +40,7 @@ def _worker(rank, world, port, n, d, comm, q, both=False):
         assert exchange.comm_kind(dist.group.WORLD) == comm
         if both:
             from clip_dplm_b200.engine import default_engine
-            assert default_engine().backward_both_bytes(nl, n, d, torch.bfloat16, 14.3, 0, world) > 0, "two-sided path not served"
+            assert default_engine().backward_both_bytes(nl, n, d, torch.bfloat16, math.exp(ls), 0, world) > 0, "two-sided path not served"
         q.put((rank, float(loss.detach()), ac.grad.float().cpu().numpy(), bc.grad.float().cpu().numpy(), float(t.grad)))
         exchange.reset()
     finally:
@@ -125,19 +125,21 @@ def _worker_topk_and_graph(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("n,d", [(1024, 256), (8192, 512)])
-def test_row_sharded_two_sided_backward(n, d):
+@pytest.mark.parametrize("n,d,ls,mix", [(1024, 256, O.LOGIT_SCALE_INIT, 0.5), (8192, 512, O.LOGIT_SCALE_INIT, 0.5),
+                                        (4096, 512, math.log(100.0), 0.12)])
+def test_row_sharded_two_sided_backward(n, d, ls, mix):
     """The row-sharded step through the two-sided kernel: local A rows x all columns in one sweep, dA finished locally,
     every owner's partial dB stored into its slot over NVLink peer memory (contraction + reduce-scatter), summed in fixed
     order -- against the sampled-row CPU oracle on the concatenated batch."""
     import numpy as np
     from oracle import sampled as SO
     world = 2
-    out = _run(_worker, (21700 + (os.getpid() % 2000), n, d, "link"), world, extra=(True,))
-    a, b = O.make_inputs(n, d, seed=33)
+    # the last case runs kernel family 2 (true maxima; the clamp(max=100) regime of old/clip_opt.py:100) row-sharded
+    out = _run(_worker, (21700 + (os.getpid() % 2000), n, d, "link"), world, extra=(True, ls, mix))
+    a, b = O.make_inputs(n, d, seed=33, mix=mix)
     rng = np.random.default_rng(n)
     rows = np.sort(rng.choice(n, 128, replace=False))
-    ref = SO.sampled_reference(a, b, math.exp(O.LOGIT_SCALE_INIT), rows, rows)
+    ref = SO.sampled_reference(a, b, math.exp(ls), rows, rows)
     da = np.concatenate([o[2] for o in out])
     db = np.concatenate([o[3] for o in out])
     for rank, loss, _, _, dt in out:
