@@ -311,7 +311,7 @@ int clipnce_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t d, int dtype
                                      (size_t)pair::MAX_SPLIT * (size_t)n_rows);
   if (pair_fwd > tc_fwd) tc_fwd = pair_fwd;
   const size_t online_fwd = sizeof(float) * 2 * (size_t)pair::MAX_SPLIT * (size_t)(n_rows + n_cols);   // (max, sum) partials, both launches
-  if (online_fwd > tc_fwd) tc_fwd = online_fwd;
+  tc_fwd = (pair_fwd > tc_fwd ? pair_fwd : tc_fwd) + online_fwd + 512;   // the speculative large-scale forward uses both regions + a flag
   SimtFwdWs w = simt_fwd_ws(nullptr, n_rows, n_cols);
   size_t simt_bwd = sizeof(float) * (size_t)ceil_div(n_rows, simt::TILE);
   size_t m = tc_fwd;
@@ -385,11 +385,53 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
   if (rc) return rc;
 
   if (tc_family(dtype, d, scale, flags) == 2) {
-    // online soft-max: row statistics of (x, y), then of (y, x) -- the column statistics -- with true running maxima
     if (!aligned16(x) || !aligned16(y)) return fail(CLIPNCE_EINVAL, "forward: operands must be 16-byte aligned");
     const int rows = d <= 512 ? 128 : 64;
     float* wsf = reinterpret_cast<float*>(workspace);
     size_t used = 0;
+    const int* gate = nullptr;
+    // Bounded logits (|S| <= s: normalised rows, any s up to the clamp at 100 and a little beyond).  The exact online
+    // sweeps below cost two passes over the logits.  Speculate instead: ONE fixed-shift sweep (the family-1 kernel) with
+    // the shift lowered to p = s - 72, so that e^(S - p) neither overflows (sums <= n e^72) nor -- for any row or column
+    // whose largest logit is above p - 62 = s - 134 -- loses mass to the terms that flush to zero (< n e^-87 in all,
+    // 1e-6 of a sum >= e^-62).  Rows / columns below that (a positive pair AND every negative with cosine < -0.34 at
+    // s = 100) raise a device flag in the reduction, and the exact sweeps run after all, gated on it: same results in
+    // every case, decided on the device (graph-capturable, no host read), one sweep in the common one.
+    const bool speculate = !(flags & CLIPNCE_FLAG_UNBOUNDED) && scale <= 105.f && n_cols <= (1ll << 22) && n_rows <= (1ll << 22) &&
+                           !getenv("CLIPNCE_NO_SPECULATE");
+    if (speculate) {
+      constexpr float kOff = 72.f;
+      // a sum of n terms loses less than n e^-87.3 to flushed terms: demand 1e6 times that (n = 65536: 1.1e-27 = e^-62)
+      const float thr_row = 1.2e-38f * 1e6f * (float)n_cols, thr_col = 1.2e-38f * 1e6f * (float)n_rows;
+      pair::FwdParams p;
+      memset(&p, 0, sizeof p);
+      p.n_rows = (int)n_rows; p.n_cols = (int)n_cols; p.d = (int)d;
+      p.nkc = (int)ceil_div(d, 64); p.n_steps = (int)ceil_div(n_cols, pair::STEP_J);
+      p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev;
+      p.rinv_x = rinv_x; p.rinv_y = rinv_y; p.diag = diag; p.shift_off = kOff;
+      p.n_pairs = (int)ceil_div(n_rows, 2 * rows);
+      p.split_steps = pick_split_steps(p.n_pairs, p.n_steps, pair::MAX_SPLIT);
+      const int n_split = (int)ceil_div(p.n_steps, p.split_steps);
+      p.col_ld = (long long)p.n_steps * pair::STEP_J;
+      const int n_part = 2 * p.n_pairs;
+      const size_t col_bytes = sizeof(float) * (size_t)n_part * (size_t)p.col_ld;
+      const size_t need = round_up(col_bytes + sizeof(float) * (size_t)n_split * (size_t)n_rows, 256) + 256;
+      if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
+      p.col_part = wsf;
+      p.row_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + col_bytes);
+      int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + need - 256);
+      CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      rc = rows == 128 ? launch_pair_fwd<128>(4, x, y, p, st) : launch_pair_fwd<64>(5, x, y, p, st);
+      if (rc) return rc;
+      aux::reduce_shifted_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, n_part, p.col_ld, n_cols, scale,
+                                                                                      scale_dev, kOff, thr_col, col_m, col_l, flag);
+      aux::reduce_shifted_partials<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(p.row_part, n_split, n_rows, n_rows, scale,
+                                                                                      scale_dev, kOff, thr_row, row_m, row_l, flag);
+      CUDA_TRY(cudaGetLastError());
+      gate = flag;
+      used = need;
+    }
+    // online soft-max: row statistics of (x, y), then of (y, x) -- the column statistics -- with true running maxima
     for (int side = 0; side < 2; ++side) {
       const int64_t nr = side == 0 ? n_rows : n_cols, nc = side == 0 ? n_cols : n_rows;
       pair::FwdParams p;
@@ -399,6 +441,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       p.diag_offset = diag_offset; p.scale = scale; p.scale_dev = scale_dev;
       p.rinv_x = side == 0 ? rinv_x : rinv_y; p.rinv_y = side == 0 ? rinv_y : rinv_x;
       p.diag = side == 0 ? diag : nullptr;
+      p.gate = gate;
       p.n_pairs = (int)ceil_div(nr, 2 * rows);
       p.split_steps = pick_split_steps(p.n_pairs, p.n_steps, pair::MAX_SPLIT);
       const int n_split = (int)ceil_div(p.n_steps, p.split_steps);
@@ -412,7 +455,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       rc = rows == 128 ? launch_pair_fwd<128, 2>(7, xs, ys, p, st) : launch_pair_fwd<64, 2>(11, xs, ys, p, st);
       if (rc) return rc;
       aux::reduce_ml_partials<<<(unsigned)ceil_div(nr, 256), 256, 0, st>>>(p.row_part_m, p.row_part, n_split, nr, nr,
-                                                                            side == 0 ? row_m : col_m, side == 0 ? row_l : col_l);
+                                                                            side == 0 ? row_m : col_m, side == 0 ? row_l : col_l, gate);
       CUDA_TRY(cudaGetLastError());
     }
     return 0;

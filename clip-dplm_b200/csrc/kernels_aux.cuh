@@ -166,9 +166,36 @@ __global__ void reduce_col_partials(const float* __restrict__ part, int n_part, 
   col_l[j] = acc;
 }
 
-// Combine (m,l) partial pairs: out over `n` entries, `n_part` partials with leading dimension ld.
+// Sums taken relative to the offset shift p = s - off (the speculative large-scale forward): l = sum_p part[p][j] in fixed
+// order, returned as an exactly rescaled pair (m = p + k ln 2, l 2^-k in [1, 2)) so that the soft-max weights coef / l of
+// the backward stay normal numbers whatever the magnitude of the sum (up to n e^off).  A sum below `thr` means the
+// entry's largest logit lies so far under the shift that terms were flushed to zero: *flag is raised and the exact
+// sweeps that follow (gated on it) replace the statistics.
+__global__ void reduce_shifted_partials(const float* __restrict__ part, int n_part, int64_t ld, int64_t n, float scale,
+                                        const float* __restrict__ scale_dev, float off, float thr, float* __restrict__ out_m,
+                                        float* __restrict__ out_l, int* __restrict__ flag) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);
+  float acc = 0.f;
+  for (int p = 0; p < n_part; ++p) acc += part[(int64_t)p * ld + j];
+  if (!(acc >= thr) || !(acc < INFINITY)) {
+    *flag = 1;                      // every writer stores the same value
+    out_m[j] = scale - off;
+    out_l[j] = acc;
+    return;
+  }
+  const int k = ilogbf(acc);
+  out_m[j] = fmaf((float)k, 0.6931471805599453f, scale - off);
+  out_l[j] = ldexpf(acc, -k);
+}
+
+// Combine (m,l) partial pairs: out over `n` entries, `n_part` partials with leading dimension ld.  gate: optional DEVICE
+// flag, the kernel does nothing while it is 0.
 __global__ void reduce_ml_partials(const float* __restrict__ pm, const float* __restrict__ pl, int n_part, int64_t ld,
-                                   int64_t n, float* __restrict__ out_m, float* __restrict__ out_l) {
+                                   int64_t n, float* __restrict__ out_m, float* __restrict__ out_l,
+                                   const int* __restrict__ gate = nullptr) {
+  if (gate != nullptr && __ldg(gate) == 0) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float M = -INFINITY;

@@ -512,6 +512,9 @@ struct FwdParams {
   long long col_offset;
   Group grp;          // MODE 0 / 2: several problems in one launch (n_prob = 0: one); the column-partial matrix then has
                       // 2 * pairs_per_prob rows (the problems own disjoint column ranges)
+  float shift_off;    // MODE 0: the sums are taken relative to the fixed shift s - shift_off (0: the plain fixed shift s)
+  const int* gate;    // optional DEVICE flag: the launch does nothing unless *gate != 0 (the exact fallback sweeps of the
+                      // speculative large-scale forward, clipnce_api.cu)
 };
 
 __host__ __device__ constexpr int fwd_smem_bytes(int rows, int nkc, int stages) {
@@ -554,6 +557,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
   const int t_end = min(gv.t_hi, t_begin + p.split_steps);
   // this CTA's row of the column-partial matrix
   const int col_row = 2 * (p.grp.n_prob ? (item % p.n_pairs) % p.grp.pairs_per_prob : item % p.n_pairs) + (int)rank;
+  if (p.gate != nullptr && __ldg(p.gate) == 0) return;   // uniform over the grid: before any barrier / TMEM allocation
   const float k2 = (p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale) * LOG2E;
 
   const uint32_t x_smem = base;
@@ -885,7 +889,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
       float* const cv = colv + (tl & 1) * 512;
       if (te < STEP_J) {
         cv[te] = ry_n < 0.f ? 0.f : ry_n * k2;
-        cv[256 + te] = ry_n < 0.f ? -10000.f : -k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
+        cv[256 + te] = ry_n < 0.f ? -10000.f : p.shift_off * LOG2E - k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
         const long long jn = (long long)(t + 1) * STEP_J + te;
         ry_n = (t + 1 < t_end && jn < gv.n_cols) ? p.rinv_y[jn + gv.ys] : -1.f;
       }

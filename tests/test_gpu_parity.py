@@ -525,3 +525,35 @@ def test_large_scale_and_unbounded_logits_on_tensor_cores(eng, n, m_extra, d, s,
     assert abs(loss - float(ref["loss"])) <= LOSS_RTOL_BF16 * abs(float(ref["loss"]))
     assert rel(da, ref["d_a"]) <= GRAD_RTOL_BF16 and rel(db, ref["d_b"]) <= GRAD_RTOL_BF16
     assert abs(dt - float(ref["d_logit_scale"])) <= GRAD_RTOL_BF16 * abs(float(ref["d_logit_scale"])) + 1e-7
+
+
+@pytest.mark.parametrize("flip", ["none", "rows", "cols"])
+@pytest.mark.parametrize("n,d", [(1024, 256), (1500, 512)])
+def test_speculative_large_scale_forward_and_its_exact_fallback(monkeypatch, n, d, flip):
+    """s = 100 (clamp regime, old/clip_opt.py:100): clipnce_forward runs ONE fixed-shift sweep with the shift lowered to
+    s - 72 and falls back to the exact online sweeps, on the device, when a row or column has every logit below s - 134.
+    `flip` builds such rows / columns (embeddings pointing away from everything, positive pair included); all three
+    cases must match the float64 oracle and the always-exact path (CLIPNCE_NO_SPECULATE=1)."""
+    g = torch.Generator().manual_seed(n + d)
+    v = torch.nn.functional.normalize(torch.randn(1, d, generator=g), dim=-1)
+    a = (v * 8.0 + 0.25 * torch.randn(n, d, generator=g)).bfloat16().float()
+    b = (v * 8.0 + 0.25 * torch.randn(n, d, generator=g)).bfloat16().float()
+    idx = [5, 77, n - 3]
+    if flip == "rows":
+        a[idx] = -a[idx]
+    elif flip == "cols":
+        b[idx] = -b[idx]
+    s = 100.0
+    kw = dict(scale_is_log=False)
+    ref = O.ref_step(a.double(), b.double(), s, **kw)
+    loss, da, db, dt = run_fused(a, b, s, torch.bfloat16, **kw)
+    monkeypatch.setenv("CLIPNCE_NO_SPECULATE", "1")
+    loss_x, da_x, db_x, dt_x = run_fused(a, b, s, torch.bfloat16, **kw)
+    monkeypatch.delenv("CLIPNCE_NO_SPECULATE")
+    assert abs(loss - float(ref["loss"])) <= LOSS_RTOL_BF16 * abs(float(ref["loss"]))
+    assert abs(loss - loss_x) <= 2e-5 * abs(loss_x)
+    assert rel(da, ref["d_a"]) <= GRAD_RTOL_BF16 and rel(db, ref["d_b"]) <= GRAD_RTOL_BF16
+    assert rel(da, da_x) <= 2e-3 and rel(db, db_x) <= 2e-3
+    assert abs(dt - float(ref["d_logit_scale"])) <= GRAD_RTOL_BF16 * abs(float(ref["d_logit_scale"])) + 1e-7
+    if flip != "none":    # the flipped entries decide the loss: it is ~ 2 s cos / n per entry, far from the unflipped value
+        assert float(ref["loss"]) > 0.05
