@@ -38,20 +38,28 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of this rank's GPU through NVML while the timed region runs."""
+    """Samples SM clock / throttle reasons of this rank's GPU through NVML while the timed region runs (NVML is initialised
+    before the region starts, one sample every 5 ms: the timed region of the default run is ~150 ms)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
-
-    def run(self):
+        self._nv = self._h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
-                     "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        nv, h = self._nv, self._h
+        if nv is None:
+            return
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        try:
             while not self._stop_evt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
@@ -61,9 +69,9 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.05)
-        except Exception as e:  # NVML missing: report that instead of inventing clocks
-            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+                time.sleep(0.005)
+        except Exception as e:
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
 
     def finish(self):
         self._stop_evt.set()

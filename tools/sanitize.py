@@ -35,9 +35,30 @@ one(1024, 128, 1 / 0.07, "two-sided backward")
 one(1024, 512, 1 / 0.07, "two-sided, 3 producers, 2 seg", CLIPNCE_BWD2_P="3", CLIPNCE_BWD2_SEG="2")
 one(512, 512, 1 / 0.07, "two-sweep backward", CLIPNCE_NO_BWD2="1")
 one(512, 256, 1 / 0.07, "two-sweep, split sweep", CLIPNCE_NO_BWD2="1", CLIPNCE_SPLIT_STEPS="1")
-one(512, 256, 100.0, "online max (family 2)")
+one(512, 256, 100.0, "family 2, speculative forward")
+one(512, 256, 100.0, "family 2, exact online sweeps", CLIPNCE_NO_SPECULATE="1")
+one(1024, 256, 100.0, "family 2, two-sided backward", CLIPNCE_BWD2_P="5")
+one(1024, 512, 1 / 0.07, "two-sweep, 4-CTA multicast", CLIPNCE_NO_BWD2="1", CLIPNCE_BWD_MC="1")
 one(300, 192, 10.0, "single-CTA tcgen05 kernels")
 one(200, 100, 10.0, "exact CUDA-core kernels")
+# grouped launch: three pairs over three embeddings (tri-modal model), ragged rows
+from clip_dplm_b200 import modules as M  # noqa: E402
+gg = torch.Generator().manual_seed(4)
+base = torch.randn(700, 256, generator=gg)
+embs = [(m * base + (1 - m) * torch.randn(700, 256, generator=gg)).bfloat16() for m in (1.0, 0.5, 0.3)]
+refs = [e.double().requires_grad_(True) for e in embs]
+rt = torch.tensor(2.6592, dtype=torch.float64)
+rl = O.ref_loss(refs[0], refs[1], rt) + O.ref_loss(refs[0], refs[2], rt) + O.ref_loss(refs[1], refs[2], rt)
+rl.backward()
+ce = [e.cuda().requires_grad_(True) for e in embs]
+out = M.trimodal_contrastive_losses(*ce, torch.tensor(2.6592, device="cuda"))
+out["loss"].backward()
+torch.cuda.synchronize()
+assert "embed_grad_sumsq" in out.grad_info, "grouped launch not taken"
+relg = lambda x, r: float((x.float().cpu().double() - r).norm() / r.norm())
+eg = [relg(c.grad, r.grad) for c, r in zip(ce, refs)]
+print(f"grouped tri-modal launch      n=700 d=256: loss rel {abs(float(out['loss']) - float(rl)) / float(rl):.1e} grads {eg[0]:.1e} {eg[1]:.1e} {eg[2]:.1e}", flush=True)
+assert abs(float(out["loss"]) - float(rl)) <= 1e-3 * float(rl) and max(eg) <= 2e-2
 g = torch.Generator().manual_seed(1)
 q, lib = torch.randn(300, 256, generator=g).bfloat16().cuda(), torch.randn(2000, 256, generator=g).bfloat16().cuda()
 s, i = topk_similarity(q, lib, 10)
