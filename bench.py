@@ -471,7 +471,27 @@ def run_ours(args, rank, local_rank, world):
     feeder = None
     if gstep is not None:
         from clip_dplm_b200.graph import HostFedClipStep
-        feeder = HostFedClipStep(inner=gstep)      # shares the already captured graph
+        feeder = None
+        if world > 1:
+            # row-sharded: a step captured as forward graph + backward graph, so that the next batch's H2D starts behind
+            # the forward (graph.GraphedClipStep.split) instead of beside the push / barrier phase of the step
+            try:
+                g2 = GraphedClipStep(n_local, d, group=group, engine=eng, split=True)
+                with torch.no_grad():
+                    g2.a.copy_(a)
+                    g2.b.copy_(b)
+                    g2.logit_scale.copy_(logit_scale.detach())
+                g2.recapture()
+                feeder = HostFedClipStep(inner=g2)
+            except Exception as e:
+                print(f"bench: split capture failed ({type(e).__name__}: {e}); e2e shares the one-graph step", file=sys.stderr)
+                feeder = None
+            okf = torch.tensor([1 if feeder is not None else 0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf) == 0:
+                feeder = None
+        if feeder is None:
+            feeder = HostFedClipStep(inner=gstep)      # shares the already captured graph
 
     def step_e2e_graph():
         # every step: this batch's embeddings come from pinned host memory (the transfer of the NEXT batch is started
@@ -484,6 +504,21 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(2):
         e2e_fn()
     ms_e2e = timed(e2e_fn, args.steps)
+    if args.timeline_e2e:
+        # kernel / copy timeline of four host-fed steps (CUPTI through torch.profiler), rank 0 writes it as text
+        from torch.profiler import profile, ProfilerActivity
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(4):
+                e2e_fn()
+            barrier()
+        if rank == 0:
+            evs = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+            evs.sort(key=lambda e: e.time_range.start)
+            t0 = evs[0].time_range.start if evs else 0
+            with open(args.timeline_e2e, "w") as f:
+                for e in evs:
+                    f.write(f"{(e.time_range.start - t0) / 1e3:10.3f} ms  {e.time_range.elapsed_us():9.1f} us  {e.name[:110]}\n")
 
     comm = "none"
     if world > 1:
@@ -589,6 +624,8 @@ def main():
     ap.add_argument("--parity-rows", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")
     ap.add_argument("--timeline", default=None, help="write a kernel timeline of three steps (torch.profiler) to this file")
+    ap.add_argument("--timeline-e2e", dest="timeline_e2e", default=None,
+                    help="write a kernel / copy timeline of four host-fed (e2e) steps to this file")
     ap.add_argument("--trace", action="store_true", help="print a per-phase device-time breakdown of the step to stderr")
     ap.add_argument("--comm", default="auto", choices=["auto", "link", "nccl"],
                     help="multi-GPU exchange: this repository's kernels over NVLink peer memory (link; the default where "

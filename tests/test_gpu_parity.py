@@ -289,9 +289,10 @@ def test_device_scale_and_graphed_step():
         assert torch.equal(l2.detach(), loss) and torch.equal(ar.grad, da) and torch.equal(br.grad, db)
 
 
-def test_host_fed_step_pipelines_batches():
+@pytest.mark.parametrize("split", [False, True])
+def test_host_fed_step_pipelines_batches(split):
     """HostFedClipStep: batches from pinned host memory, H2D of batch k+1 overlapped with step k; every step must
-    return the results of ITS batch."""
+    return the results of ITS batch.  split: forward and backward captured as two graphs, the H2D ordered behind the forward."""
     from clip_dplm_b200.graph import GraphedClipStep, HostFedClipStep
     n, d = 512, 128
     batches = []
@@ -299,7 +300,7 @@ def test_host_fed_step_pipelines_batches():
         a, b = O.make_inputs(n, d, seed=seed, mix=0.4)
         batches.append((a.bfloat16().pin_memory(), b.bfloat16().pin_memory()))
     ref_step = GraphedClipStep(n, d)
-    feeder = HostFedClipStep(n, d)
+    feeder = HostFedClipStep(n, d, split=split)
     feeder.prefetch(*batches[0])
     for k, (ah, bh) in enumerate(batches):
         loss, da, db, dt = feeder.step()
