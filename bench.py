@@ -276,6 +276,17 @@ def run_ours(args, rank, local_rank, world):
             self.launches += 1
             return super().finish_slots(*a, **k)
 
+        def group_forward(self, *a, **k):
+            # small batches: grouped launch -- sweep, two partial reductions, per-problem losses
+            self.launches += 4
+            return self._timed("fwd", super().group_forward, *a, **k)
+
+        def group_backward(self, *a, **k):
+            # soft-max weights, ONE sweep over both backward sides, finishing pass, scalar reduction
+            self.launches += 4
+            self.grouped = True
+            return self._timed("bwd2", super().group_backward, *a, **k)
+
         def backward_both_sharded_sweep(self, *a, **k):
             self.launches += 1          # the two-sided contraction + reduce-scatter kernel
             return self._timed("bwd2", super().backward_both_sharded_sweep, *a, **k)
@@ -585,7 +596,10 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "launch_mode": graph_note, "eager_ms_per_step": ms_eager / args.steps,
         "roofline": {"bound": "tensor",
-                     "kernel": ("pair2::bwd2_kernel (both backward sides in one sweep: logits recompute + dA and dB gradient GEMMs, "
+                     "kernel": ("pair::bwd_kernel, grouped launch (both backward sides of the pair as the two virtual problems of "
+                                "one sweep + finishing pass: small batches, algorithmic 4 N^2 d of 8 N^2 d executed)"
+                                if getattr(eng, "grouped", False) else
+                                "pair2::bwd2_kernel (both backward sides in one sweep: logits recompute + dA and dB gradient GEMMs, "
                                 "algorithmic 4 N^2 d of 6 N^2 d executed, cta_group::2)" if two_sided else
                                 "pair::bwd_kernel (one backward side: logits recompute + gradient GEMM, cta_group::2)"),
                      "achieved": achieved,

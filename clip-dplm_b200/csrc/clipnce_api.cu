@@ -779,7 +779,7 @@ int group_plan(int n_members, int n_prob, int64_t n, int64_t d, int dtype, float
   // true maxima -- (max, sum) row partials of both launches
   const size_t f1 = sizeof(float) * ((size_t)2 * pl->fwd_pairs + pair::MAX_SPLIT) * (size_t)pl->V;
   const size_t f2 = sizeof(float) * 4 * (size_t)pair::MAX_SPLIT * (size_t)pl->V;
-  pl->fwd_bytes = round_up(pl->fam == 2 ? f2 : f1, 256);
+  pl->fwd_bytes = round_up(pl->fam == 2 ? f1 + f2 + 1024 : f1, 256);   // family 2: the speculative sweep's partials + the exact sweeps'
   // backward: soft-max weights [2 V] | row-dot and |dx|^2 block partials | split slabs [n_split][2 V, d] f32 (<= 512 MiB)
   pl->n_blk = (int)ceil_div(pl->n_pad, 8);
   const size_t slab = sizeof(float) * 2 * (size_t)pl->V * (size_t)d;
@@ -849,7 +849,38 @@ int clipnce_group_forward(const void* stack, const float* rinv, int n_members, i
   p.grp.stack_rows = (int)(n_members * pl.n_pad);
   float* wsf = reinterpret_cast<float*>(workspace);
 
+  const int* gate = nullptr;
+  size_t exact_off = 0;   // floats: where the exact sweeps' partials start
+  if (pl.fam == 2 && scale <= 105.f && !getenv("CLIPNCE_NO_SPECULATE")) {
+    // bounded logits: one fixed-shift sweep with the shift lowered to s - 72, the exact sweeps gated on a device flag
+    // (see clipnce_forward)
+    constexpr float kOff = 72.f;
+    const float thr = 1.2e-38f * 1e6f * (float)n;
+    for (int k = 0; k < n_prob; ++k) {
+      p.grp.xshift[k] = (int)((x_member[k] - k) * pl.n_pad);
+      p.grp.yshift[k] = (int)((y_member[k] - k) * pl.n_pad);
+    }
+    p.diag = diag;
+    p.col_ld = V;
+    p.shift_off = kOff;
+    const int n_part = 2 * pl.fwd_pairs;
+    p.col_part = wsf;
+    p.row_part = wsf + (size_t)n_part * (size_t)V;
+    exact_off = (size_t)round_up((int64_t)(((size_t)n_part + (size_t)n_split) * (size_t)V), 64) + 64;
+    int* flag = reinterpret_cast<int*>(wsf + exact_off - 64);
+    CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    rc = pl.rows == 128 ? launch_pair_fwd<128>(4, stack, stack, p, st) : launch_pair_fwd<64>(5, stack, stack, p, st);
+    if (rc) return rc;
+    aux::reduce_shifted_partials<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(p.col_part, n_part, V, V, scale, scale_dev, kOff, thr,
+                                                                              stat_m + V, stat_l + V, flag, pl.n_pad, n);
+    aux::reduce_shifted_partials<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(p.row_part, n_split, V, V, scale, scale_dev, kOff, thr,
+                                                                              stat_m, stat_l, flag, pl.n_pad, n);
+    CUDA_TRY(cudaGetLastError());
+    p.shift_off = 0.f; p.col_part = nullptr; p.col_ld = 0;
+    gate = flag;
+  }
   if (pl.fam == 2) {   // true maxima: row statistics of (x, y), then of (y, x) = the column statistics
+    p.gate = gate;
     for (int side = 0; side < 2; ++side) {
       for (int k = 0; k < n_prob; ++k) {
         const int res = side == 0 ? x_member[k] : y_member[k], str = side == 0 ? y_member[k] : x_member[k];
@@ -857,12 +888,12 @@ int clipnce_group_forward(const void* stack, const float* rinv, int n_members, i
         p.grp.yshift[k] = (int)((str - k) * pl.n_pad);
       }
       p.diag = side == 0 ? diag : nullptr;
-      p.row_part_m = wsf + (size_t)side * 2 * (size_t)n_split * (size_t)V;
+      p.row_part_m = wsf + exact_off + (size_t)side * 2 * (size_t)n_split * (size_t)V;
       p.row_part = p.row_part_m + (size_t)n_split * (size_t)V;
       rc = pl.rows == 128 ? launch_pair_fwd<128, 2>(7, stack, stack, p, st) : launch_pair_fwd<64, 2>(11, stack, stack, p, st);
       if (rc) return rc;
       aux::reduce_ml_partials<<<(unsigned)ceil_div(V, 256), 256, 0, st>>>(p.row_part_m, p.row_part, n_split, V, V,
-                                                                           stat_m + side * V, stat_l + side * V);
+                                                                           stat_m + side * V, stat_l + side * V, gate);
       CUDA_TRY(cudaGetLastError());
     }
   } else {

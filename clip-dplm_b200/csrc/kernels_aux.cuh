@@ -171,16 +171,18 @@ __global__ void reduce_col_partials(const float* __restrict__ part, int n_part, 
 // the backward stay normal numbers whatever the magnitude of the sum (up to n e^off).  A sum below `thr` means the
 // entry's largest logit lies so far under the shift that terms were flushed to zero: *flag is raised and the exact
 // sweeps that follow (gated on it) replace the statistics.
+// n_pad > 0 (grouped launch): entry j belongs to a problem's padding when j % n_pad >= n_valid -- written, never flagged.
 __global__ void reduce_shifted_partials(const float* __restrict__ part, int n_part, int64_t ld, int64_t n, float scale,
                                         const float* __restrict__ scale_dev, float off, float thr, float* __restrict__ out_m,
-                                        float* __restrict__ out_l, int* __restrict__ flag) {
+                                        float* __restrict__ out_l, int* __restrict__ flag, int64_t n_pad = 0,
+                                        int64_t n_valid = 0) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   if (scale_dev != nullptr) scale = __ldg(scale_dev);
   float acc = 0.f;
   for (int p = 0; p < n_part; ++p) acc += part[(int64_t)p * ld + j];
   if (!(acc >= thr) || !(acc < INFINITY)) {
-    *flag = 1;                      // every writer stores the same value
+    if (n_pad == 0 || j % n_pad < n_valid) *flag = 1;   // every writer stores the same value
     out_m[j] = scale - off;
     out_l[j] = acc;
     return;

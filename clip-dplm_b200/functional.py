@@ -215,6 +215,19 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
     flags = 0
     if extra_cols is not None and not extra_normalized:
         flags |= _step.FLAG_UNBOUNDED
+    if (symmetric and extra_cols is None and group is None and not return_stats and compute_dtype == torch.bfloat16
+            and a.is_cuda and a.shape == b.shape and a.dtype == b.dtype and not _no_group()):
+        # small batches on one GPU (the reference trains at 32 ... 4096 rows): a pair's two backward sides are two sweeps of
+        # <= 32 row blocks each on a GPU with 74 CTA-pair slots.  The grouped launch runs them as the two
+        # virtual problems of ONE sweep, with one finishing pass -- taken where the two-sided kernel does not serve the shape
+        n, d = a.shape
+        probe = 14.0 if (torch.is_tensor(logit_scale) and logit_scale.is_cuda) else _scale_value(logit_scale, scale_is_log, clamp_max)[1]
+        both_bytes = getattr(engine, "backward_both_bytes", None)
+        if n < GROUP_MAX_ROWS and both_bytes is not None and both_bytes(n, n, d, torch.bfloat16, probe, 0) == 0:
+            losses = fused_clip_loss_group((a, b), (0,), (1,), logit_scale, scale_is_log=scale_is_log, clamp_max=clamp_max,
+                                           engine=engine, autocast_ok=True)
+            if losses is not None:
+                return losses[0]
     loss, row_lse, col_lse, diag = _FusedClipLoss.apply(a, b, logit_scale, extra_cols, symmetric, scale_is_log,
                                                         clamp_max, group, compute_dtype, flags, engine, bool(return_stats),
                                                         torch.is_grad_enabled(), bool(ddp),
@@ -228,6 +241,11 @@ def fused_clip_loss(a, b, logit_scale, *, symmetric: bool = True, scale_is_log: 
 # ------------------------------------------------------------------------------------------------------------------------
 # several pair problems over shared members in one launch per kernel (the tri-modal model)
 # ------------------------------------------------------------------------------------------------------------------------
+def _no_group():
+    import os
+    return os.environ.get("CLIPNCE_NO_GROUP", "0") not in ("", "0")     # A/B and test hook: pair steps only
+
+
 GROUP_MAX_ROWS = 8192     # measured (tools/bench_trimodal.py): 3.4x at N = 1024, 1.43x at 4096, 0.92x at 8192 against three pair steps
 
 
@@ -301,7 +319,7 @@ class _GroupedClipLoss(torch.autograd.Function):
 
 
 def fused_clip_loss_group(members, x_member, y_member, logit_scale, *, scale_is_log: bool = True,
-                          clamp_max: Optional[float] = None, holder=None, engine=None):
+                          clamp_max: Optional[float] = None, holder=None, engine=None, autocast_ok: bool = False):
     """Symmetric InfoNCE losses of several pairs over shared embeddings, one launch per kernel for the whole group.
 
     members     sequence of [N,d] CUDA embeddings of one dtype (bf16, or fp32/fp16 computed in bf16), un-normalised
@@ -320,7 +338,9 @@ def fused_clip_loss_group(members, x_member, y_member, logit_scale, *, scale_is_
         return None
     if m0.dtype not in (torch.bfloat16, torch.float32) or m0.shape[0] >= GROUP_MAX_ROWS:
         return None
-    if m0.dtype == torch.float32 and not torch.is_autocast_enabled():
+    if _no_group():
+        return None
+    if m0.dtype == torch.float32 and not (autocast_ok or torch.is_autocast_enabled()):
         return None     # fp32 rows outside autocast are computed exactly (the reference's numerics): no tensor-core group
     n, d = m0.shape
     if torch.is_tensor(logit_scale) and logit_scale.is_cuda:
