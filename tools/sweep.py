@@ -8,9 +8,9 @@ start-up sixteen times.  This tool pays it once:
         --configs 65536x512:link 65536x512:nccl 262144x512:link 32768x768:link --steps 20
 
 Every configuration is `bench.run_ours` unchanged: same timing rules, the same JSON line on rank 0's stdout, in the order
-of --configs (stderr carries a "# sweep: <config>" marker before each).  Not run on a GPU yet (written after the round's
-GPU budget was spent); it is a measurement convenience, not part of the product path.
-Format of a configuration:  <global batch>x<d>[:<comm>]   with comm in {auto, link, nccl}.
+of --configs (stderr carries a "# sweep: <config>" marker before each).  A measurement convenience, not part of the product path.
+Format of a configuration:  <global batch>x<d>[:<comm>[:s<scale>][:parity]]   with comm in {auto, link, nccl}; s<scale> sets
+exp(logit_scale) (s100: the clamp regime, weakly correlated pairs), `parity` runs the sampled-row oracle check on that line.
 """
 import argparse
 import os
@@ -43,9 +43,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         for cfg in args.configs:
-            shape, _, comm = cfg.partition(":")
+            parts = cfg.split(":")
+            shape, opts = parts[0], parts[1:]
             n, d = (int(v) for v in shape.lower().split("x"))
-            comm = comm or "auto"
+            comm, scale, parity = "auto", 1 / 0.07, False
+            for o in opts:
+                if o in ("auto", "link", "nccl"):
+                    comm = o
+                elif o == "parity":
+                    parity = True
+                elif o.startswith("s"):
+                    scale = float(o[1:])
+                elif o:
+                    raise SystemExit(f"sweep: unknown option '{o}' in '{cfg}'")
             if comm not in ("auto", "link", "nccl"):
                 raise SystemExit(f"sweep: unknown comm '{comm}' in '{cfg}'")
             if comm == "auto":
@@ -54,7 +64,9 @@ def main():
                 os.environ["CLIPNCE_COMM"] = comm
             exchange.reset()     # forget the previous configuration's buffers and its link/nccl decision
             ns = argparse.Namespace(gpus=world, steps=args.steps, warmup=args.warmup, impl="ours", n=n, d=d, ref_rows=1024,
-                                    no_cpu_baseline=True, no_graph=args.no_graph, timeline=None, trace=False, comm=comm)
+                                    no_cpu_baseline=True, no_graph=args.no_graph, timeline=None, timeline_e2e=None, trace=False,
+                                    comm=comm, scale=scale, mix=0.1 if scale > 50 else 0.5, no_parity=not parity,
+                                    parity_rows=256)
             if rank == 0:
                 print(f"# sweep: {cfg}", file=sys.stderr, flush=True)
             bench.run_ours(ns, rank, local_rank, world)
