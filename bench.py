@@ -483,9 +483,12 @@ def run_ours(args, rank, local_rank, world):
     if gstep is not None:
         from clip_dplm_b200.graph import HostFedClipStep
         feeder = None
-        if world > 1:
+        e2e_split = os.environ.get("CLIPNCE_E2E_SPLIT", "auto")
+        if (world >= 4 and e2e_split != "0") or (world > 1 and e2e_split == "1"):
             # row-sharded: a step captured as forward graph + backward graph, so that the next batch's H2D starts behind
-            # the forward (graph.GraphedClipStep.split) instead of beside the push / barrier phase of the step
+            # the forward (graph.GraphedClipStep.split) instead of beside the push / barrier phase of the step.  Measured:
+            # pays from 4 GPUs on (e2e gap 4.5 % -> 2.5 %); on 2 GPUs the 64 MB transfer beside the backward sweep costs
+            # more than the stretched barriers did (gap -2 % -> 5 %)
             try:
                 g2 = GraphedClipStep(n_local, d, group=group, engine=eng, split=True)
                 with torch.no_grad():

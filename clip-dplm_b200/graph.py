@@ -153,7 +153,10 @@ class HostFedClipStep:
     def __init__(self, n_local: Optional[int] = None, d: Optional[int] = None, *, inner: Optional[GraphedClipStep] = None,
                  **kw):
         if inner is None and kw.get("group") is not None:
-            kw.setdefault("split", True)      # row-sharded: keep the H2D away from the exchange phase (GraphedClipStep.split)
+            # row-sharded over 4+ ranks: keep the H2D away from the exchange phase (GraphedClipStep.split); with fewer
+            # ranks the per-rank transfer is large and is better hidden beside the forward (measured)
+            import torch.distributed as dist
+            kw.setdefault("split", dist.get_world_size(kw["group"]) >= 4)
         self.inner = inner if inner is not None else GraphedClipStep(n_local, d, **kw)
         dev = self.inner.device
         self.stage = [(torch.empty_like(self.inner.a), torch.empty_like(self.inner.b)) for _ in range(2)]

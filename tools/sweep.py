@@ -47,11 +47,14 @@ def main():
             shape, opts = parts[0], parts[1:]
             n, d = (int(v) for v in shape.lower().split("x"))
             comm, scale, parity = "auto", 1 / 0.07, False
+            os.environ.pop("CLIPNCE_E2E_SPLIT", None)
             for o in opts:
                 if o in ("auto", "link", "nccl"):
                     comm = o
                 elif o == "parity":
                     parity = True
+                elif o in ("split", "nosplit"):     # host-fed (e2e) step as forward graph + backward graph, or as one graph
+                    os.environ["CLIPNCE_E2E_SPLIT"] = "1" if o == "split" else "0"
                 elif o.startswith("s"):
                     scale = float(o[1:])
                 elif o:
