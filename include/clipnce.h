@@ -53,8 +53,12 @@ const char* clipnce_last_error(void);
 /* Kernel family serving (dtype, d, scale, flags):
  *   0  exact CUDA-core kernels (dtype F32, d % 8 != 0, d > 768, CLIPNCE_FLAG_FORCE_EXACT);
  *   1  tcgen05 tensor-core kernels with the fixed shift exp(S - s)   (2 * scale <= 80 and |S| <= s);
- *   2  tcgen05 kernels with true running maxima (online soft-max forward, two-exponential backward): larger scales --
- *      exp().clamp(max=100), old/clip_opt.py:100 -- and CLIPNCE_FLAG_UNBOUNDED; d % 128 == 0. */
+ *   2  tcgen05 kernels with per-row / per-column shifts (two-exponential backward): larger scales -- exp().clamp(max=100),
+ *      old/clip_opt.py:100 -- and CLIPNCE_FLAG_UNBOUNDED; d % 128 == 0.  With bounded logits (no CLIPNCE_FLAG_UNBOUNDED)
+ *      clipnce_forward first runs ONE fixed-shift sweep with the shift lowered to s - 72 and returns its sums as exactly
+ *      rescaled (shift, sum) pairs; a row or column whose every logit lies below s - 134 raises a device flag, and the
+ *      exact online soft-max sweeps enqueued behind it (true running maxima, one launch for the rows, one for the columns)
+ *      run only then: the results are the same in every case, the common one costs a single sweep, nothing reads the host. */
 int clipnce_uses_tensor_cores(int dtype, int64_t d, float scale, int flags);
 
 /* 1 if clipnce_backward needs the transposed copy y_t for these arguments.  The CTA-pair kernels (d % 128 == 0,
