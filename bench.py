@@ -328,6 +328,18 @@ def run_ours(args, rank, local_rank, world):
             self.launches += 1
             return super().link_barrier(*a, **k)
 
+        def forward_gathered(self, *a, **k):
+            self.launches += 3          # contraction kernel + the two partial reductions (the gather runs beside it)
+            return self._timed("fwd", super().forward_gathered, *a, **k)
+
+        def link_epoch_advance(self, *a, **k):
+            self.launches += 1
+            return super().link_epoch_advance(*a, **k)
+
+        def link_send_blocks(self, rows, rinv, peers, world, *a, **k):
+            self.launches += world - 1  # copy-engine transfers + one flag kernel per peer
+            return super().link_send_blocks(rows, rinv, peers, world, *a, **k)
+
         def link_copy(self, *a, **k):      # copy engines: no kernel launch
             return super().link_copy(*a, **k)
 

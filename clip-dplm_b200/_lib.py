@@ -65,6 +65,11 @@ SIGNATURES = {
     "clipnce_link_barrier": [ctypes.POINTER(_vp), _int, _int, _int, _vp],
     "clipnce_link_push_rows": [_vp, _int, _i64, _i64, _int, ctypes.POINTER(_vp), _int, _int, _i64, _i64, _i64, _int, _vp],
     "clipnce_link_copy": [_vp, _sz, ctypes.POINTER(_vp), _int, _int, _i64, _vp],
+    "clipnce_link_epoch_advance": [ctypes.POINTER(_vp), _int, _int, _int, _vp],
+    "clipnce_link_send_blocks": [_vp, _sz, _vp, _sz, ctypes.POINTER(_vp), _int, _int, _i64, _i64, _int, _vp],
+    "clipnce_forward_gathered_ok": [_int, _i64, _f32, _int],
+    "clipnce_forward_gathered": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp,
+                                 ctypes.POINTER(_vp), _int, _int, _int, _vp, _sz, _vp],
     "clipnce_link_push_f32": [ctypes.POINTER(_vp), ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, ctypes.POINTER(_vp),
                               _int, _int, _vp],
     "clipnce_link_sum_scalars": [_vp, _int, ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp],
@@ -125,7 +130,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError here == header/library mismatch
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if lib.clipnce_version() != 107:
+        if lib.clipnce_version() != 108:
             raise RuntimeError("clip_dplm_b200: libclipnce.so version mismatch; rebuild")
         _lib = lib
         return lib

@@ -41,6 +41,15 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(CLIPNCE_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));     \
   } while (0)
 
+// a peer that does not arrive within this time is fatal (barriers and per-block waits trap)
+unsigned long long link_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* e = getenv("CLIPNCE_LINK_TIMEOUT_MS");
+    const long long ms = e ? atoll(e) : 600000;   // 10 minutes, the order of NCCL's watchdog; a timeout is fatal (trap)
+    return (unsigned long long)(ms > 0 ? ms : 600000) * 1000000ull;
+  }();
+  return ns;
+}
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
@@ -369,11 +378,31 @@ int clipnce_stage_operand(const void* x, int in_dtype, int64_t n, int64_t d, voi
   return 0;
 }
 
-int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
-                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* scale_dev, int dtype,
-                    int flags, float* row_m,
-                    float* row_l, float* col_m, float* col_l, float* diag, void* workspace, size_t workspace_bytes,
-                    void* stream) {
+}  // extern "C"
+
+namespace {
+// the gather of the columns runs beside the sweep (clipnce_forward_gathered): where the flags live and how the columns
+// map to source ranks
+struct Gathered {
+  const uint32_t* flags = nullptr;
+  const uint32_t* epoch = nullptr;
+  int world = 0, rank = 0;
+};
+void set_gathered(pair::FwdParams& p, const Gathered* g) {
+  if (!g || !g->flags) return;
+  p.src_flags = g->flags;
+  p.src_epoch = g->epoch;
+  p.steps_per_src = p.n_steps / g->world;
+  p.rot_steps = g->rank * p.steps_per_src;
+  p.self_src = g->rank;
+  p.wait_timeout_ns = link_timeout_ns();
+}
+
+int forward_impl(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                 int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* scale_dev, int dtype,
+                 int flags, float* row_m,
+                 float* row_l, float* col_m, float* col_l, float* diag, void* workspace, size_t workspace_bytes,
+                 void* stream, const Gathered* gat) {
   if (!x || !y || !rinv_x || !rinv_y || !row_m || !row_l || !col_m || !col_l || !diag || !workspace)
     return fail(CLIPNCE_EINVAL, "forward: null pointer");
   if (n_rows < 1 || n_cols < 1 || d < 1 || n_rows > (1ll << 30) || n_cols > (1ll << 30))
@@ -421,6 +450,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       p.row_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + col_bytes);
       int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + need - 256);
       CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      set_gathered(p, gat);
       rc = rows == 128 ? launch_pair_fwd<128>(4, x, y, p, st) : launch_pair_fwd<64>(5, x, y, p, st);
       if (rc) return rc;
       aux::reduce_shifted_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, n_part, p.col_ld, n_cols, scale,
@@ -481,6 +511,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
       if (workspace_bytes < need) return fail(CLIPNCE_EWORKSPACE, "forward: workspace %zu < %zu", workspace_bytes, need);
       p.col_part = reinterpret_cast<float*>(workspace);
       p.row_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + col_bytes);
+      set_gathered(p, gat);
       rc = rows == 128 ? launch_pair_fwd<128>(4, x, y, p, st) : launch_pair_fwd<64>(5, x, y, p, st);
       if (rc) return rc;
       aux::reduce_col_partials<<<(unsigned)ceil_div(n_cols, 256), 256, 0, st>>>(p.col_part, n_part, p.col_ld, n_cols, scale,
@@ -534,6 +565,44 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
                                                                              n_cols, col_m, col_l);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int clipnce_forward(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                    int64_t n_cols, int64_t d, int64_t diag_offset, float scale, const float* scale_dev, int dtype,
+                    int flags, float* row_m, float* row_l, float* col_m, float* col_l, float* diag, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return forward_impl(x, y, rinv_x, rinv_y, n_rows, n_cols, d, diag_offset, scale, scale_dev, dtype, flags, row_m, row_l, col_m,
+                      col_l, diag, workspace, workspace_bytes, stream, nullptr);
+}
+
+int clipnce_forward_gathered_ok(int dtype, int64_t d, float scale, int flags) {
+  const int fam = tc_family(dtype, d, scale, flags);
+  if (fam == 1) return pair_eligible(d) ? 1 : 0;
+  return (fam == 2 && !(flags & CLIPNCE_FLAG_UNBOUNDED) && scale <= 105.f && !getenv("CLIPNCE_NO_SPECULATE")) ? 1 : 0;
+}
+
+int clipnce_forward_gathered(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                             int64_t n_cols, int64_t d, float scale, const float* scale_dev, int dtype, int flags,
+                             float* row_m, float* row_l, float* col_m, float* col_l, float* diag, void* const* peer_base,
+                             int world, int rank, int phase, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!peer_base || world < 2 || world > link::MAX_WORLD || rank < 0 || rank >= world || phase < 0 || phase >= link::MAX_PHASE)
+    return fail(CLIPNCE_EINVAL, "forward_gathered: bad peers / phase");
+  if (n_cols != n_rows * world || n_rows % pair::STEP_J != 0)
+    return fail(CLIPNCE_EUNSUPPORTED, "forward_gathered: n_cols must be world * n_rows, n_rows a multiple of 256");
+  if (!clipnce_forward_gathered_ok(dtype, d, scale, flags))
+    return fail(CLIPNCE_EUNSUPPORTED, "forward_gathered: kernel family without a fixed-shift sweep (use clipnce_link_barrier + clipnce_forward)");
+  if (!peer_base[rank]) return fail(CLIPNCE_EINVAL, "forward_gathered: null peer buffer");
+  Gathered g;
+  const char* mine = reinterpret_cast<const char*>(peer_base[rank]);
+  g.flags = reinterpret_cast<const uint32_t*>(mine + link::OFF_FLAGS) + phase * link::MAX_WORLD;
+  g.epoch = reinterpret_cast<const uint32_t*>(mine + link::OFF_EPOCH) + phase;
+  g.world = world;
+  g.rank = rank;
+  return forward_impl(x, y, rinv_x, rinv_y, n_rows, n_cols, d, (int64_t)rank * n_rows, scale, scale_dev, dtype, flags, row_m,
+                      row_l, col_m, col_l, diag, workspace, workspace_bytes, stream, &g);
 }
 
 }  // extern "C"
@@ -1498,14 +1567,6 @@ int make_peers(void* const* peer_base, int world, int rank, link::Peers* out) {
   }
   return 0;
 }
-unsigned long long link_timeout_ns() {
-  static const unsigned long long ns = [] {
-    const char* e = getenv("CLIPNCE_LINK_TIMEOUT_MS");
-    const long long ms = e ? atoll(e) : 600000;   // 10 minutes, the order of NCCL's watchdog; a timeout is fatal (trap)
-    return (unsigned long long)(ms > 0 ? ms : 600000) * 1000000ull;
-  }();
-  return ns;
-}
 }  // namespace
 
 int clipnce_link_control_bytes(int64_t* control_bytes, int64_t* status_offset) {
@@ -1571,6 +1632,37 @@ int clipnce_link_copy(const void* src, size_t bytes, void* const* peer_base, int
   for (int k = 1; k <= world; ++k) {   // start behind the own rank: the ranks' copies fan out over different peers
     const int r = (rank + k) % world;
     CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(peers.base[r]) + dst_offset, src, bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int clipnce_link_epoch_advance(void* const* peer_base, int world, int rank, int phase, void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, rank, &peers);
+  if (rc) return rc;
+  if (phase < 0 || phase >= link::MAX_PHASE) return fail(CLIPNCE_EINVAL, "link_epoch_advance: bad phase %d", phase);
+  link::epoch_advance<<<1, 32, 0, as_stream(stream)>>>(peers, rank, phase);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int clipnce_link_send_blocks(const void* rows, size_t row_bytes, const float* rinv, size_t rinv_bytes, void* const* peer_base,
+                             int world, int rank, int64_t rows_offset, int64_t rinv_offset, int phase, void* stream) {
+  link::Peers peers;
+  int rc = make_peers(peer_base, world, rank, &peers);
+  if (rc) return rc;
+  if (!rows || !rinv || row_bytes < 1 || rinv_bytes < 1 || rows_offset < link::CONTROL_BYTES || rinv_offset < link::CONTROL_BYTES)
+    return fail(CLIPNCE_EINVAL, "link_send_blocks: bad argument");
+  if (phase < 0 || phase >= link::MAX_PHASE) return fail(CLIPNCE_EINVAL, "link_send_blocks: bad phase %d", phase);
+  cudaStream_t st = as_stream(stream);
+  // rank r sweeps the blocks in the order r, r + 1, r + 2, ...: send first to the rank that needs this block first
+  for (int k = 1; k < world; ++k) {
+    const int dst = (rank - k + world) % world;
+    char* base = reinterpret_cast<char*>(peers.base[dst]);
+    CUDA_TRY(cudaMemcpyAsync(base + rows_offset, rows, row_bytes, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + rinv_offset, rinv, rinv_bytes, cudaMemcpyDeviceToDevice, st));
+    link::signal<<<1, 32, 0, st>>>(peers, rank, dst, phase);
+    CUDA_TRY(cudaGetLastError());
   }
   return 0;
 }

@@ -94,6 +94,21 @@ __device__ __forceinline__ uint32_t barrier_arrive_wait(const Peers& peers, int 
   return e;
 }
 
+// The two halves of a barrier for data that is CONSUMED BLOCK BY BLOCK (the gather of the columns beside the forward sweep,
+// clipnce_link_send_blocks / clipnce_forward_gathered): `epoch_advance` opens phase `phase` of a new step on this GPU,
+// `signal` tells ONE peer that this rank's block has landed in its buffer (enqueued behind the copy that delivered it);
+// the consumer kernel waits for flags[phase][src] >= epoch[phase] before it touches block src.
+__global__ void epoch_advance(Peers peers, int rank, int phase) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) at<uint32_t>(peers.base[rank], OFF_EPOCH)[phase] += 1u;
+}
+__global__ void signal(Peers peers, int rank, int dst, int phase) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const uint32_t e = at<uint32_t>(peers.base[rank], OFF_EPOCH)[phase];
+    __threadfence_system();
+    st_release_sys(at<uint32_t>(peers.base[dst], OFF_FLAGS) + phase * MAX_WORLD + rank, e);
+  }
+}
+
 __global__ void barrier(Peers peers, int world, int rank, int phase, unsigned long long timeout_ns) {
   __shared__ uint32_t epoch_sh;
   barrier_arrive_wait(peers, world, rank, phase, timeout_ns, &epoch_sh);

@@ -512,10 +512,30 @@ struct FwdParams {
   long long col_offset;
   Group grp;          // MODE 0 / 2: several problems in one launch (n_prob = 0: one); the column-partial matrix then has
                       // 2 * pairs_per_prob rows (the problems own disjoint column ranges)
+  // Row-sharded step with the gather of the columns running BESIDE this sweep (MODE 0, clipnce_forward_gathered): the
+  // columns are the row blocks of `n_src` ranks, steps_per_src steps each; the copy engines of the peers deliver them
+  // while the sweep runs and raise src_flags[q] (>= *src_epoch) behind block q.  The sweep visits the steps ROTATED by
+  // rot_steps -- the local block first, then the blocks in the order the peers send them -- and waits for a block's
+  // flag before its first TMA load / rinv read.  src_flags = nullptr: everything is there, no rotation.
+  const uint32_t* src_flags;
+  const uint32_t* src_epoch;
+  int rot_steps, steps_per_src, self_src;
+  unsigned long long wait_timeout_ns;
   float shift_off;    // MODE 0: the sums are taken relative to the fixed shift s - shift_off (0: the plain fixed shift s)
   const int* gate;    // optional DEVICE flag: the launch does nothing unless *gate != 0 (the exact fallback sweeps of the
                       // speculative large-scale forward, clipnce_api.cu)
 };
+
+// wait until the peer that owns source block `src` has delivered it (see FwdParams::src_flags); bounded: a lost rank traps
+__device__ __forceinline__ void wait_src_block(const uint32_t* flags, uint32_t epoch, int src, unsigned long long timeout_ns) {
+  const uint32_t* f = flags + src;
+  if ((int32_t)(ptx::ld_acquire_sys(f) - epoch) >= 0) return;
+  const unsigned long long t0 = ptx::globaltimer_ns();
+  while ((int32_t)(ptx::ld_acquire_sys(f) - epoch) < 0) {
+    __nanosleep(100);
+    if (ptx::globaltimer_ns() - t0 > timeout_ns) __trap();
+  }
+}
 
 __host__ __device__ constexpr int fwd_smem_bytes(int rows, int nkc, int stages) {
   return nkc * rows * 128 + stages * STAGE_BYTES + FWD_SMALL;
@@ -559,6 +579,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
   const int col_row = 2 * (p.grp.n_prob ? (item % p.n_pairs) % p.grp.pairs_per_prob : item % p.n_pairs) + (int)rank;
   if (p.gate != nullptr && __ldg(p.gate) == 0) return;   // uniform over the grid: before any barrier / TMEM allocation
   const float k2 = (p.scale_dev != nullptr ? __ldg(p.scale_dev) : p.scale) * LOG2E;
+  // loop steps are ROTATED steps; act() gives the step's place in the column order of the operands and statistics
+  const bool gathered = p.src_flags != nullptr;
+  const uint32_t src_epoch = gathered ? __ldg(p.src_epoch) : 0u;
+  auto act = [&](int t) -> int {
+    if (!gathered) return t;
+    const int ta = t + p.rot_steps;
+    return ta >= p.n_steps ? ta - p.n_steps : ta;
+  };
 
   const uint32_t x_smem = base;
   const uint32_t ring_a = x_smem + p.nkc * X_CHUNK;
@@ -601,12 +629,24 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         ptx::tma_load_2d_pair(x_smem + kc * X_CHUNK, &tmap_x, bar(B_XFULL), kc * 64, i0 + gv.xs);
       int stage = 0;
       uint32_t phase = 0;
+      int cur_src = p.self_src;
       for (int t = t_begin; t < t_end; ++t) {
+        const int ta = act(t);
+        if (gathered) {
+          const int src = ta / p.steps_per_src;
+          if (src != cur_src) {   // first tile of a block another rank delivers: its flag, then generic -> async proxy
+            if (src != p.self_src) {
+              wait_src_block(p.src_flags, src_epoch, src, p.wait_timeout_ns);
+              ptx::fence_proxy_async_all();
+            }
+            cur_src = src;
+          }
+        }
         for (int g = 0; g < p.nkc; ++g) {
           ptx::mbar_wait(bar(B_EMPTY_A + stage), phase ^ 1u);
           if (leader) ptx::mbar_arrive_expect_tx(bar(B_FULL_A + stage), 2 * STAGE_BYTES);
           ptx::tma_load_2d_pair(ring_a + stage * STAGE_BYTES, &tmap_y, bar(B_FULL_A + stage), g * 64,
-                                t * STEP_J + (int)rank * 128 + gv.ys);
+                                ta * STEP_J + (int)rank * 128 + gv.ys);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -874,24 +914,35 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
         const float* cr = colred + ((t - t_begin) & 1) * 1024 + te;
         float s = cr[0] + cr[256];
         if (NSLOT == 4) s = (s + cr[512]) + cr[768];
-        p.col_part[(long long)col_row * p.col_ld + (long long)t * STEP_J + te] = s;
+        p.col_part[(long long)col_row * p.col_ld + (long long)act(t) * STEP_J + te] = s;
       }
+    };
+    // 1/norm of the columns of (rotated) step t; gathered: a block's values are read only behind its owner's flag
+    int cur_src = p.self_src;
+    auto load_ry = [&](int t) -> float {
+      const int ta = act(t);
+      if (gathered) {
+        const int src = ta / p.steps_per_src;
+        if (src != cur_src) {
+          if (src != p.self_src) wait_src_block(p.src_flags, src_epoch, src, p.wait_timeout_ns);
+          cur_src = src;
+        }
+      }
+      const long long j = (long long)ta * STEP_J + te;
+      return (j < gv.n_cols) ? p.rinv_y[j + gv.ys] : -1.f;   // -1 marks a column past the end
     };
 
     float ry_n = 0.f;
-    if (te < STEP_J) {   // -1 marks a column past the end
-      const long long j = (long long)t_begin * STEP_J + te;
-      ry_n = (j < gv.n_cols) ? p.rinv_y[j + gv.ys] : -1.f;
-    }
+    if (te < STEP_J) ry_n = load_ry(t_begin);
     for (int t = t_begin; t < t_end; ++t) {
       const int tl = t - t_begin;
       const int sb = tl & 1;
+      const int ta = act(t);
       float* const cv = colv + (tl & 1) * 512;
       if (te < STEP_J) {
         cv[te] = ry_n < 0.f ? 0.f : ry_n * k2;
         cv[256 + te] = ry_n < 0.f ? -10000.f : p.shift_off * LOG2E - k2;   // invalid column: exp2(-10000) = 0 leaves every sum untouched
-        const long long jn = (long long)(t + 1) * STEP_J + te;
-        ry_n = (t + 1 < t_end && jn < gv.n_cols) ? p.rinv_y[jn + gv.ys] : -1.f;
+        ry_n = t + 1 < t_end ? load_ry(t + 1) : -1.f;
       }
       named_bar_sync(1, EPI_THREADS);
       if (t > t_begin) flush_cols(t - 1);
@@ -909,7 +960,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,   // X box {64 k, ROWS ro
           if (lane == 0) ptx::mbar_arrive_cluster(sempty_leader + 8u * sb);
         }
         const float* const cjp = cv + jl0 + 32 * c;
-        const long long dl = dcol0 - ((long long)t * STEP_J + jl0 + 32 * c);
+        const long long dl = dcol0 - ((long long)ta * STEP_J + jl0 + 32 * c);
         if (row_ok && dl >= 0 && dl < 32) {
 #pragma unroll
           for (int x = 0; x < 32; ++x)

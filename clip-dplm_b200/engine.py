@@ -410,6 +410,42 @@ class CudaEngine:
         _lib.check(self.lib.clipnce_link_copy(_p(src), src.numel() * src.element_size(), peers, world, rank, dst_off,
                                               _stream()), "link_copy")
 
+    def forward_gathered_ok(self, dtype, d, scale, flags=0):
+        return bool(self.lib.clipnce_forward_gathered_ok(_DT[dtype], d, float(scale), flags))
+
+    def link_epoch_advance(self, peers, world, rank, phase):
+        _lib.check(self.lib.clipnce_link_epoch_advance(peers, world, rank, phase, _stream()), "link_epoch_advance")
+
+    @_guard
+    def link_send_blocks(self, rows, rinv, peers, world, rank, rows_off, rinv_off, phase):
+        """Copy-engine delivery of this rank's rows / 1-norms to every peer, each followed by a flag (enqueue on a side
+        stream behind `link_epoch_advance`)."""
+        self._chk(rows, (torch.bfloat16, torch.float32), "rows")
+        self._chk(rinv, (torch.float32,), "rinv")
+        _lib.check(self.lib.clipnce_link_send_blocks(_p(rows), rows.numel() * rows.element_size(), _p(rinv), rinv.numel() * 4,
+                                                     peers, world, rank, int(rows_off), int(rinv_off), phase, _stream()),
+                   "link_send_blocks")
+
+    @_guard
+    def forward_gathered(self, x, y, rinv_x, rinv_y, scale, peers, world, rank, phase, flags=0, scale_dev=None):
+        """`forward` over the gathered columns while their blocks are still arriving (clipnce_forward_gathered)."""
+        self._chk(x, (torch.bfloat16,), "x")
+        self._chk(y, (x.dtype,), "y")
+        n_rows, d = x.shape
+        n_cols = y.shape[0]
+        dev = x.device
+        ws = self.workspace(n_rows, n_cols, d, x.dtype, flags, dev)
+        row_m = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        col_m = torch.empty(n_cols, dtype=torch.float32, device=dev)
+        col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
+        diag = torch.empty(n_rows, dtype=torch.float32, device=dev)
+        _lib.check(self.lib.clipnce_forward_gathered(_p(x), _p(y), _p(rinv_x), _p(rinv_y), n_rows, n_cols, d, float(scale),
+                                                     _p(scale_dev), _DT[x.dtype], flags, _p(row_m), _p(row_l), _p(col_m),
+                                                     _p(col_l), _p(diag), peers, world, rank, phase, _p(ws), ws.numel(),
+                                                     _stream()), "forward_gathered")
+        return row_m, row_l, col_m, col_l, diag
+
     def link_push_f32(self, srcs, dst_offs, peers, world, rank):
         k = len(srcs)
         for t in srcs:

@@ -26,7 +26,14 @@ import warnings
 import torch
 import torch.distributed as dist
 
-PHASE_COLS, PHASE_STATS, PHASE_LOSS, PHASE_CLOSE, PHASE_GRADS = 0, 1, 2, 3, 4
+PHASE_COLS, PHASE_STATS, PHASE_LOSS, PHASE_CLOSE, PHASE_GRADS, PHASE_BLOCKS = 0, 1, 2, 3, 4, 5
+# The B rows travel BESIDE the forward sweep (copy engines + per-block flags, PeerExchange.gather_cols_beside) where the
+# forward kernel can wait block by block; CLIPNCE_GATHER_BESIDE=0 keeps the push kernel + barrier in front of the sweep.
+GATHER_BESIDE = os.environ.get("CLIPNCE_GATHER_BESIDE", "1") not in ("", "0")
+# ... and where the sweep is long enough to hide the delivery chain (world - 1 blocks, each two copy-engine transfers and a
+# flag kernel, ~25 us per block): measured on 8 GPUs, 8192 local rows x 65536 columns x 512 gain 4.4 % of the step, 4096
+# local rows x 32768 x 768 (a 190 us sweep) lose 8 %
+GATHER_BESIDE_MIN_ROWS = int(os.environ.get("CLIPNCE_GATHER_BESIDE_MIN_ROWS", "8192"))
 # The A rows travel beside the forward sweep.  Every SM a push kernel takes costs the sweep a CTA-pair slot and -- its grid
 # being sized in whole waves of slots -- part of an extra wave (a full-grid push: 365 -> 435 us on 8 GPUs; 8 fat blocks:
 # +20 us on 8 GPUs, +80 us on 2 and 4), so by default the copy engines move them (CLIPNCE_LINK_BG=kernel for the push kernel
@@ -179,6 +186,24 @@ class PeerExchange:
         e.link_push_rows(b, compute_dtype, self.peers, self.world, self.rank, self.o_y, self.o_rinv_y, lo)
         e.link_barrier(self.peers, self.world, self.rank, PHASE_COLS)
         return self.y[lo:lo + self.n], self.rinv_y[lo:lo + self.n], self.y, self.rinv_y
+
+    def gather_cols_beside(self, b, rinv_b):
+        """The gather of the columns for `engine.forward_gathered`: own block copied locally, every peer's copy of it
+        delivered by the copy engines on the side stream, flagged block by block.  b [n,d] in the compute type."""
+        e, lo = self.engine, self.rank * self.n
+        esz = b.element_size()
+        if rinv_b is None:
+            rinv_b, _ = e.normalize(b)
+        self.y[lo:lo + self.n].copy_(b, non_blocking=True)
+        self.rinv_y[lo:lo + self.n].copy_(rinv_b, non_blocking=True)
+        e.link_epoch_advance(self.peers, self.world, self.rank, PHASE_BLOCKS)
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            e.link_send_blocks(b, rinv_b, self.peers, self.world, self.rank, self.o_y + lo * self.d * esz,
+                               self.o_rinv_y + lo * 4, PHASE_BLOCKS)
+        self._side_busy = True              # joined before the step's next barrier (exchange_stats)
+        return b, rinv_b, self.y, self.rinv_y
 
     def gather_rows_begin(self, a, a_c, rinv_a, compute_dtype):
         cur = torch.cuda.current_stream()

@@ -83,6 +83,7 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
 
     xchg = None
     both_sharded = False
+    beside = False
     # rinv_a / rinv_b: 1/norms that came with the rows (the fused projection-head tail, heads.py): nothing to recompute
     if rinv_a is None:
         rinv_a, _ = engine.normalize(a)
@@ -91,10 +92,19 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
         # the exchange buffers do not depend on the number of extra columns (a hard-negative cache that grows from step
         # to step would otherwise need a new set -- a host-side rendezvous -- for every length)
         xchg = _exchange.open_exchange(engine, group, n_local, d, n_global, compute_dtype, a.device)
-        b_c, rinv_b, y, rinv_y = xchg.gather_cols(b, compute_dtype)
+        if callable(scale):
+            scale = scale()
+        # the gather runs BESIDE the forward sweep where the sweep can wait block by block (include/clipnce.h,
+        # clipnce_forward_gathered): every rank decides from the same shapes, types and scale hint
+        beside = bool(_exchange.GATHER_BESIDE and getattr(xchg, "kind", "") == "nvlink-peer" and extra is None
+                      and b.dtype == compute_dtype == torch.bfloat16 and n_local % 256 == 0
+                      and n_local >= _exchange.GATHER_BESIDE_MIN_ROWS
+                      and hasattr(engine, "forward_gathered") and engine.forward_gathered_ok(compute_dtype, d, scale, flags))
+        if beside:
+            b_c, rinv_b, y, rinv_y = xchg.gather_cols_beside(b.contiguous(), rinv_b)
+        else:
+            b_c, rinv_b, y, rinv_y = xchg.gather_cols(b, compute_dtype)
         if need_grad:
-            if callable(scale):
-                scale = scale()
             # two-sided backward over peer memory (one sweep emits dA and the reduce-scattered dB): nothing to gather
             both_sharded = bool(symmetric and extra is None and compute_dtype == torch.bfloat16 and
                                 getattr(xchg, "kind", "") == "nvlink-peer" and hasattr(engine, "backward_both_sharded") and
@@ -118,7 +128,11 @@ def contrastive_forward(engine, a, b, scale, *, symmetric=True, extra=None, grou
         _, y_t = engine.stage(y, compute_dtype, want_t=True)
 
     kw = {"scale_dev": scale_dev} if scale_dev is not None else {}
-    row_m, row_l, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags, **kw)
+    if beside:
+        row_m, row_l, col_m, col_l, diag = engine.forward_gathered(a_c, y, rinv_a, rinv_y, scale, xchg.peers, xchg.world,
+                                                                   xchg.rank, _exchange.PHASE_BLOCKS, flags, **kw)
+    else:
+        row_m, row_l, col_m, col_l, diag = engine.forward(a_c, y, rinv_a, rinv_y, diag_offset, scale, flags, **kw)
     xa, rinv_xa, row_m_all, row_l_all = a_c, rinv_a, row_m, row_l
     if world > 1:
         fixed = getattr(engine, "fixed_shift", None)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CLIPNCE_VERSION 107
+#define CLIPNCE_VERSION 108
 
 /* element types */
 #define CLIPNCE_BF16 0
@@ -364,6 +364,31 @@ int clipnce_link_push_rows(const void* x, int in_dtype, int64_t n, int64_t d, in
  * the backward only -- which keeps every SM.  Publish with a barrier on a stream that waited for this one. */
 int clipnce_link_copy(const void* src, size_t bytes, void* const* peer_base, int world, int rank, int64_t dst_offset,
                       void* stream);
+
+/*
+ * The gather of the columns BESIDE the forward sweep (replaces clipnce_link_push_rows + clipnce_link_barrier before
+ * clipnce_forward; the reference's dist.all_gather is a blocking call in front of its matmul, old/clip_opt.py:102-112):
+ *   clipnce_link_epoch_advance   opens phase `phase` of a new step on this GPU (one tiny kernel on the step's stream);
+ *   clipnce_link_send_blocks     on a SIDE stream that waited for it: the copy engines deliver this rank's rows
+ *                                (row_bytes at rows_offset) and 1/norms (rinv_bytes at rinv_offset) to every peer, the peer
+ *                                that sweeps this block first served first, each delivery followed by a flag for that peer.
+ *                                The caller copies its own block into its own buffer itself (on the step's stream);
+ *   clipnce_forward_gathered     clipnce_forward over x = the local rows and y = the gathered buffer [world * n_rows, d]
+ *                                (rinv_y likewise), diag_offset = rank * n_rows, sweeping the column blocks in the order
+ *                                rank, rank + 1, ... and waiting for a block's flag before its first load -- the sweep
+ *                                starts on the local block at once and the transfers hide behind it.  Served where
+ *                                clipnce_forward_gathered_ok() says so (the CTA-pair kernels with a fixed-shift sweep:
+ *                                family 1, and family 2 with bounded logits); otherwise gather with push_rows + barrier.
+ * All ranks must take the same route in a step.  The side stream must be joined before the step's next barrier.
+ */
+int clipnce_link_epoch_advance(void* const* peer_base, int world, int rank, int phase, void* stream);
+int clipnce_link_send_blocks(const void* rows, size_t row_bytes, const float* rinv, size_t rinv_bytes, void* const* peer_base,
+                             int world, int rank, int64_t rows_offset, int64_t rinv_offset, int phase, void* stream);
+int clipnce_forward_gathered_ok(int dtype, int64_t d, float scale, int flags);
+int clipnce_forward_gathered(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
+                             int64_t n_cols, int64_t d, float scale, const float* scale_dev, int dtype, int flags,
+                             float* row_m, float* row_l, float* col_m, float* col_l, float* diag, void* const* peer_base,
+                             int world, int rank, int phase, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Copy n_seg (<= 4) local f32 vectors src[k][0..n[k]) to byte offset dst_offset[k] of every rank's buffer
  * (the statistics exchange after the forward sweep).  src, n, dst_offset are HOST arrays.  Publish with a barrier. */

@@ -20,6 +20,9 @@ def _worker(rank, world, port, n, d, comm, q, both=False, ls=O.LOGIT_SCALE_INIT,
     os.environ["MASTER_PORT"] = str(port)
     if both:
         os.environ["CLIPNCE_BWD2_MIN_N"] = "256"    # serve the small test shape with the two-sided kernel
+        # ... and gather the columns BESIDE the forward sweep (copy engines + per-block flags, clipnce_forward_gathered),
+        # which by default starts at 8192 local rows; the other tests keep the push kernel + barrier in front of the sweep
+        os.environ["CLIPNCE_GATHER_BESIDE_MIN_ROWS"] = "256"
     else:
         os.environ["CLIPNCE_NO_BWD2"] = "1"
     os.environ.setdefault("CLIPNCE_LINK_TIMEOUT_MS", "30000")   # a lost rank fails the test in 30 s, not in 10 min
