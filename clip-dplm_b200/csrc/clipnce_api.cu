@@ -419,15 +419,18 @@ int forward_impl(const void* x, const void* y, const float* rinv_x, const float*
     float* wsf = reinterpret_cast<float*>(workspace);
     size_t used = 0;
     const int* gate = nullptr;
-    // Bounded logits (|S| <= s: normalised rows, any s up to the clamp at 100 and a little beyond).  The exact online
+    // Bounded logits (|S| <= s: normalised rows; the clamp at 100 of old/clip_opt.py:100 is the case that matters).  The exact online
     // sweeps below cost two passes over the logits.  Speculate instead: ONE fixed-shift sweep (the family-1 kernel) with
     // the shift lowered to p = s - 72, so that e^(S - p) neither overflows (sums <= n e^72) nor -- for any row or column
     // whose largest logit is above p - 62 = s - 134 -- loses mass to the terms that flush to zero (< n e^-87 in all,
     // 1e-6 of a sum >= e^-62).  Rows / columns below that (a positive pair AND every negative with cosine < -0.34 at
     // s = 100) raise a device flag in the reduction, and the exact sweeps run after all, gated on it: same results in
     // every case, decided on the device (graph-capturable, no host read), one sweep in the common one.
-    const bool speculate = !(flags & CLIPNCE_FLAG_UNBOUNDED) && scale <= 105.f && n_cols <= (1ll << 22) && n_rows <= (1ll << 22) &&
+    // (any scale: beyond ~105 more rows fall under the bound and the fallback runs more often, the results stay exact;
+    // the decision must not depend on the scale -- ranks of a row-sharded step hold slightly different host copies of it)
+    const bool speculate = !(flags & CLIPNCE_FLAG_UNBOUNDED) && n_cols <= (1ll << 22) && n_rows <= (1ll << 22) &&
                            !getenv("CLIPNCE_NO_SPECULATE");
+    if (gat && !speculate) return fail(CLIPNCE_EUNSUPPORTED, "forward_gathered: no fixed-shift sweep for these arguments");
     if (speculate) {
       constexpr float kOff = 72.f;
       // a sum of n terms loses less than n e^-87.3 to flushed terms: demand 1e6 times that (n = 65536: 1.1e-27 = e^-62)
@@ -581,7 +584,7 @@ int clipnce_forward(const void* x, const void* y, const float* rinv_x, const flo
 int clipnce_forward_gathered_ok(int dtype, int64_t d, float scale, int flags) {
   const int fam = tc_family(dtype, d, scale, flags);
   if (fam == 1) return pair_eligible(d) ? 1 : 0;
-  return (fam == 2 && !(flags & CLIPNCE_FLAG_UNBOUNDED) && scale <= 105.f && !getenv("CLIPNCE_NO_SPECULATE")) ? 1 : 0;
+  return (fam == 2 && !(flags & CLIPNCE_FLAG_UNBOUNDED) && !getenv("CLIPNCE_NO_SPECULATE")) ? 1 : 0;
 }
 
 int clipnce_forward_gathered(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n_rows,
@@ -590,8 +593,8 @@ int clipnce_forward_gathered(const void* x, const void* y, const float* rinv_x, 
                              int world, int rank, int phase, void* workspace, size_t workspace_bytes, void* stream) {
   if (!peer_base || world < 2 || world > link::MAX_WORLD || rank < 0 || rank >= world || phase < 0 || phase >= link::MAX_PHASE)
     return fail(CLIPNCE_EINVAL, "forward_gathered: bad peers / phase");
-  if (n_cols != n_rows * world || n_rows % pair::STEP_J != 0)
-    return fail(CLIPNCE_EUNSUPPORTED, "forward_gathered: n_cols must be world * n_rows, n_rows a multiple of 256");
+  if (n_cols != n_rows * world || n_rows % pair::STEP_J != 0 || n_cols > (1ll << 22))
+    return fail(CLIPNCE_EUNSUPPORTED, "forward_gathered: n_cols must be world * n_rows <= 2^22, n_rows a multiple of 256");
   if (!clipnce_forward_gathered_ok(dtype, d, scale, flags))
     return fail(CLIPNCE_EUNSUPPORTED, "forward_gathered: kernel family without a fixed-shift sweep (use clipnce_link_barrier + clipnce_forward)");
   if (!peer_base[rank]) return fail(CLIPNCE_EINVAL, "forward_gathered: null peer buffer");
@@ -920,7 +923,7 @@ int clipnce_group_forward(const void* stack, const float* rinv, int n_members, i
 
   const int* gate = nullptr;
   size_t exact_off = 0;   // floats: where the exact sweeps' partials start
-  if (pl.fam == 2 && scale <= 105.f && !getenv("CLIPNCE_NO_SPECULATE")) {
+  if (pl.fam == 2 && !getenv("CLIPNCE_NO_SPECULATE")) {
     // bounded logits: one fixed-shift sweep with the shift lowered to s - 72, the exact sweeps gated on a device flag
     // (see clipnce_forward)
     constexpr float kOff = 72.f;

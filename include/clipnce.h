@@ -378,7 +378,8 @@ int clipnce_link_copy(const void* src, size_t bytes, void* const* peer_base, int
  *                                rank, rank + 1, ... and waiting for a block's flag before its first load -- the sweep
  *                                starts on the local block at once and the transfers hide behind it.  Served where
  *                                clipnce_forward_gathered_ok() says so (the CTA-pair kernels with a fixed-shift sweep:
- *                                family 1, and family 2 with bounded logits); otherwise gather with push_rows + barrier.
+ *                                family 1, and family 2 with bounded logits -- a function of type, d and flags only,
+ *                                so that every rank of a step answers alike); otherwise gather with push_rows + barrier.
  * All ranks must take the same route in a step.  The side stream must be joined before the step's next barrier.
  */
 int clipnce_link_epoch_advance(void* const* peer_base, int world, int rank, int phase, void* stream);
