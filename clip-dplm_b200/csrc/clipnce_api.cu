@@ -1118,7 +1118,9 @@ bool bwd2_plan(int64_t n_rows, int64_t n_cols, int64_t d, int dtype, float scale
   if (!((fam == 1 || fam == 2) && pair_eligible(d)) || (flags & CLIPNCE_FLAG_UNBOUNDED)) return false;
   if (world == 1 || world < 0 || world > pair2::MAX_WORLD) return false;
   if (world == 0 ? n_rows != n_cols : n_rows * world != n_cols) return false;
-  int64_t min_pairs = 16384ll * 16384ll;   // below this the items do not fill the producer pairs (CLIPNCE_BWD2_MIN_N: test hook)
+  // below this the items do not fill the producer pairs; measured on one GPU, d = 512 (tools/run_bwd2_threshold.sh): 12288 rows
+  // 0.571 ms per step against 0.692 with two sweeps, 8192 rows 0.329 against 0.307 (CLIPNCE_BWD2_MIN_N: test hook)
+  int64_t min_pairs = 12288ll * 12288ll;
   if (const char* e = getenv("CLIPNCE_BWD2_MIN_N")) min_pairs = atoll(e) * atoll(e);
   if (n_rows % 128 != 0 || n_cols % 256 != 0 || n_rows * n_cols < min_pairs || n_cols > (1ll << 22)) return false;
   if (world >= 2 && (n_cols / world) % 256 != 0) return false;

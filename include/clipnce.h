@@ -182,7 +182,7 @@ int clipnce_backward_dx(const void* x, const void* y, const void* y_t, int64_t l
  * d_scale_sum [1] += sum_ij G_ij S_ij (or NULL).
  * clipnce_backward_both_workspace_bytes() returns 0 bytes in *out when the shape is not served (then use two
  * clipnce_backward_dx calls): bf16, kernel family 1 or 2 without CLIPNCE_FLAG_UNBOUNDED, d in {128,...,768}, n_rows % 128 == 0,
- * n_cols % 256 == 0, n_rows * n_cols >= 16384^2, and a device on which all CTA pairs of the persistent grid are
+ * n_cols % 256 == 0, n_rows * n_cols >= 12288^2, and a device on which all CTA pairs of the persistent grid are
  * co-resident.  world = 0: one GPU (n_rows == n_cols); world >= 2: the row-sharded step below.  CLIPNCE_NO_BWD2=1
  * disables the path.
  */
