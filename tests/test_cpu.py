@@ -107,6 +107,53 @@ def test_host_only_entry_points():
     assert lib.clipnce_uses_tensor_cores(_lib.BF16, 512, 14.3, _lib.FLAG_FORCE_EXACT) == 0
 
 
+def test_group_and_gathered_host_entry_points():
+    """Host-side answers of the entry points added for the grouped launch (tri-modal model, small batches) and for the
+    gather beside the forward sweep: which shapes are served, argument validation -- no GPU involved."""
+    from clip_dplm_b200 import _lib
+    lib = _lib.load()
+    nb = ctypes.c_size_t(7)
+    # three pairs over three members, N = 4096, d = 512: served by both tensor-core families
+    for s in (14.3, 100.0):
+        assert lib.clipnce_group_workspace_bytes(3, 3, 4096, 512, _lib.BF16, s, 0, ctypes.byref(nb)) == 0
+        assert nb.value >= 6 * 4096 * 512 * 4              # one split's gradient slabs of the six backward sides
+    # not served: fp32 (check mode), d % 128 != 0, un-normalised columns -> 0 bytes, the caller issues the pairs one by one
+    for dt, d, fl in ((_lib.F32, 512, 0), (_lib.BF16, 192, 0), (_lib.BF16, 512, _lib.FLAG_UNBOUNDED)):
+        assert lib.clipnce_group_workspace_bytes(3, 3, 4096, d, dt, 14.3, fl, ctypes.byref(nb)) == 0 and nb.value == 0
+    assert lib.clipnce_group_workspace_bytes(5, 3, 4096, 512, _lib.BF16, 14.3, 0, ctypes.byref(nb)) == -1   # > 4 members
+    assert lib.clipnce_group_workspace_bytes(3, 5, 4096, 512, _lib.BF16, 14.3, 0, ctypes.byref(nb)) == -1   # > 4 problems
+    # the gathered forward is a function of type, d and flags only (every rank of a step must answer alike)
+    assert lib.clipnce_forward_gathered_ok(_lib.BF16, 512, 14.3, 0) == 1
+    assert lib.clipnce_forward_gathered_ok(_lib.BF16, 512, 100.0, 0) == 1
+    assert lib.clipnce_forward_gathered_ok(_lib.BF16, 512, 500.0, 0) == 1
+    assert lib.clipnce_forward_gathered_ok(_lib.BF16, 512, 14.3, _lib.FLAG_UNBOUNDED) == 0
+    assert lib.clipnce_forward_gathered_ok(_lib.BF16, 192, 14.3, 0) == 0
+    assert lib.clipnce_forward_gathered_ok(_lib.F32, 512, 14.3, 0) == 0
+    # the two-sided backward answers 0 bytes below 12288 rows (host-only part of the plan; the device check comes after)
+    assert lib.clipnce_backward_both_workspace_bytes(8192, 8192, 512, _lib.BF16, 14.3, 0, 0, ctypes.byref(nb)) == 0 and nb.value == 0
+
+
+def test_grouped_loss_declines_what_it_does_not_serve():
+    """functional.fused_clip_loss_group returns None (the caller then issues pair steps) for CPU tensors, mixed shapes,
+    and when CLIPNCE_NO_GROUP is set -- it never falls back to a CPU computation."""
+    from clip_dplm_b200.functional import fused_clip_loss_group
+    a, b = O.make_inputs(16, 64)
+    assert fused_clip_loss_group((a, b), (0,), (1,), 2.0) is None
+    assert fused_clip_loss_group((a, b[:8]), (0,), (1,), 2.0) is None
+
+
+def test_source_hash_of_the_build_changes_with_the_sources(tmp_path):
+    from clip_dplm_b200 import _lib
+    f1, f2 = tmp_path / "a.cu", tmp_path / "b.cuh"
+    f1.write_text("int x;")
+    f2.write_text("int y;")
+    h0 = _lib._source_hash([str(f1), str(f2)])
+    assert h0 == _lib._source_hash([str(f2), str(f1)])      # order of discovery does not matter
+    f2.write_text("int y; ")
+    assert _lib._source_hash([str(f1), str(f2)]) != h0
+    assert os.path.exists(_lib.LIB_PATH + ".srchash") or os.path.exists(_lib.LIB_PATH)
+
+
 def test_product_path_refuses_cpu_tensors():
     from clip_dplm_b200 import fused_clip_loss
     a, b = O.make_inputs(16, 64)
